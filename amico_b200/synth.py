@@ -1,0 +1,495 @@
+"""Synthetic protocols, dictionaries and volumes for the per-voxel fit.
+
+Host-side tooling (numpy/scipy) used by the tests and by ``bench.py``: nothing
+here is on the product path.  It builds inputs in exactly the layouts the
+reference hands to ``model.fit(evaluation)``:
+
+* ``Scheme``         -- the attributes of ``amico/scheme.py:21-154`` the path reads
+                        (``b``, ``b0_idx``, ``dwi_idx``, ``dwi_count``, ``nS``, ``shells``);
+* ``lut_directions`` / ``build_htable`` -- a half-sphere direction set and the
+                        181x181 one-degree hash table with the semantics of
+                        ``amico/directions/htable_ndirs=*.bin`` (nearest LUT
+                        direction by |dot|; checked against the reference's own
+                        500-direction table in ``tests/test_synth.py``);
+* ``make_kernels``   -- the ``KERNELS`` dict of each model's ``resample``
+                        (``amico/models.pyx:754-792, 1113-1144, 482-523, 1446-1486``);
+* ``make_voxels``    -- ``y`` (float32-valued, >= 0) and unit ``DIRs``.
+
+The compartment signals are the standard closed forms (stick / zeppelin /
+ball, Watson-dispersed NODDI sticks with tortuosity, Van Gelderen cylinder,
+Murday-Cotts sphere, astrosticks).  Every anisotropic atom is a zonal function
+of ``t = g . d`` per shell; as in the reference it is band-limited to even
+Legendre orders <= 12 before being sampled on the subject's gradients (the
+reference does this through an lmax=12 SH fit, ``amico/lut.pyx:227-311``; the
+m=0 coefficients it keeps are exactly a Legendre series).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+
+import numpy as np
+from numpy.polynomial import legendre as npleg
+from scipy import optimize, special
+
+GAMMA = 2.675987e8  # proton gyromagnetic ratio [rad/(s T)]
+LMAX = 12
+
+CONFIGS = {
+    # id: (model, volume dims, description)
+    1: ("FreeWater", (8, 8, 8)),
+    2: ("NODDI", (128, 128, 64)),
+    3: ("NODDI", (256, 256, 160)),
+    4: ("SANDI", (128, 128, 128)),
+    5: ("CylinderZeppelinBall", (200, 200, 200)),
+}
+
+
+# --------------------------------------------------------------------------- scheme
+class Scheme:
+    """Acquisition scheme: Nx4 (dir, b) or Nx7 (dir, G, Delta, delta, TE) table.
+
+    Mirrors the attributes of ``amico/scheme.py:50-135`` consumed downstream.
+    """
+
+    def __init__(self, raw, b0_thr=0.0):
+        raw = np.array(raw, dtype=np.float64)
+        if raw.ndim != 2 or raw.shape[1] not in (4, 7):
+            raise ValueError("Unrecognized scheme format")
+        self.raw = raw
+        if raw.shape[1] == 4:
+            self.version = 0
+            self.b = raw[:, 3].copy()
+        else:
+            self.version = 1
+            self.b = (GAMMA * raw[:, 3] * raw[:, 5]) ** 2 * (raw[:, 4] - raw[:, 5] / 3.0) * 1e-6
+        self.b0_thr = b0_thr
+        self.b0_idx = np.where(self.b <= b0_thr)[0]
+        self.b0_count = len(self.b0_idx)
+        self.dwi_idx = np.where(self.b > b0_thr)[0]
+        self.dwi_count = len(self.dwi_idx)
+        flip = self.raw[:, 1] < 0
+        self.raw[flip, 0:3] *= -1.0
+        self.shells = []
+        par = np.ascontiguousarray(self.raw[:, 3:])
+        seen = []
+        for i in range(par.shape[0]):
+            if self.b[i] <= b0_thr:
+                continue
+            key = tuple(par[i])
+            if key in seen:
+                continue
+            seen.append(key)
+            idx = np.where((par == par[i]).all(axis=1))[0]
+            sh = {"b": self.b[i], "idx": idx, "grad": self.raw[idx, 0:3]}
+            if self.version == 1:
+                sh.update(G=par[i, 0], Delta=par[i, 1], delta=par[i, 2], TE=par[i, 3])
+            else:
+                sh.update(G=None, Delta=None, delta=None, TE=None)
+            self.shells.append(sh)
+
+    @property
+    def nS(self):
+        return self.b0_count + self.dwi_count
+
+
+def fibonacci_sphere(n, phase=0.0):
+    """n quasi-uniform unit vectors on the full sphere."""
+    k = np.arange(n) + 0.5
+    z = 1.0 - 2.0 * k / n
+    phi = (math.pi * (3.0 - math.sqrt(5.0))) * k + phase
+    r = np.sqrt(np.maximum(0.0, 1.0 - z * z))
+    return np.stack([r * np.cos(phi), r * np.sin(phi), z], axis=1)
+
+
+def make_scheme(cfg):
+    """Synthetic protocol of SURVEY 8(d) / BASELINE.md section 3 for config ``cfg``."""
+    def shell_dirs(n, s):
+        return fibonacci_sphere(n, phase=0.37 * (s + 1))
+
+    if cfg == 1:
+        parts = [(1, 0.0), (32, 1000.0)]
+    elif cfg == 2:
+        parts = [(10, 0.0), (45, 1000.0), (45, 2000.0)]
+    elif cfg == 3:
+        parts = [(18, 0.0), (135, 1000.0), (135, 2000.0)]
+    elif cfg == 4:
+        parts = [(12, 0.0), (60, 1000.0), (60, 3000.0), (60, 10000.0)]
+    elif cfg == 5:
+        parts = [(12, 0.0), (72, 1000.0), (72, 2000.0), (72, 3000.0), (72, 4000.0)]
+    else:
+        raise ValueError(cfg)
+    stejskal = cfg in (4, 5)
+    Delta, delta, TE = 0.040, 0.020, 0.080
+    rows = []
+    s = 0
+    for n, b in parts:
+        if b == 0.0:
+            g = np.zeros((n, 3))
+        else:
+            g = shell_dirs(n, s)
+            s += 1
+        if stejskal:
+            G = math.sqrt(b * 1e6 / (Delta - delta / 3.0)) / (GAMMA * delta) if b > 0 else 0.0
+            rows.append(np.hstack([g, np.tile([G, Delta, delta, TE], (n, 1))]))
+        else:
+            rows.append(np.hstack([g, np.full((n, 1), b)]))
+    return Scheme(np.vstack(rows))
+
+
+def directional_average_scheme(scheme):
+    """Scheme after ``doDirectionalAverage`` (``amico/core.py:232-268``): one b0 + one row per shell."""
+    n = 1 + len(scheme.shells)
+    raw = np.zeros((n, scheme.raw.shape[1]))
+    for i, sh in enumerate(scheme.shells):
+        raw[i + 1, 0:3] = [1.0, 0.0, 0.0]
+        raw[i + 1, 3:] = scheme.raw[sh["idx"][0], 3:]
+    return Scheme(raw)
+
+
+# --------------------------------------------------------------------------- LUT directions
+def lut_directions(ndirs=500):
+    """Half-sphere (y >= 0) direction set standing in for ``directions/ndirs=*.bin``."""
+    d = fibonacci_sphere(2 * ndirs)
+    d = d[d[:, 1] >= 0]
+    if len(d) < ndirs:  # pragma: no cover
+        raise RuntimeError("direction set too small")
+    return np.ascontiguousarray(d[:ndirs])
+
+
+def build_htable(dirs):
+    """int16[181*181]: nearest direction (max |dot|) for each whole-degree (theta, phi)."""
+    ang = np.deg2rad(np.arange(181.0))
+    T, P = np.meshgrid(ang, ang, indexing="ij")
+    v = np.stack([np.sin(T) * np.cos(P), np.sin(T) * np.sin(P), np.cos(T)], -1).reshape(-1, 3)
+    return np.abs(v @ dirs.T).argmax(1).astype(np.int16)
+
+
+# --------------------------------------------------------------------------- zonal atoms
+_GL_X, _GL_W = npleg.leggauss(256)
+_PL = np.stack([special.eval_legendre(l, _GL_X) for l in range(0, LMAX + 1, 2)])  # (7, 256)
+
+
+def _legendre_coeffs(f_vals):
+    """Even Legendre coefficients a_l (l=0..12) of a zonal profile sampled on the GL nodes."""
+    l = np.arange(0, LMAX + 1, 2)
+    return (2 * l + 1) / 2.0 * (_PL * (f_vals * _GL_W)).sum(axis=1)
+
+
+def _band_limit(profile):
+    """callable t -> S(t)  ==>  callable t -> sum_{l even<=12} a_l P_l(t)."""
+    a = _legendre_coeffs(profile(_GL_X))
+
+    def f(t):
+        out = np.zeros_like(t)
+        for k, l in enumerate(range(0, LMAX + 1, 2)):
+            out += a[k] * special.eval_legendre(l, t)
+        return out
+
+    return f
+
+
+def _cyl_roots(n=60):
+    return special.jnp_zeros(1, n)
+
+
+def _sph_roots(n=60):
+    f = lambda x: x * special.jvp(1.5, x) - 0.5 * special.jv(1.5, x)
+    roots, x = [], 1.0
+    while len(roots) < n:
+        if f(x) * f(x + 0.25) < 0:
+            roots.append(optimize.brentq(f, x, x + 0.25))
+        x += 0.25
+    return np.array(roots)
+
+
+_CYL_AM = _cyl_roots()
+_SPH_AM = _sph_roots()
+
+
+def _gpd_sum(am, Delta, delta, D, R, n):
+    a = am / R
+    dam = D * a * a
+    num = 2 * dam * delta - 2 + 2 * np.exp(-dam * delta) + 2 * np.exp(-dam * Delta) \
+        - np.exp(-dam * (Delta - delta)) - np.exp(-dam * (Delta + delta))
+    den = dam * dam * a * a * (R * R * a * a - n)
+    return float((num / den).sum())
+
+
+def _watson_tau1(kappa):
+    if kappa < 1e-5:
+        return 1.0 / 3.0
+    sk = math.sqrt(kappa)
+    return -1.0 / (2.0 * kappa) + 1.0 / (2.0 * special.dawsn(sk) * sk)
+
+
+def _watson_coeffs(kappa):
+    f = np.exp(kappa * (_GL_X ** 2 - 1.0))
+    f /= 2.0 * math.pi * (f * _GL_W).sum()
+    return _legendre_coeffs(f)
+
+
+class _Atom:
+    """One dictionary atom: per-shell zonal profile, or isotropic per-shell value."""
+
+    def __init__(self, per_shell, isotropic):
+        self.per_shell = per_shell
+        self.isotropic = isotropic
+
+
+def _shell_par(sh):
+    return sh["b"], sh["G"], sh["Delta"], sh["delta"]
+
+
+def atom_stick(scheme, d):
+    return _Atom([_band_limit(lambda t, b=sh["b"]: np.exp(-b * d * t * t)) for sh in scheme.shells], False)
+
+
+def atom_zeppelin(scheme, d_par, d_perp):
+    return _Atom([_band_limit(lambda t, b=sh["b"]: np.exp(-b * (d_perp + (d_par - d_perp) * t * t)))
+                  for sh in scheme.shells], False)
+
+
+def atom_ball(scheme, d):
+    return _Atom([math.exp(-sh["b"] * d) for sh in scheme.shells], True)
+
+
+def atom_noddi(scheme, d_par, kappa, v_ic):
+    """v_ic * Watson-dispersed sticks + (1-v_ic) * Watson-averaged tortuous zeppelin."""
+    fw = _watson_coeffs(kappa)
+    l = np.arange(0, LMAX + 1, 2)
+    tau1 = _watson_tau1(kappa)
+    d_perp = d_par * (1.0 - v_ic)
+    dw_par = d_par * tau1 + d_perp * (1.0 - tau1)
+    dw_perp = d_par * (1.0 - tau1) / 2.0 + d_perp * (1.0 + tau1) / 2.0
+    out = []
+    for sh in scheme.shells:
+        b = sh["b"]
+        ks = _legendre_coeffs(np.exp(-b * d_par * _GL_X ** 2))
+        a_ic = fw * ks * 4.0 * math.pi / (2 * l + 1)
+        a_ec = _legendre_coeffs(np.exp(-b * (dw_perp + (dw_par - dw_perp) * _GL_X ** 2)))
+        a = v_ic * a_ic + (1.0 - v_ic) * a_ec
+
+        def f(t, a=a):
+            o = np.zeros_like(t)
+            for k, ll in enumerate(range(0, LMAX + 1, 2)):
+                o += a[k] * special.eval_legendre(ll, t)
+            return o
+
+        out.append(f)
+    return _Atom(out, False)
+
+
+def atom_cylinder(scheme, d_par, R):
+    D = d_par * 1e-6  # mm^2/s -> m^2/s
+    out = []
+    for sh in scheme.shells:
+        _, G, Delta, delta = _shell_par(sh)
+        s = _gpd_sum(_CYL_AM, Delta, delta, D, R, 1)
+        q2 = (GAMMA * delta * G) ** 2
+
+        def prof(t, G=G, s=s, q2=q2, Delta=Delta, delta=delta):
+            return np.exp(-2 * GAMMA ** 2 * G ** 2 * (1 - t * t) * s) * np.exp(-(Delta - delta / 3.0) * q2 * t * t * D)
+
+        out.append(_band_limit(prof))
+    return _Atom(out, False)
+
+
+def atom_sphere(scheme, d_is, R):
+    D = d_is * 1e-6
+    out = []
+    for sh in scheme.shells:
+        _, G, Delta, delta = _shell_par(sh)
+        out.append(math.exp(-2 * GAMMA ** 2 * G ** 2 * _gpd_sum(_SPH_AM, Delta, delta, D, R, 2)))
+    return _Atom(out, True)
+
+
+def atom_astrosticks(scheme, d):
+    out = []
+    for sh in scheme.shells:
+        x = math.sqrt(sh["b"] * d)
+        out.append(math.sqrt(math.pi) / (2 * x) * math.erf(x))
+    return _Atom(out, True)
+
+
+def _sample(atom, scheme, dirs):
+    """float32 (ndirs, nS) for a rotated atom, (nS,) for an isotropic one; b0 rows are 1."""
+    if atom.isotropic:
+        k = np.ones(scheme.nS, dtype=np.float32)
+        for sh, v in zip(scheme.shells, atom.per_shell):
+            k[sh["idx"]] = np.float32(v)
+        return k
+    k = np.ones((len(dirs), scheme.nS), dtype=np.float32)
+    for sh, f in zip(scheme.shells, atom.per_shell):
+        t = np.clip(dirs @ sh["grad"].T, -1.0, 1.0)
+        k[:, sh["idx"]] = f(t).astype(np.float32)
+    return k
+
+
+# --------------------------------------------------------------------------- model parameter grids
+def default_params(model):
+    """Default physical grids of each reference model (``amico/models.pyx:400-424, 675-706, 1004-1058, 1367-1391``)."""
+    if model == "NODDI":
+        return dict(dPar=1.7e-3, dIso=3.0e-3, IC_VFs=np.linspace(0.1, 0.99, 12),
+                    IC_ODs=np.hstack((np.array([0.03, 0.06]), np.linspace(0.09, 0.99, 10))), isExvivo=False)
+    if model == "FreeWater":
+        return dict(d_par=1.0e-3, d_perps=np.linspace(0.1, 1.0, 10) * 1e-3, d_isos=[2.5e-3], type="Human")
+    if model == "FreeWaterMouse":
+        return dict(d_par=1.0e-3, d_perps=np.linspace(0.15, 0.55, 10) * 1e-3, d_isos=[1.5e-3, 3e-3], type="Mouse")
+    if model == "CylinderZeppelinBall":
+        return dict(d_par=0.6e-3, Rs=np.concatenate(([0.01], np.linspace(0.5, 8.0, 20))) * 1e-6,
+                    d_perps=np.array([1.19e-3, 0.85e-3, 0.51e-3, 0.17e-3]), d_isos=np.array([2.0e-3]))
+    if model == "SANDI":
+        return dict(d_is=3.0e-3, Rs=np.linspace(1.0, 12.0, 5) * 1e-6, d_in=np.linspace(0.25, 3.0, 5) * 1e-3,
+                    d_isos=np.linspace(0.25, 3.0, 5) * 1e-3)
+    raise ValueError(model)
+
+
+def make_kernels(model, scheme, dirs, params=None):
+    """KERNELS dict in the layout ``<Model>.resample`` returns (no b0 merging)."""
+    p = dict(default_params(model))
+    if params:
+        p.update(params)
+    nS, nd = scheme.nS, len(dirs)
+    K = {}
+    if model == "NODDI":
+        K["model"] = "NODDI"
+        n_wm = len(p["IC_ODs"]) * len(p["IC_VFs"])
+        K["wm"] = np.zeros((n_wm, nd, nS), dtype=np.float32)
+        K["kappa"] = np.zeros(n_wm, dtype=np.float32)
+        K["icvf"] = np.zeros(n_wm, dtype=np.float32)
+        K["norms"] = np.zeros((scheme.dwi_count, n_wm))
+        idx = 0
+        for od in p["IC_ODs"]:
+            kappa = 1.0 / math.tan(od * math.pi / 2.0)
+            for vf in p["IC_VFs"]:
+                K["wm"][idx] = _sample(atom_noddi(scheme, p["dPar"], kappa, vf), scheme, dirs)
+                K["kappa"][idx] = kappa
+                K["icvf"][idx] = vf
+                K["norms"][:, idx] = 1.0 / np.linalg.norm(K["wm"][idx, 0, scheme.dwi_idx])
+                idx += 1
+        K["iso"] = _sample(atom_ball(scheme, p["dIso"]), scheme, dirs)
+    elif model in ("FreeWater", "FreeWaterMouse"):
+        K["model"] = "FreeWater"
+        K["D"] = np.stack([_sample(atom_zeppelin(scheme, p["d_par"], d), scheme, dirs) for d in p["d_perps"]])
+        K["CSF"] = np.stack([_sample(atom_ball(scheme, d), scheme, dirs) for d in p["d_isos"]])
+    elif model == "CylinderZeppelinBall":
+        K["model"] = "CylinderZeppelinBall"
+        K["wmr"] = np.stack([_sample(atom_cylinder(scheme, p["d_par"], R), scheme, dirs) for R in p["Rs"]])
+        K["wmh"] = np.stack([_sample(atom_zeppelin(scheme, p["d_par"], d), scheme, dirs) for d in p["d_perps"]])
+        K["iso"] = np.stack([_sample(atom_ball(scheme, d), scheme, dirs) for d in p["d_isos"]])
+    elif model == "SANDI":
+        K["model"] = "SANDI"
+        atoms = [atom_sphere(scheme, p["d_is"], R) for R in p["Rs"]] \
+            + [atom_astrosticks(scheme, d) for d in p["d_in"]] + [atom_ball(scheme, d) for d in p["d_isos"]]
+        K["signal"] = np.zeros((nS, len(atoms)), dtype=np.float64, order="F")
+        K["norms"] = np.zeros(len(atoms))
+        for i, a in enumerate(atoms):
+            s = _sample(a, scheme, dirs).astype(np.float64)
+            K["norms"][i] = 1.0 / np.linalg.norm(s)
+            K["signal"][:, i] = s * K["norms"][i]
+    else:
+        raise ValueError(model)
+    return K, p
+
+
+def dictionary_for_direction(model, K, k):
+    """float64 (m, n) dictionary the reference assembles for LUT index k (``models.pyx:905-908`` etc.)."""
+    if model == "NODDI":
+        return np.hstack([K["wm"][:, k, :].T.astype(np.float64), K["iso"].astype(np.float64)[:, None]])
+    if model in ("FreeWater", "FreeWaterMouse"):
+        return np.hstack([K["D"][:, k, :].T.astype(np.float64), K["CSF"].T.astype(np.float64)])
+    if model == "CylinderZeppelinBall":
+        return np.hstack([K["wmr"][:, k, :].T.astype(np.float64), K["wmh"][:, k, :].T.astype(np.float64),
+                          K["iso"].T.astype(np.float64)])
+    if model == "SANDI":
+        return np.asarray(K["signal"], dtype=np.float64)
+    raise ValueError(model)
+
+
+# --------------------------------------------------------------------------- voxels
+def lut_index_numpy(dirs_in, htable):
+    """Vectorised restatement of ``amico/lut.pyx:314-356`` (does not flip its input)."""
+    d = np.array(dirs_in, dtype=np.float64)
+    neg = d[:, 1] < 0
+    d[neg] *= -1.0
+    two_pi = 2.0 * math.pi
+    i2 = np.fmod(np.arctan2(d[:, 1], d[:, 0]), two_pi)
+    lo = i2 < 0
+    i2[lo] = np.fmod(i2[lo] + two_pi, two_pi)
+    big = i2 > math.pi
+    rxy = np.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2)
+    i1 = np.arctan2(rxy, d[:, 2])
+    i2[big] = np.fmod(np.arctan2(-d[big, 1], -d[big, 0]), two_pi)
+    i1[big] = np.arctan2(rxy[big], -d[big, 2])
+    c_round = lambda x: np.sign(x) * np.floor(np.abs(x) + 0.5)
+    ii1 = c_round(i1 / math.pi * 180.0).astype(np.int64)
+    ii2 = c_round(i2 / math.pi * 180.0).astype(np.int64)
+    if ((ii1 < 0) | (ii1 > 180) | (ii2 < 0) | (ii2 > 180)).any():
+        raise RuntimeError('"amico.lut.dir_to_lut_idx" index out of bounds')
+    return htable[ii1 * 181 + ii2].astype(np.int64)
+
+
+def make_voxels(model, K, htable, n_vox, seed, snr=30.0, iso_max=0.5):
+    """Seeded voxels: ground truth = 1-2 atoms + isotropic fraction, Rician noise at ``snr``.
+
+    Returns ``y`` (n_vox, m) float32 >= 0 and ``dirs`` (n_vox, 3) float64 unit vectors.
+    """
+    rng = np.random.default_rng(seed)
+    v = rng.standard_normal((n_vox, 3))
+    dirs = v / np.linalg.norm(v, axis=1, keepdims=True)
+    f_iso = rng.uniform(0.0, iso_max, n_vox)
+    two = rng.random(n_vox) < 0.5
+    w1 = np.where(two, rng.uniform(0.3, 0.7, n_vox), 1.0)
+    if model == "SANDI":
+        A = np.asarray(K["signal"]) / K["norms"][None, :]
+        n = A.shape[1]
+        j1, j2 = rng.integers(0, n, n_vox), rng.integers(0, n, n_vox)
+        sig = w1[:, None] * A[:, j1].T + (1 - w1)[:, None] * A[:, j2].T
+    else:
+        k = lut_index_numpy(dirs, htable)
+        if model == "NODDI":
+            rot, iso = K["wm"], K["iso"][None, :]
+        elif model in ("FreeWater", "FreeWaterMouse"):
+            rot, iso = K["D"], K["CSF"]
+        else:
+            rot, iso = np.concatenate([K["wmr"], K["wmh"]]), K["iso"]
+        n_rot = rot.shape[0]
+        j1, j2 = rng.integers(0, n_rot, n_vox), rng.integers(0, n_rot, n_vox)
+        ji = rng.integers(0, iso.shape[0], n_vox)
+        sig = (1 - f_iso)[:, None] * (w1[:, None] * rot[j1, k, :] + (1 - w1)[:, None] * rot[j2, k, :]) \
+            + f_iso[:, None] * iso[ji]
+    sigma = 1.0 / snr
+    m = sig.shape[1]
+    re = sig + sigma * rng.standard_normal((n_vox, m))
+    im = sigma * rng.standard_normal((n_vox, m))
+    y = np.sqrt(re * re + im * im).astype(np.float32)
+    return y, dirs
+
+
+@dataclass
+class Problem:
+    """Everything ``model.fit(evaluation)`` reads, for one synthetic config."""
+    cfg: int
+    model: str
+    scheme: Scheme
+    lut_dirs: np.ndarray
+    htable: np.ndarray
+    KERNELS: dict
+    params: dict
+    y: np.ndarray = field(default=None)
+    DIRs: np.ndarray = field(default=None)
+
+
+def make_problem(cfg, n_vox=None, ndirs=500, model=None, seed=None, snr=30.0):
+    model = model or CONFIGS[cfg][0]
+    scheme = make_scheme(cfg)
+    if model == "SANDI":
+        scheme = directional_average_scheme(scheme)
+    lut = lut_directions(ndirs)
+    ht = build_htable(lut)
+    K, p = make_kernels(model, scheme, lut)
+    if n_vox is None:
+        n_vox = int(np.prod(CONFIGS[cfg][1]))
+    y, dirs = make_voxels(model, K, ht, n_vox, (20251017 + cfg) if seed is None else seed, snr=snr)
+    return Problem(cfg, model, scheme, lut, ht, K, p, y, dirs)
