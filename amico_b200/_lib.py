@@ -1,0 +1,83 @@
+"""ctypes binding of ``libamico_b200.so`` (C ABI declared in ``include/amico_b200.h``).
+
+The library is built in-tree by :mod:`amico_b200.build`.  There is no CPU fallback: if the shared
+library is missing, or no B200 is visible, every fit raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libamico_b200.so")
+
+AMX_OK, AMX_E_INVALID, AMX_E_CUDA, AMX_E_LUT_RANGE, AMX_E_CAPACITY = 0, -1, -2, -3, -4
+MODEL_NODDI, MODEL_FREEWATER, MODEL_CZB, MODEL_SANDI = 0, 1, 2, 3
+FLAG_RMSE, FLAG_NRMSE, FLAG_EXTRA = 1, 2, 4
+F32, F64 = 0, 1
+SPACE_HOST, SPACE_DEVICE = 0, 1
+
+# every symbol include/amico_b200.h declares
+EXPORTS = [
+    "amx_last_error", "amx_version", "amx_device_count",
+    "amx_plan_create_noddi", "amx_plan_create_freewater", "amx_plan_create_czb", "amx_plan_create_sandi",
+    "amx_plan_destroy", "amx_plan_info", "amx_fit", "amx_lut_indices", "amx_plan_last_timing",
+    "amx_plan_last_counters",
+]
+
+
+class FitArgs(C.Structure):
+    """``amx_fit_args`` of include/amico_b200.h."""
+    _fields_ = [
+        ("space", C.c_int), ("y_dtype", C.c_int), ("y", C.c_void_p), ("n_vox", C.c_int64), ("dirs", C.c_void_p),
+        ("lambda1", C.c_double), ("lambda2", C.c_double), ("flags", C.c_uint32), ("estimates", C.c_void_p),
+        ("rmse", C.c_void_p), ("nrmse", C.c_void_p), ("extra", C.c_void_p), ("lut_out", C.c_void_p),
+        ("support_out", C.c_void_p), ("coeff_out", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+class AmxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m amico_b200.build` (needs nvcc). "
+            "amico_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    lib.amx_last_error.restype = C.c_char_p
+    lib.amx_last_error.argtypes = []
+    lib.amx_version.restype = i32
+    lib.amx_device_count.restype = i32
+    lib.amx_plan_create_noddi.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, vp, C.POINTER(vp)]
+    lib.amx_plan_create_freewater.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, C.POINTER(vp)]
+    lib.amx_plan_create_czb.argtypes = [i32, i32, i32, i32, vp, i32, vp, i32, vp, vp, vp, C.POINTER(vp)]
+    lib.amx_plan_create_sandi.argtypes = [i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, C.POINTER(vp)]
+    lib.amx_plan_destroy.argtypes = [vp]
+    lib.amx_plan_info.argtypes = [vp] + [C.POINTER(i32)] * 6
+    lib.amx_fit.argtypes = [vp, C.POINTER(FitArgs), C.POINTER(i64)]
+    lib.amx_lut_indices.argtypes = [vp, i32, vp, i64, vp]
+    lib.amx_plan_last_timing.argtypes = [vp, C.POINTER(dbl), i32]
+    lib.amx_plan_last_counters.argtypes = [vp, C.POINTER(i64), i32]
+    for name in EXPORTS:
+        if name not in ("amx_last_error",):
+            getattr(lib, name).restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != AMX_OK:
+        msg = load().amx_last_error().decode("utf-8", "replace")
+        raise AmxError(rc, msg)

@@ -1,0 +1,611 @@
+// C ABI of the B200-native per-voxel fit (see include/amico_b200.h).
+#include "../../include/amico_b200.h"
+#include "amx_kernels.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace amx;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess) return fail(AMX_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                                           __FILE__, __LINE__);                                              \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+}  // namespace
+
+struct amx_plan {
+    int device = 0, model = 0, m = 0, n = 0, n_pad = 0, ndirs = 1, n_maps = 0, npl = 1;
+    int n_rot = 0, n_wm = 0, exvivo = 0, mouse = 0, n_perp = 0, n_iso = 0, n_rs = 0, n_in = 0, dc = 0, norms_const = 0;
+    bool slab_f64 = false;
+    size_t slab_stride = 0;   // elements per direction
+    unsigned slab_bytes = 0;  // bytes to stage per direction
+    void *d_slab = nullptr;
+    double *d_T1 = nullptr, *d_T2 = nullptr;
+    int ldT1 = 0, ldT2 = 0, K2 = 0;
+    size_t T1_stride = 0, T2_stride = 0;
+    int16_t *d_htable = nullptr;
+    int *d_dwi_rows = nullptr;
+    double *d_norms = nullptr;
+    float *d_icvf = nullptr, *d_kappa = nullptr;
+    double *d_Rs = nullptr, *d_sandi_norms = nullptr, *d_d_in = nullptr, *d_d_isos = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
+    // workspace
+    DevBuf lut, order, bins, tiles, status, st_y, st_dirs, st_est, st_rmse, st_nrmse, st_extra, st_sup, st_coef;
+    int max_smem = 0, sm_count = 0;
+    // last-call records
+    double last_ms[8] = {0};
+    int64_t last_cnt[8] = {0};
+    bool timing_valid = false;
+};
+
+namespace {
+
+template <typename T>
+int upload(T **dst, const T *src, size_t count)
+{
+    CK(cudaMalloc((void **)dst, std::max<size_t>(count, 1) * sizeof(T)));
+    if (count) CK(cudaMemcpy(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    return AMX_OK;
+}
+
+int plan_common_init(amx_plan *pl, int device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return fail(AMX_E_CUDA, "no CUDA device available (%s): amico_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(AMX_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    CK(cudaSetDevice(device));
+    pl->device = device;
+    CK(cudaDeviceGetAttribute(&pl->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    CK(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    for (auto &ev : pl->ev) CK(cudaEventCreate(&ev));
+    return AMX_OK;
+}
+
+// slab geometry shared by every model
+void slab_geometry(amx_plan *pl, size_t elem)
+{
+    pl->n_pad = pl->n | 1;  // odd row stride: conflict-free for both lane-per-atom and lane-per-row access
+    size_t bytes = (size_t)pl->m * pl->n_pad * elem;
+    bytes = (bytes + 127) & ~(size_t)127;
+    pl->slab_bytes = (unsigned)bytes;
+    pl->slab_stride = bytes / elem;
+    pl->npl = (pl->n + 31) / 32;
+}
+
+int build_gram(amx_plan *pl, double **G, int K, int *ld, size_t *stride, const int *d_rows, int nrows, const double *d_norms,
+               int ldn, int norms_const)
+{
+    *ld = (K + 3) & ~3;
+    *stride = (size_t)K * *ld;
+    CK(cudaMalloc((void **)G, (size_t)pl->ndirs * *stride * sizeof(double)));
+    CK(cudaMemsetAsync(*G, 0, (size_t)pl->ndirs * *stride * sizeof(double), pl->stream));
+    int by = std::max(1, std::min(64, (K * K + 8 * 256 - 1) / (8 * 256)));
+    dim3 grid(pl->ndirs, by);
+    if (pl->slab_f64)
+        k_gram<double><<<grid, 256, 0, pl->stream>>>((const double *)pl->d_slab, pl->slab_stride, pl->n_pad, K, d_rows, nrows,
+                                                      d_norms, ldn, norms_const, *G, *ld, *stride);
+    else
+        k_gram<float><<<grid, 256, 0, pl->stream>>>((const float *)pl->d_slab, pl->slab_stride, pl->n_pad, K, d_rows, nrows,
+                                                     d_norms, ldn, norms_const, *G, *ld, *stride);
+    CK(cudaGetLastError());
+    return AMX_OK;
+}
+
+int build_rotated_plan(amx_plan *pl, const float *rot0, int n0, const float *rot1, int n1, int with_dot, const float *iso,
+                       int n_iso, const int16_t *htable)
+{
+    const int m = pl->m, ndirs = pl->ndirs;
+    pl->n = n0 + n1 + (with_dot ? 1 : 0) + n_iso;
+    pl->n_rot = n0 + n1;
+    slab_geometry(pl, sizeof(float));
+    float *d_rot0 = nullptr, *d_rot1 = nullptr, *d_iso = nullptr;
+    int rc;
+    if ((rc = upload(&d_rot0, rot0, (size_t)n0 * ndirs * m))) return rc;
+    if (n1 && (rc = upload(&d_rot1, rot1, (size_t)n1 * ndirs * m))) return rc;
+    if ((rc = upload(&d_iso, iso, (size_t)n_iso * m))) return rc;
+    if ((rc = upload(&pl->d_htable, htable, (size_t)181 * 181))) return rc;
+    CK(cudaMalloc(&pl->d_slab, (size_t)ndirs * pl->slab_stride * sizeof(float) + 1024));
+    CK(cudaMemsetAsync(pl->d_slab, 0, (size_t)ndirs * pl->slab_stride * sizeof(float) + 1024, pl->stream));
+    k_build_slab<<<ndirs, 256, 0, pl->stream>>>(d_rot0, n0, d_rot1, n1, with_dot, d_iso, n_iso, ndirs, m, pl->n_pad,
+                                                 pl->slab_stride, (float *)pl->d_slab);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(pl->stream));
+    cudaFree(d_rot0);
+    if (d_rot1) cudaFree(d_rot1);
+    cudaFree(d_iso);
+    return AMX_OK;
+}
+
+int check_common(int m, int ndirs, const void *a, const void *b, amx_plan **out)
+{
+    if (!out) return fail(AMX_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (m <= 0 || ndirs <= 0) return fail(AMX_E_INVALID, "m and ndirs must be positive (m=%d, ndirs=%d)", m, ndirs);
+    if (!a || !b) return fail(AMX_E_INVALID, "NULL kernel table");
+    return AMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *amx_last_error(void) { return g_err.c_str(); }
+int amx_version(void) { return AMX_VERSION; }
+
+int amx_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(AMX_E_CUDA, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    return n;
+}
+
+int amx_plan_destroy(amx_plan *pl)
+{
+    if (!pl) return AMX_OK;
+    cudaSetDevice(pl->device);
+    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
+                    pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->st_y, &pl->st_dirs, &pl->st_est,
+                      &pl->st_rmse, &pl->st_nrmse, &pl->st_extra, &pl->st_sup, &pl->st_coef};
+    for (DevBuf *b : bufs) b->release();
+    for (auto &ev : pl->ev) if (ev) cudaEventDestroy(ev);
+    if (pl->stream) cudaStreamDestroy(pl->stream);
+    delete pl;
+    return AMX_OK;
+}
+
+int amx_plan_create_noddi(int device, int m, int ndirs, int n_wm, const float *wm, const float *iso, const double *norms,
+                          const float *icvf, const float *kappa, const int64_t *dwi_idx, int dwi_count, int is_exvivo,
+                          const int16_t *htable, amx_plan **out)
+{
+    int rc = check_common(m, ndirs, wm, iso, out);
+    if (rc) return rc;
+    if (n_wm <= 0 || dwi_count <= 0 || dwi_count > m || !norms || !icvf || !kappa || !htable || (!dwi_idx && m != 1 + dwi_count))
+        return fail(AMX_E_INVALID, "bad NODDI tables (n_wm=%d, dwi_count=%d, m=%d)", n_wm, dwi_count, m);
+    if (n_wm + 2 > 32 * 8) return fail(AMX_E_INVALID, "n_wm=%d exceeds the supported 254 atoms", n_wm);
+    amx_plan *pl = new amx_plan;
+    pl->model = AMX_MODEL_NODDI; pl->m = m; pl->ndirs = ndirs; pl->n_wm = n_wm; pl->exvivo = is_exvivo ? 1 : 0;
+    pl->n_maps = is_exvivo ? 4 : 3; pl->dc = dwi_count;
+    if ((rc = plan_common_init(pl, device))) { amx_plan_destroy(pl); return rc; }
+    if ((rc = build_rotated_plan(pl, wm, n_wm, nullptr, 0, pl->exvivo, iso, 1, htable))) { amx_plan_destroy(pl); return rc; }
+    // DWI rows: scheme.dwi_idx, or rows 1..m-1 in the single-b0 case (amico/models.pyx:916-918)
+    std::vector<int> rows(dwi_count);
+    for (int j = 0; j < dwi_count; ++j) {
+        long long r = (m == 1 + dwi_count) ? j + 1 : (long long)dwi_idx[j];
+        if (r < 0 || r >= m) { amx_plan_destroy(pl); return fail(AMX_E_INVALID, "dwi_idx[%d]=%lld outside [0,%d)", j, r, m); }
+        rows[j] = (int)r;
+    }
+    // norms rows are identical by construction (models.pyx:781-784); detect it to keep them in registers
+    pl->norms_const = 1;
+    for (int j = 1; j < dwi_count && pl->norms_const; ++j)
+        if (memcmp(norms, norms + (size_t)j * n_wm, sizeof(double) * n_wm) != 0) pl->norms_const = 0;
+    if ((rc = upload(&pl->d_dwi_rows, rows.data(), rows.size())) || (rc = upload(&pl->d_norms, norms, (size_t)dwi_count * n_wm)) ||
+        (rc = upload(&pl->d_icvf, icvf, (size_t)n_wm)) || (rc = upload(&pl->d_kappa, kappa, (size_t)n_wm))) {
+        amx_plan_destroy(pl);
+        return rc;
+    }
+    if ((rc = build_gram(pl, &pl->d_T1, pl->n, &pl->ldT1, &pl->T1_stride, nullptr, m, nullptr, 0, 0)) ||
+        (rc = build_gram(pl, &pl->d_T2, n_wm, &pl->ldT2, &pl->T2_stride, pl->d_dwi_rows, dwi_count, pl->d_norms, n_wm, pl->norms_const))) {
+        amx_plan_destroy(pl);
+        return rc;
+    }
+    pl->K2 = n_wm;
+    cudaError_t e = cudaStreamSynchronize(pl->stream);
+    if (e != cudaSuccess) { amx_plan_destroy(pl); return fail(AMX_E_CUDA, "table build failed: %s", cudaGetErrorString(e)); }
+    *out = pl;
+    return AMX_OK;
+}
+
+int amx_plan_create_freewater(int device, int m, int ndirs, int n_perp, const float *D, int n_iso, const float *CSF,
+                              int is_mouse, const int16_t *htable, amx_plan **out)
+{
+    int rc = check_common(m, ndirs, D, CSF, out);
+    if (rc) return rc;
+    if (n_perp <= 0 || n_iso <= 0 || !htable || (is_mouse && n_iso < 2)) return fail(AMX_E_INVALID, "bad FreeWater tables (n_perp=%d, n_iso=%d)", n_perp, n_iso);
+    if (n_perp + n_iso > 256) return fail(AMX_E_INVALID, "too many atoms (%d)", n_perp + n_iso);
+    amx_plan *pl = new amx_plan;
+    pl->model = AMX_MODEL_FREEWATER; pl->m = m; pl->ndirs = ndirs; pl->n_perp = n_perp; pl->n_iso = n_iso; pl->mouse = is_mouse ? 1 : 0;
+    pl->n_maps = is_mouse ? 4 : 2;
+    if ((rc = plan_common_init(pl, device)) || (rc = build_rotated_plan(pl, D, n_perp, nullptr, 0, 0, CSF, n_iso, htable)) ||
+        (rc = build_gram(pl, &pl->d_T2, pl->n, &pl->ldT2, &pl->T2_stride, nullptr, m, nullptr, 0, 0))) {
+        amx_plan_destroy(pl);
+        return rc;
+    }
+    pl->K2 = pl->n;
+    cudaError_t e = cudaStreamSynchronize(pl->stream);
+    if (e != cudaSuccess) { amx_plan_destroy(pl); return fail(AMX_E_CUDA, "table build failed: %s", cudaGetErrorString(e)); }
+    *out = pl;
+    return AMX_OK;
+}
+
+int amx_plan_create_czb(int device, int m, int ndirs, int n_rs, const float *wmr, int n_perp, const float *wmh, int n_iso,
+                        const float *iso, const double *Rs, const int16_t *htable, amx_plan **out)
+{
+    int rc = check_common(m, ndirs, wmr, iso, out);
+    if (rc) return rc;
+    if (n_rs <= 0 || n_perp < 0 || n_iso <= 0 || !Rs || !htable || (n_perp && !wmh))
+        return fail(AMX_E_INVALID, "bad CylinderZeppelinBall tables (n_rs=%d, n_perp=%d, n_iso=%d)", n_rs, n_perp, n_iso);
+    if (n_rs + n_perp + n_iso > 256) return fail(AMX_E_INVALID, "too many atoms (%d)", n_rs + n_perp + n_iso);
+    amx_plan *pl = new amx_plan;
+    pl->model = AMX_MODEL_CZB; pl->m = m; pl->ndirs = ndirs; pl->n_rs = n_rs; pl->n_perp = n_perp; pl->n_iso = n_iso; pl->n_maps = 3;
+    if ((rc = plan_common_init(pl, device)) || (rc = build_rotated_plan(pl, wmr, n_rs, wmh, n_perp, 0, iso, n_iso, htable)) ||
+        (rc = upload(&pl->d_Rs, Rs, (size_t)n_rs)) ||
+        (rc = build_gram(pl, &pl->d_T2, pl->n, &pl->ldT2, &pl->T2_stride, nullptr, m, nullptr, 0, 0))) {
+        amx_plan_destroy(pl);
+        return rc;
+    }
+    pl->K2 = pl->n;
+    cudaError_t e = cudaStreamSynchronize(pl->stream);
+    if (e != cudaSuccess) { amx_plan_destroy(pl); return fail(AMX_E_CUDA, "table build failed: %s", cudaGetErrorString(e)); }
+    *out = pl;
+    return AMX_OK;
+}
+
+int amx_plan_create_sandi(int device, int m, int n_rs, int n_in, int n_iso, const double *signal, const double *norms,
+                          const double *Rs, const double *d_in, const double *d_isos, amx_plan **out)
+{
+    int rc = check_common(m, 1, signal, norms, out);
+    if (rc) return rc;
+    if (n_rs < 0 || n_in < 0 || n_iso < 0 || n_rs + n_in + n_iso <= 0 || !Rs || !d_in || !d_isos)
+        return fail(AMX_E_INVALID, "bad SANDI tables");
+    if (n_rs + n_in + n_iso > 256) return fail(AMX_E_INVALID, "too many atoms (%d)", n_rs + n_in + n_iso);
+    amx_plan *pl = new amx_plan;
+    pl->model = AMX_MODEL_SANDI; pl->m = m; pl->ndirs = 1; pl->n_rs = n_rs; pl->n_in = n_in; pl->n_iso = n_iso; pl->n_maps = 6;
+    pl->n = n_rs + n_in + n_iso; pl->slab_f64 = true;
+    if ((rc = plan_common_init(pl, device))) { amx_plan_destroy(pl); return rc; }
+    slab_geometry(pl, sizeof(double));
+    double *d_A = nullptr;
+    if ((rc = upload(&d_A, signal, (size_t)m * pl->n)) || (rc = upload(&pl->d_sandi_norms, norms, (size_t)pl->n)) ||
+        (rc = upload(&pl->d_Rs, Rs, (size_t)std::max(n_rs, 1))) || (rc = upload(&pl->d_d_in, d_in, (size_t)std::max(n_in, 1))) ||
+        (rc = upload(&pl->d_d_isos, d_isos, (size_t)std::max(n_iso, 1)))) {
+        amx_plan_destroy(pl);
+        return rc;
+    }
+    cudaError_t e = cudaMalloc(&pl->d_slab, pl->slab_stride * sizeof(double) + 1024);
+    if (e == cudaSuccess) e = cudaMemsetAsync(pl->d_slab, 0, pl->slab_stride * sizeof(double) + 1024, pl->stream);
+    if (e != cudaSuccess) { amx_plan_destroy(pl); return fail(AMX_E_CUDA, "slab alloc: %s", cudaGetErrorString(e)); }
+    k_build_slab_f64<<<1, 256, 0, pl->stream>>>(d_A, m, pl->n, pl->n_pad, (double *)pl->d_slab);
+    if ((rc = build_gram(pl, &pl->d_T2, pl->n, &pl->ldT2, &pl->T2_stride, nullptr, m, nullptr, 0, 0))) { amx_plan_destroy(pl); return rc; }
+    pl->K2 = pl->n;
+    e = cudaStreamSynchronize(pl->stream);
+    cudaFree(d_A);
+    if (e != cudaSuccess) { amx_plan_destroy(pl); return fail(AMX_E_CUDA, "table build failed: %s", cudaGetErrorString(e)); }
+    *out = pl;
+    return AMX_OK;
+}
+
+int amx_plan_info(const amx_plan *pl, int *model, int *m, int *n_atoms, int *n_maps, int *ndirs, int *device)
+{
+    if (!pl) return fail(AMX_E_INVALID, "plan is NULL");
+    if (model) *model = pl->model;
+    if (m) *m = pl->m;
+    if (n_atoms) *n_atoms = pl->n;
+    if (n_maps) *n_maps = pl->n_maps;
+    if (ndirs) *ndirs = pl->ndirs;
+    if (device) *device = pl->device;
+    return AMX_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <int MODEL, int NPL, typename TS>
+int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+{
+    auto kern = k_fit<MODEL, NPL, TS>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return AMX_OK;
+}
+
+template <int MODEL, typename TS>
+int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+{
+    switch (npl) {
+    case 1: return launch_fit<MODEL, 1, TS>(p, grid, block, smem, st);
+    case 2: return launch_fit<MODEL, 2, TS>(p, grid, block, smem, st);
+    case 3: case 4: return launch_fit<MODEL, 4, TS>(p, grid, block, smem, st);
+    case 5: return launch_fit<MODEL, 5, TS>(p, grid, block, smem, st);
+    case 6: case 7: case 8: return launch_fit<MODEL, 8, TS>(p, grid, block, smem, st);
+    }
+    return fail(AMX_E_INVALID, "unsupported atom count (npl=%d)", npl);
+}
+
+// Enqueue LUT index + binning + fused fit for device-resident voxels.  All pointers are device pointers.
+int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launches)
+{
+    const long long n_vox = a->n_vox;
+    const int tile_v = std::max(1, env_int("AMX_TILE_VOX", 256));
+    const bool rotated = pl->model != AMX_MODEL_SANDI;
+    const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
+    CK(pl->status.reserve(64));
+    CK(pl->tiles.reserve((size_t)max_tiles * sizeof(int4)));
+    CK(pl->bins.reserve(((size_t)4 * pl->ndirs + 8) * sizeof(int)));
+    int *bins = (int *)pl->bins.p;
+    int *hist = bins, *offs = bins + pl->ndirs, *cursor = bins + 2 * pl->ndirs, *tile_offs = bins + 3 * pl->ndirs,
+        *totals = bins + 4 * pl->ndirs;  // totals[0]=n_tiles, [1]=n binned, [2]=tile counter
+    long long *status = (long long *)pl->status.p;
+    CK(cudaMemsetAsync(pl->bins.p, 0, ((size_t)4 * pl->ndirs + 8) * sizeof(int), st));
+    {
+        long long init[3] = {0, (long long)1 << 62, 0};
+        CK(cudaMemcpyAsync(status, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaEventRecord(pl->ev[0], st));
+    int n_tiles = 0;
+    int *lut = nullptr;
+    if (rotated) {
+        if (!a->dirs) return fail(AMX_E_INVALID, "dirs is NULL");
+        if (a->lut_out) lut = a->lut_out;
+        else { CK(pl->lut.reserve((size_t)n_vox * sizeof(int))); lut = (int *)pl->lut.p; }
+        CK(pl->order.reserve((size_t)n_vox * sizeof(int)));
+        const int B = 256;
+        const unsigned G = (unsigned)((n_vox + B - 1) / B);
+        k_lut<<<G, B, 0, st>>>(a->dirs, n_vox, pl->d_htable, pl->ndirs, lut, hist, status);
+        k_scan_bins<<<1, 1024, 0, st>>>(hist, pl->ndirs, tile_v, offs, cursor, tile_offs, totals);
+        k_scatter<<<G, B, 0, st>>>(lut, n_vox, cursor, (int *)pl->order.p);
+        k_tiles<<<(pl->ndirs + 127) / 128, 128, 0, st>>>(hist, offs, tile_offs, pl->ndirs, tile_v, (int4 *)pl->tiles.p);
+        CK(cudaGetLastError());
+        *launches += 4;
+        // the tile count and the error flag decide the launch: one small read-back
+        int h_tot[2];
+        long long h_status[2];
+        CK(cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (h_status[0]) {
+            pl->last_cnt[6] = h_status[1];
+            return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
+        }
+        n_tiles = h_tot[0];
+    } else {
+        n_tiles = (int)((n_vox + tile_v - 1) / tile_v);
+        k_tiles_linear<<<(n_tiles + 127) / 128, 128, 0, st>>>(n_vox, tile_v, (int4 *)pl->tiles.p, n_tiles);
+        CK(cudaGetLastError());
+        *launches += 1;
+        if (a->lut_out) CK(cudaMemsetAsync(a->lut_out, 0, (size_t)n_vox * sizeof(int), st));
+    }
+    CK(cudaEventRecord(pl->ev[1], st));
+
+    FitParams p;
+    memset(&p, 0, sizeof p);
+    p.model = pl->model; p.m = pl->m; p.n = pl->n; p.n_pad = pl->n_pad; p.ndirs = pl->ndirs; p.n_maps = pl->n_maps;
+    p.NA = 32 * (pl->npl == 3 ? 4 : (pl->npl == 6 || pl->npl == 7) ? 8 : pl->npl);
+    p.slab = pl->d_slab; p.slab_stride = pl->slab_stride;
+    p.T1 = pl->d_T1; p.ldT1 = pl->ldT1; p.T1_stride = pl->T1_stride;
+    p.T2 = pl->d_T2; p.ldT2 = pl->ldT2; p.T2_stride = pl->T2_stride; p.K2 = pl->K2;
+    p.y = a->y; p.y_f64 = a->y_dtype == AMX_F64; p.n_vox = n_vox;
+    p.order = rotated ? (const int *)pl->order.p : nullptr; p.tiles = (const int4 *)pl->tiles.p; p.n_tiles = n_tiles;
+    p.tile_counter = totals + 2;
+    p.lambda1 = a->lambda1; p.lambda2 = a->lambda2; p.flags = a->flags;
+    p.dwi_rows = pl->d_dwi_rows; p.dc = pl->dc; p.norms = pl->d_norms; p.norms_const = pl->norms_const;
+    p.icvf = pl->d_icvf; p.kappa = pl->d_kappa; p.exvivo = pl->exvivo; p.n_wm = pl->n_wm;
+    p.mouse = pl->mouse; p.n_perp = pl->n_perp; p.n_iso = pl->n_iso; p.n_rs = pl->n_rs; p.n_in = pl->n_in;
+    p.Rs = pl->d_Rs; p.sandi_norms = pl->d_sandi_norms; p.d_in = pl->d_d_in; p.d_isos = pl->d_d_isos;
+    p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
+    p.status = status;
+    p.m_pad = (pl->m + 1) & ~1; p.dc_pad = (pl->dc + 1) & ~1;
+    p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad);
+
+    // shared-memory budget: [header 128][slab (optional)][nwarps x workspace]
+    const size_t ws_bytes = (size_t)p.ws_doubles * sizeof(double);
+    const size_t budget = (size_t)pl->max_smem;
+    const int want_warps = std::min(16, std::max(1, env_int("AMX_WARPS", 16)));
+    const int min_staged_warps = std::max(1, env_int("AMX_MIN_STAGED_WARPS", 8));
+    bool staged = env_int("AMX_NO_TMA", 0) == 0 && 128 + (size_t)pl->slab_bytes + ws_bytes * min_staged_warps <= budget;
+    size_t fixed = 128 + (staged ? pl->slab_bytes : 0);
+    int nwarps = (int)std::min<size_t>(want_warps, (budget - fixed) / ws_bytes);
+    if (nwarps < 1) return fail(AMX_E_INVALID, "per-warp workspace (%zu B) does not fit in shared memory (m=%d, n=%d)", ws_bytes, pl->m, pl->n);
+    p.slab_bytes = staged ? pl->slab_bytes : 0;
+    p.slab_smem_off = 128;
+    p.ws_smem_off = (unsigned)fixed;
+    p.nwarps = nwarps;
+    const size_t smem = fixed + ws_bytes * nwarps;
+    int ctas_per_sm = std::max(1, (int)std::min<size_t>(budget / smem, (size_t)(16 / nwarps)));
+    if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
+    int grid = std::max(1, std::min(n_tiles, pl->sm_count * ctas_per_sm));
+
+    int rc;
+    switch (pl->model) {
+    case AMX_MODEL_NODDI: rc = dispatch_npl<MODEL_NODDI, float>(pl->npl, p, grid, nwarps * 32, smem, st); break;
+    case AMX_MODEL_FREEWATER: rc = dispatch_npl<MODEL_FREEWATER, float>(pl->npl, p, grid, nwarps * 32, smem, st); break;
+    case AMX_MODEL_CZB: rc = dispatch_npl<MODEL_CZB, float>(pl->npl, p, grid, nwarps * 32, smem, st); break;
+    default: rc = dispatch_npl<MODEL_SANDI, double>(pl->npl, p, grid, nwarps * 32, smem, st); break;
+    }
+    if (rc) return rc;
+    *launches += 1;
+    CK(cudaEventRecord(pl->ev[2], st));
+    pl->last_cnt[1] = n_tiles;
+    pl->last_cnt[3] = (int64_t)smem;
+    pl->last_cnt[4] = nwarps;
+    pl->last_cnt[5] = staged ? 1 : 0;
+    pl->last_cnt[7] = grid;
+    return AMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
+{
+    if (!pl || !a) return fail(AMX_E_INVALID, "plan/args is NULL");
+    if (a->n_vox < 0 || a->n_vox >= ((long long)1 << 31)) return fail(AMX_E_INVALID, "n_vox=%lld out of range", (long long)a->n_vox);
+    if (!a->y || !a->estimates) return fail(AMX_E_INVALID, "y/estimates is NULL");
+    if ((a->flags & AMX_FLAG_RMSE) && !a->rmse) return fail(AMX_E_INVALID, "AMX_FLAG_RMSE without rmse buffer");
+    if ((a->flags & AMX_FLAG_NRMSE) && !a->nrmse) return fail(AMX_E_INVALID, "AMX_FLAG_NRMSE without nrmse buffer");
+    const bool has_extra = (a->flags & AMX_FLAG_EXTRA) && (pl->model == AMX_MODEL_NODDI || pl->model == AMX_MODEL_FREEWATER);
+    if (has_extra && !a->extra) return fail(AMX_E_INVALID, "AMX_FLAG_EXTRA without extra buffer");
+    if (a->y_dtype != AMX_F32 && a->y_dtype != AMX_F64) return fail(AMX_E_INVALID, "bad y_dtype %d", a->y_dtype);
+    if (pl->model != AMX_MODEL_SANDI && !a->dirs) return fail(AMX_E_INVALID, "dirs is NULL");
+    CK(cudaSetDevice(pl->device));
+    pl->timing_valid = false;
+    memset(pl->last_cnt, 0, sizeof pl->last_cnt);
+    if (a->n_vox == 0) return AMX_OK;
+    int launches = 0;
+    int rc = AMX_OK;
+    amx_fit_args d = *a;
+    if (!has_extra) d.flags &= ~AMX_FLAG_EXTRA;
+    const size_t n = (size_t)a->n_vox, m = (size_t)pl->m;
+    const size_t ybytes = n * m * (a->y_dtype == AMX_F64 ? 8 : 4);
+    const size_t extra_elems = has_extra ? (pl->model == AMX_MODEL_NODDI ? 2 * n : n * m) : 0;
+    cudaStream_t st = pl->stream;
+    if (a->space == AMX_SPACE_DEVICE) {
+        if (a->stream) st = (cudaStream_t)a->stream;
+        CK(cudaEventRecord(pl->ev[3], st));
+        rc = fit_device(pl, &d, st, &launches);
+    } else if (a->space == AMX_SPACE_HOST) {
+        CK(pl->st_y.reserve(ybytes));
+        CK(pl->st_est.reserve(n * pl->n_maps * sizeof(double)));
+        CK(cudaEventRecord(pl->ev[3], st));
+        CK(cudaMemcpyAsync(pl->st_y.p, a->y, ybytes, cudaMemcpyHostToDevice, st));
+        d.y = pl->st_y.p; d.estimates = (double *)pl->st_est.p;
+        if (a->dirs) {
+            CK(pl->st_dirs.reserve(n * 3 * sizeof(double)));
+            CK(cudaMemcpyAsync(pl->st_dirs.p, a->dirs, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+            d.dirs = (double *)pl->st_dirs.p;
+        }
+        if (d.flags & AMX_FLAG_RMSE) { CK(pl->st_rmse.reserve(n * sizeof(double))); d.rmse = (double *)pl->st_rmse.p; }
+        if (d.flags & AMX_FLAG_NRMSE) { CK(pl->st_nrmse.reserve(n * sizeof(double))); d.nrmse = (double *)pl->st_nrmse.p; }
+        if (has_extra) { CK(pl->st_extra.reserve(extra_elems * sizeof(double))); d.extra = (double *)pl->st_extra.p; }
+        if (a->support_out) { CK(pl->st_sup.reserve(n * sizeof(int))); d.support_out = (int *)pl->st_sup.p; }
+        if (a->coeff_out) { CK(pl->st_coef.reserve(n * pl->n * sizeof(double))); d.coeff_out = (double *)pl->st_coef.p; }
+        if (a->lut_out) { CK(pl->lut.reserve(n * sizeof(int))); d.lut_out = (int *)pl->lut.p; }
+        rc = fit_device(pl, &d, st, &launches);
+        // the reference flips DIRs in place before it can fail, so hand the flipped directions back either way
+        if (a->dirs && (rc == AMX_OK || rc == AMX_E_LUT_RANGE))
+            CK(cudaMemcpyAsync(a->dirs, d.dirs, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        if (a->lut_out && (rc == AMX_OK || rc == AMX_E_LUT_RANGE))
+            CK(cudaMemcpyAsync(a->lut_out, d.lut_out, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (rc == AMX_OK) {
+            CK(cudaMemcpyAsync(a->estimates, d.estimates, n * pl->n_maps * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (d.flags & AMX_FLAG_RMSE) CK(cudaMemcpyAsync(a->rmse, d.rmse, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (d.flags & AMX_FLAG_NRMSE) CK(cudaMemcpyAsync(a->nrmse, d.nrmse, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (has_extra) CK(cudaMemcpyAsync(a->extra, d.extra, extra_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (a->support_out) CK(cudaMemcpyAsync(a->support_out, d.support_out, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+            if (a->coeff_out) CK(cudaMemcpyAsync(a->coeff_out, d.coeff_out, n * pl->n * sizeof(double), cudaMemcpyDeviceToHost, st));
+        }
+    } else {
+        return fail(AMX_E_INVALID, "bad space %d", a->space);
+    }
+    if (rc != AMX_OK) {
+        std::string keep = g_err;
+        cudaStreamSynchronize(st);
+        if (err_voxel) *err_voxel = pl->last_cnt[6];
+        g_err = keep;
+        return rc;
+    }
+    CK(cudaEventRecord(pl->ev[4], st));
+    long long h_status[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->last_ms[0] = ms;
+    if (cudaEventElapsedTime(&ms, pl->ev[1], pl->ev[2]) == cudaSuccess) pl->last_ms[1] = ms;
+    if (cudaEventElapsedTime(&ms, pl->ev[3], pl->ev[4]) == cudaSuccess) pl->last_ms[2] = ms;
+    pl->timing_valid = true;
+    pl->last_cnt[0] = launches;
+    pl->last_cnt[2] = h_status[2];
+    if (h_status[2])
+        return fail(AMX_E_CAPACITY, "%lld voxel(s) outgrew the %d-atom active-set workspace", h_status[2], LC);
+    return AMX_OK;
+}
+
+int amx_lut_indices(amx_plan *pl, int space, double *dirs, int64_t n, int32_t *idx)
+{
+    if (!pl || !dirs || !idx || n < 0) return fail(AMX_E_INVALID, "bad argument");
+    if (pl->model == AMX_MODEL_SANDI) return fail(AMX_E_INVALID, "SANDI has no direction LUT");
+    if (n == 0) return AMX_OK;
+    CK(cudaSetDevice(pl->device));
+    cudaStream_t st = pl->stream;
+    double *d_dirs = dirs;
+    int *d_idx = idx;
+    if (space == AMX_SPACE_HOST) {
+        CK(pl->st_dirs.reserve((size_t)n * 3 * sizeof(double)));
+        CK(pl->lut.reserve((size_t)n * sizeof(int)));
+        d_dirs = (double *)pl->st_dirs.p; d_idx = (int *)pl->lut.p;
+        CK(cudaMemcpyAsync(d_dirs, dirs, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    CK(pl->status.reserve(64));
+    long long init[3] = {0, (long long)1 << 62, 0};
+    CK(cudaMemcpyAsync(pl->status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    k_lut<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_dirs, n, pl->d_htable, pl->ndirs, d_idx, nullptr, (long long *)pl->status.p);
+    CK(cudaGetLastError());
+    if (space == AMX_SPACE_HOST) {
+        CK(cudaMemcpyAsync(dirs, d_dirs, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(idx, d_idx, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
+    }
+    long long h_status[2];
+    CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (h_status[0]) return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
+    return AMX_OK;
+}
+
+int amx_plan_last_timing(amx_plan *pl, double *out_ms, int n)
+{
+    if (!pl || !out_ms) return fail(AMX_E_INVALID, "bad argument");
+    if (!pl->timing_valid) return fail(AMX_E_INVALID, "no completed fit on this plan");
+    for (int i = 0; i < n && i < 8; ++i) out_ms[i] = pl->last_ms[i];
+    return AMX_OK;
+}
+
+int amx_plan_last_counters(amx_plan *pl, int64_t *out, int n)
+{
+    if (!pl || !out) return fail(AMX_E_INVALID, "bad argument");
+    for (int i = 0; i < n && i < 8; ++i) out[i] = pl->last_cnt[i];
+    return AMX_OK;
+}
+
+}  // extern "C"

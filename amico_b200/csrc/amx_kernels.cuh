@@ -1,0 +1,525 @@
+// Device kernels of the per-voxel fit: LUT index + binning, table construction, fused fit.
+#pragma once
+#include "amx_solvers.cuh"
+
+namespace amx {
+
+enum { MODEL_NODDI = 0, MODEL_FREEWATER = 1, MODEL_CZB = 2, MODEL_SANDI = 3 };
+enum { FLAG_RMSE = 1, FLAG_NRMSE = 2, FLAG_EXTRA = 4 };
+
+// ------------------------------------------------------------------------------------------------
+// direction -> LUT index (amico/lut.pyx:314-356), flips `d` in place; -1 when out of range.
+__device__ __forceinline__ int dir_to_lut_idx(double *d, const int16_t *__restrict__ htable)
+{
+    const double PI = 3.14159265358979323846;
+    double x = d[0], y = d[1], z = d[2];
+    if (y < 0.0) {
+        x = -x; y = -y; z = -z;
+        d[0] = x; d[1] = y; d[2] = z;
+    }
+    double i1, i2 = fmod(atan2(y, x), 2.0 * PI);
+    if (i2 < 0.0) i2 = fmod(i2 + 2.0 * PI, 2.0 * PI);
+    if (i2 > PI) {
+        i2 = fmod(atan2(-y, -x), 2.0 * PI);
+        i1 = atan2(sqrt(x * x + y * y), -z);
+    } else {
+        i1 = atan2(sqrt(x * x + y * y), z);
+    }
+    double r1 = round(i1 / PI * 180.0), r2 = round(i2 / PI * 180.0);
+    if (!(r1 >= 0.0 && r1 <= 180.0 && r2 >= 0.0 && r2 <= 180.0)) return -1;
+    return (int)htable[(int)r1 * 181 + (int)r2];
+}
+
+// status words: [0] error flag, [1] first offending voxel, [2] workspace-overflow voxel count
+__global__ void k_lut(double *dirs, long long n, const int16_t *__restrict__ htable, int ndirs, int *lut, int *hist,
+                      long long *status)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int idx = dir_to_lut_idx(dirs + 3 * i, htable);
+    if (idx < 0 || idx >= ndirs) {
+        idx = -1;
+        atomicExch((unsigned long long *)&status[0], 1ull);
+        atomicMin(&status[1], i);
+    } else if (hist) {
+        atomicAdd(&hist[idx], 1);
+    }
+    lut[i] = idx;
+}
+
+// exclusive scan of the per-direction histogram + tile bookkeeping; one block.
+// offs[d] = first slot of bin d in `order`; tile_offs[d] = first tile of bin d; totals[0] = n tiles
+__global__ void k_scan_bins(const int *hist, int ndirs, int tile_v, int *offs, int *cursor, int *tile_offs, int *totals)
+{
+    __shared__ int s_part[1024], s_tpart[1024];
+    int tid = threadIdx.x, nt = blockDim.x;
+    int per = (ndirs + nt - 1) / nt;
+    int b0 = tid * per, b1 = min(ndirs, b0 + per);
+    int sum = 0, tsum = 0;
+    for (int d = b0; d < b1; ++d) { sum += hist[d]; tsum += (hist[d] + tile_v - 1) / tile_v; }
+    s_part[tid] = sum; s_tpart[tid] = tsum;
+    __syncthreads();
+    if (tid == 0) {
+        int a = 0, t = 0;
+        for (int i = 0; i < nt; ++i) {
+            int v = s_part[i], tv = s_tpart[i];
+            s_part[i] = a; s_tpart[i] = t;
+            a += v; t += tv;
+        }
+        totals[0] = t;
+        totals[1] = a;
+    }
+    __syncthreads();
+    int a = s_part[tid], t = s_tpart[tid];
+    for (int d = b0; d < b1; ++d) {
+        offs[d] = a; cursor[d] = a; tile_offs[d] = t;
+        a += hist[d]; t += (hist[d] + tile_v - 1) / tile_v;
+    }
+}
+
+__global__ void k_scatter(const int *lut, long long n, int *cursor, int *order)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = lut[i];
+    if (d < 0) return;
+    int pos = atomicAdd(&cursor[d], 1);
+    order[pos] = (int)i;
+}
+
+__global__ void k_tiles(const int *hist, const int *offs, const int *tile_offs, int ndirs, int tile_v, int4 *tiles)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndirs) return;
+    int c = hist[d], o = offs[d], t = tile_offs[d];
+    for (int s = 0; s < c; s += tile_v, ++t) tiles[t] = make_int4(d, o + s, min(tile_v, c - s), 0);
+}
+
+// tiles of consecutive voxels (models without a direction)
+__global__ void k_tiles_linear(long long n, int tile_v, int4 *tiles, int n_tiles)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    long long s = (long long)t * tile_v;
+    tiles[t] = make_int4(0, (int)s, (int)min((long long)tile_v, n - s), 0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-direction slab  S[d][r][k], k < n: columns = rotated blocks, optional all-ones "dot" column, isotropic block.
+// rot0/rot1: float32 [n0|n1][ndirs][m] (reference layout), iso: float32 [n_iso][m].
+__global__ void k_build_slab(const float *__restrict__ rot0, int n0, const float *__restrict__ rot1, int n1, int with_dot,
+                             const float *__restrict__ iso, int n_iso, int ndirs, int m, int n_pad, size_t slab_stride,
+                             float *slab)
+{
+    int d = blockIdx.x;
+    float *S = slab + (size_t)d * slab_stride;
+    int n = n0 + n1 + (with_dot ? 1 : 0) + n_iso;
+    for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
+        int k = e / m, r = e - k * m;
+        float v;
+        if (k < n0) v = rot0[((size_t)k * ndirs + d) * m + r];
+        else if (k < n0 + n1) v = rot1[((size_t)(k - n0) * ndirs + d) * m + r];
+        else if (with_dot && k == n0 + n1) v = 1.0f;
+        else v = iso[(size_t)(k - n0 - n1 - (with_dot ? 1 : 0)) * m + r];
+        S[(size_t)r * n_pad + k] = v;
+    }
+    // zero the padding columns so that no uninitialised value is ever staged
+    for (int e = threadIdx.x; e < (n_pad - n) * m; e += blockDim.x) {
+        int r = e / (n_pad - n), k = n + e % (n_pad - n);
+        S[(size_t)r * n_pad + k] = 0.0f;
+    }
+}
+
+// SANDI: column-major double (m x n) -> row-major [r][k] double slab
+__global__ void k_build_slab_f64(const double *__restrict__ A, int m, int n, int n_pad, double *slab)
+{
+    for (int e = threadIdx.x; e < m * n_pad; e += blockDim.x) {
+        int r = e / n_pad, k = e - r * n_pad;
+        slab[e] = k < n ? A[(size_t)k * m + r] : 0.0;
+    }
+}
+
+// Gram of the slab rows listed in `rows` (NULL = all m rows), optionally column-scaled by `norms`
+// (norms[jj*ldn + k], jj = position in `rows`): G[i][j] = sum_r (a_ri s_ri)(a_rj s_rj), accumulated
+// in row order with un-fused multiply-add exactly like oracle gram_column().
+template <typename TS>
+__global__ void k_gram(const TS *__restrict__ slab, size_t slab_stride, int n_pad, int K, const int *__restrict__ rows,
+                       int nrows, const double *__restrict__ norms, int ldn, int norms_const, double *G, int ldG,
+                       size_t G_stride)
+{
+    int d = blockIdx.x;
+    const TS *S = slab + (size_t)d * slab_stride;
+    double *Gd = G + (size_t)d * G_stride;
+    for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < K * K; e += blockDim.x * gridDim.y) {
+        int i = e / K, j = e - i * K;
+        if (j < i) continue;
+        double s = 0.0;
+        for (int rr = 0; rr < nrows; ++rr) {
+            int r = rows ? rows[rr] : rr;
+            double ai = (double)S[(size_t)r * n_pad + i], aj = (double)S[(size_t)r * n_pad + j];
+            if (norms) {
+                int nr = norms_const ? 0 : rr;
+                ai = __dmul_rn(ai, norms[(size_t)nr * ldn + i]);
+                aj = __dmul_rn(aj, norms[(size_t)nr * ldn + j]);
+            }
+            s = madd(s, ai, aj);
+        }
+        Gd[(size_t)i * ldG + j] = s;
+        Gd[(size_t)j * ldG + i] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct FitParams {
+    int model, m, n, n_pad, ndirs, n_maps, NA;
+    // slab
+    const void *slab; size_t slab_stride;  // elements per direction
+    unsigned slab_bytes;                   // bytes staged per direction (multiple of 16); 0 = read from global
+    // Gram tables
+    const double *T1; int ldT1; size_t T1_stride;  // NODDI: full dictionary (NNLS stages)
+    const double *T2; int ldT2; size_t T2_stride; int K2;  // LARS system
+    // voxels
+    const void *y; int y_f64; long long n_vox;
+    const int *order; const int4 *tiles; int n_tiles; int *tile_counter;
+    double lambda1, lambda2; unsigned flags;
+    // NODDI
+    const int *dwi_rows; int dc; const double *norms; int norms_const; const float *icvf; const float *kappa; int exvivo;
+    int n_wm;
+    // FreeWater / CZB / SANDI
+    int mouse, n_perp, n_iso, n_rs, n_in;
+    const double *Rs, *sandi_norms, *d_in, *d_isos;
+    // outputs
+    double *est, *rmse, *nrmse, *extra, *coeff_out; int *support_out; long long *status;
+    // launch geometry
+    int nwarps; unsigned ws_doubles; unsigned slab_smem_off, ws_smem_off;
+    int m_pad, dc_pad;
+};
+
+struct WarpWS {
+    double *c1, *dtr, *x, *mat, *rd, *u, *gs, *y, *y2;
+    int *P;
+};
+
+__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad) { return 3u * NA + TRI + 3 * LC + LC / 2 + m_pad + dc_pad; }
+
+__device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad)
+{
+    WarpWS w;
+    w.c1 = base; base += NA;
+    w.dtr = base; base += NA;
+    w.x = base; base += NA;
+    w.mat = base; base += TRI;
+    w.rd = base; base += LC;
+    w.u = base; base += LC;
+    w.gs = base; base += LC;
+    w.P = (int *)base; base += LC / 2;
+    w.y = base; base += m_pad;
+    w.y2 = base;
+    return w;
+}
+
+// acc[s] += sum_r S[row(r)][lane+32s] * scale * yv[r]   (sequential in r, un-fused: matches the CPU order)
+template <int NPL, typename TS>
+__device__ __forceinline__ void at_y(const TS *S, int n_pad, int n, int nrows, const int *__restrict__ rows, const double *yv,
+                                     const double *__restrict__ norms, int ldn, int norms_const, double (&acc)[NPL], int lane)
+{
+    double nk[NPL];
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        acc[s] = 0.0;
+        nk[s] = 1.0;
+        if (norms && norms_const && lane + 32 * s < n) nk[s] = norms[lane + 32 * s];
+    }
+#pragma unroll 2
+    for (int rr = 0; rr < nrows; ++rr) {
+        int r = rows ? rows[rr] : rr;
+        double yr = yv[rr];
+        const TS *row = S + (size_t)r * n_pad + lane;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            if (lane + 32 * s < n) {
+                double a = (double)row[32 * s];
+                if (norms) a = __dmul_rn(a, norms_const ? nk[s] : norms[(size_t)rr * ldn + lane + 32 * s]);
+                acc[s] = madd(acc[s], a, yr);
+            }
+        }
+    }
+}
+
+// sum_i v[i]^2 in index order (all lanes compute the same value)
+__device__ __forceinline__ double seq_sumsq(const double *v, int n)
+{
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s = madd(s, v[i], v[i]);
+    return s;
+}
+
+// Visit the strictly positive entries of x[0..n) in increasing index order; f(j, xj) runs uniformly on all lanes.
+template <int NPL, typename F>
+__device__ __forceinline__ void for_each_positive(const double *x, int n, int lane, F f)
+{
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+        int j = lane + 32 * s;
+        unsigned mask = __ballot_sync(FULL, j < n && x[j] > 0.0);
+        while (mask) {
+            int l = __ffs(mask) - 1;
+            mask &= mask - 1;
+            int jj = l + 32 * s;
+            f(jj, x[jj]);
+        }
+    }
+}
+
+// fit errors (amico/models.pyx:45-71): y_est = A x with the full dictionary; ws.y is overwritten
+template <int NPL, typename TS>
+__device__ __forceinline__ void fit_errors(const TS *S, int n_pad, int n, int m, double *yv, const double *x, unsigned flags,
+                                           double *rmse_out, double *nrmse_out, int lane)
+{
+    double den = 0.0;
+    if (flags & FLAG_NRMSE) den = seq_sumsq(yv, m);
+    __syncwarp();
+    for (int i = lane; i < m; i += 32) {
+        double ye = 0.0;
+        for (int j = 0; j < n; ++j) {
+            double xj = x[j];
+            if (xj != 0.0) ye = madd(ye, (double)S[(size_t)i * n_pad + j], xj);
+        }
+        double d = yv[i] - ye;
+        yv[i] = d * d;
+    }
+    __syncwarp();
+    if (flags & FLAG_RMSE) {
+        double acc = 0.0;
+        for (int i = 0; i < m; ++i) acc += yv[i] / (double)m;
+        if (lane == 0) *rmse_out = sqrt(acc);
+    }
+    if (flags & FLAG_NRMSE) {
+        double acc = 0.0;
+        if (den > 1e-16) {
+            for (int i = 0; i < m; ++i) acc += yv[i] / den;
+            acc = sqrt(acc);
+        }
+        if (lane == 0) *nrmse_out = acc;
+    }
+}
+
+template <int MODEL, int NPL, typename TS>
+__global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t *mbar = (uint64_t *)smem;
+    int *s_tile = (int *)(smem + 8);
+    int *s_next = (int *)(smem + 12);
+    TS *s_slab = (TS *)(smem + p.slab_smem_off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad);
+    const int m = p.m, n = p.n, n_pad = p.n_pad;
+    const bool staged = p.slab_bytes != 0;
+    uint32_t phase = 0;
+    if (threadIdx.x == 0 && staged) {
+        mbar_init(mbar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    long long n_overflow = 0;
+
+    for (;;) {
+        if (threadIdx.x == 0) *s_tile = atomicAdd(p.tile_counter, 1);
+        __syncthreads();
+        const int t = *s_tile;
+        if (t >= p.n_tiles) break;
+        const int4 tile = p.tiles[t];
+        const int dir = tile.x;
+        const TS *Sg = (const TS *)p.slab + (size_t)dir * p.slab_stride;
+        const TS *S = Sg;
+        if (staged) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(mbar, p.slab_bytes);
+                bulk_g2s(s_slab, Sg, p.slab_bytes, mbar);
+                *s_next = p.nwarps;
+            }
+            mbar_wait(mbar, phase);
+            phase ^= 1;
+            S = s_slab;
+        } else if (threadIdx.x == 0) {
+            *s_next = p.nwarps;
+        }
+        __syncthreads();
+        const double *T1 = p.T1 ? p.T1 + (size_t)dir * p.T1_stride : nullptr;
+        const double *T2 = p.T2 + (size_t)dir * p.T2_stride;
+
+        int v = warp;
+        while (v < tile.z) {
+            const long long vox = p.order ? (long long)p.order[tile.y + v] : (long long)tile.y + v;
+            // ---- signal
+            if (p.y_f64) {
+                const double *yg = (const double *)p.y + vox * m;
+                for (int i = lane; i < m; i += 32) ws.y[i] = yg[i];
+            } else {
+                const float *yg = (const float *)p.y + vox * m;
+                for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
+            }
+            __syncwarp();
+            int overflow = 0, support = 0;
+            double acc[NPL];
+
+            if (MODEL == MODEL_NODDI) {
+                const int n_wm = p.n_wm;
+                // stage 1: isotropic fraction (amico/models.pyx:911)
+                at_y<NPL, TS>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, acc, lane);
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = acc[s];
+                __syncwarp();
+                unsigned all = 0;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
+                overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
+                const double xiso = ws.x[n - 1];
+                const double xdot = p.exvivo ? ws.x[n - 2] : 0.0;
+                __syncwarp();
+                // stage 2: support selection on the normalised DWI rows (:914-926)
+                for (int jj = lane; jj < p.dc; jj += 32) {
+                    int r = p.dwi_rows[jj];
+                    double v2 = ws.y[r] - xiso * (double)S[(size_t)r * n_pad + (n - 1)];
+                    if (p.exvivo) v2 = v2 - xdot * 1.0;
+                    ws.y2[jj] = v2 < 0.0 ? 0.0 : v2;
+                }
+                __syncwarp();
+                const double normX = seq_sumsq(ws.y2, p.dc);
+                at_y<NPL, TS>(S, n_pad, n_wm, p.dc, p.dwi_rows, ws.y2, p.norms, n_wm, p.norms_const, acc, lane);
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = acc[s];
+                __syncwarp();
+                overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, normX,
+                                           ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
+                // stage 3: debias on the support (:929-942)
+                unsigned allowed = 0;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) {
+                    int j = lane + 32 * s;
+                    bool on = (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n);
+                    allowed |= (on ? 1u : 0u) << s;
+                    support += __popc(__ballot_sync(FULL, on));
+                }
+                __syncwarp();
+                overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
+                // maps (:945-967)
+                double s_all = 0.0;
+                for_each_positive<NPL>(ws.x, n, lane, [&](int, double xj) { s_all += xj; });
+                s_all += 1e-16;
+                double s_wm = 0.0;
+                for_each_positive<NPL>(ws.x, n_wm, lane, [&](int, double xj) { s_wm += xj / s_all; });
+                s_wm += 1e-16;
+                double f1 = 0.0, f2 = 0.0, k1 = 0.0;
+                for_each_positive<NPL>(ws.x, n_wm, lane, [&](int j, double xj) {
+                    float ic = p.icvf[j];
+                    f1 += (double)ic * xj / s_all / s_wm;
+                    f2 += (double)((float)(1.0 - (double)ic)) * xj / s_all / s_wm;
+                    k1 += (double)p.kappa[j] * xj / s_all / s_wm;
+                });
+                const double ndi = f1 / (f1 + f2 + 1e-16);
+                const double odi = 2.0 / 3.14159265358979323846 * atan2(1.0, k1);
+                const double fwf = ws.x[n - 1] / s_all;
+                if (lane == 0) {
+                    double *e = p.est + vox * p.n_maps;
+                    e[0] = ndi; e[1] = odi; e[2] = fwf;
+                    if (p.exvivo) e[3] = ws.x[n - 2] / s_all;
+                    if (p.flags & FLAG_EXTRA) {
+                        double tf = 1.0 - fwf;
+                        p.extra[2 * vox] = ndi * tf;
+                        p.extra[2 * vox + 1] = odi * tf;
+                    }
+                }
+            } else {
+                // single elastic-net fit on the full dictionary (:615, :1238, :1569)
+                const double normX = seq_sumsq(ws.y, m);
+                at_y<NPL, TS>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, acc, lane);
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = acc[s];
+                __syncwarp();
+                overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n, m < n ? m : n, p.lambda1, ws.dtr, normX, ws.mat, ws.u,
+                                           ws.gs, ws.P, ws.x, lane, nullptr);
+                for_each_positive<NPL>(ws.x, n, lane, [&](int, double) { ++support; });
+                if (MODEL == MODEL_FREEWATER) {
+                    double xs = 0.0, xp = 0.0;
+                    for_each_positive<NPL>(ws.x, n, lane, [&](int j, double xj) { xs += xj; if (j < p.n_perp) xp += xj; });
+                    xs += 1e-16;
+                    const double vv = xp / xs;
+                    if (lane == 0) {
+                        double *e = p.est + vox * p.n_maps;
+                        e[0] = vv; e[1] = 1.0 - vv;
+                        if (p.mouse) { e[2] = ws.x[p.n_perp] / xs; e[3] = ws.x[p.n_perp + 1] / xs; }
+                    }
+                } else if (MODEL == MODEL_CZB) {
+                    double f1 = 0.0, f2 = 0.0, aa = 0.0;
+                    for_each_positive<NPL>(ws.x, p.n_rs + p.n_perp, lane, [&](int j, double xj) { if (j < p.n_rs) f1 += xj; else f2 += xj; });
+                    f2 += 1e-16;
+                    const double vv = f1 / (f1 + f2 + 1e-16);
+                    f1 += 1e-16;
+                    for_each_positive<NPL>(ws.x, p.n_rs, lane, [&](int j, double xj) { aa += p.Rs[j] * xj; });
+                    aa = 1e6 * 2.0 * aa / f1;
+                    const double dd = (4.0 * vv) / (3.14159265358979323846 * (aa * aa) + 1e-16);
+                    if (lane == 0) {
+                        double *e = p.est + vox * 3;
+                        e[0] = vv; e[1] = aa; e[2] = dd;
+                    }
+                } else {  // SANDI (:1570-1611): un-normalise, then group sums
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        int j = lane + 32 * s;
+                        if (j < n) ws.x[j] = ws.x[j] * p.sandi_norms[j];
+                    }
+                    __syncwarp();
+                    const int n_rs = p.n_rs, n_in = p.n_in;
+                    double xs = 0, sph = 0, stk = 0, iso = 0, Rsoma = 0, Din = 0, De = 0;
+                    for_each_positive<NPL>(ws.x, n, lane, [&](int j, double xj) {
+                        xs += xj;
+                        if (j < n_rs) sph += xj;
+                        else if (j < n_rs + n_in) stk += xj;
+                        else iso += xj;
+                    });
+                    xs += 1e-16;
+                    for_each_positive<NPL>(ws.x, n, lane, [&](int j, double xj) {
+                        if (j < n_rs) Rsoma += p.Rs[j] * xj;
+                        else if (j < n_rs + n_in) Din += p.d_in[j - n_rs] * xj;
+                        else De += p.d_isos[j - n_rs - n_in] * xj;
+                    });
+                    if (lane == 0) {
+                        double *e = p.est + vox * 6;
+                        e[0] = sph / xs; e[1] = stk / xs; e[2] = iso / xs;
+                        sph += 1e-16; stk += 1e-16; iso += 1e-16;
+                        e[3] = 1e6 * Rsoma / sph; e[4] = 1e3 * Din / stk; e[5] = 1e3 * De / iso;
+                    }
+                }
+            }
+            __syncwarp();
+            if (p.support_out && lane == 0) p.support_out[vox] = support;
+            if (p.coeff_out)
+                for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
+            // FreeWater corrected DWI (:1263-1274) -- before fit_errors destroys ws.y? no: errors first use y.
+            if (MODEL == MODEL_FREEWATER && (p.flags & FLAG_EXTRA)) {
+                for (int i = lane; i < m; i += 32) {
+                    double fw = 0.0;
+                    for (int k = n - p.n_iso; k < n; ++k) fw = madd(fw, (double)S[(size_t)i * n_pad + k], ws.x[k]);
+                    double cv = ws.y[i] - fw;
+                    p.extra[vox * m + i] = cv < 0.0 ? 0.0 : cv;
+                }
+                __syncwarp();
+            }
+            if (p.flags & (FLAG_RMSE | FLAG_NRMSE))
+                fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
+                                    p.nrmse ? p.nrmse + vox : nullptr, lane);
+            if (overflow) ++n_overflow;
+            __syncwarp();
+            // next voxel of this tile
+            int nv = 0;
+            if (lane == 0) nv = atomicAdd(s_next, 1);
+            v = __shfl_sync(FULL, nv, 0);
+        }
+        __syncthreads();
+    }
+    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
+}
+
+}  // namespace amx

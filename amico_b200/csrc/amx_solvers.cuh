@@ -1,0 +1,404 @@
+// Warp-per-voxel solvers.  One warp owns one voxel; lane l owns atoms l, l+32, ... (NPL per lane)
+// and active-set position l.  Per-direction Gram tables live in global memory (L2-resident).
+//
+//  warp_lars : the `lasso` the reference calls (cyspams.interfaces.lasso -- SPAMS LARS/homotopy,
+//              mode PENALTY, pos=true; call sites amico/models.pyx:615, 926, 1238, 1569).  Same
+//              path, same operation order and un-fused arithmetic as the CPU restatement in
+//              oracle/amico_oracle.c::lars_core, so results agree bit for bit given equal inputs.
+//  warp_nnls : the `nnls` the reference calls (Lawson-Hanson; amico/models.pyx:911, 940) run in
+//              Gram space: same pivoting (largest dual enters, ratio test leaves, candidate
+//              independence + positivity test) with the passive-set system solved through a
+//              Cholesky factor of H_PP instead of a Householder QR of A_P.
+#pragma once
+#include "amx_warp.cuh"
+#include <math.h>
+
+namespace amx {
+
+// ------------------------------------------------------------------------------------------------
+// Triangular solves against the packed lower factor Lp (row-major packed, diagonal reciprocals rd).
+// Lane a holds element a of the right-hand side / the result (0 beyond np).
+__device__ __forceinline__ double fwd_subst(const double *Lp, const double *rd, int np, double t, int lane)
+{
+    double v = 0.0;
+    for (int k = 0; k < np; ++k) {
+        double vk = shfl(t, k) * rd[k];
+        if (lane == k) v = vk;
+        if (lane > k && lane < np) t = fma(-Lp[tri(lane, k)], vk, t);
+    }
+    return v;
+}
+
+__device__ __forceinline__ double back_subst(const double *Lp, const double *rd, int np, double t, int lane)
+{
+    double s = 0.0;
+    for (int k = np - 1; k >= 0; --k) {
+        double sk = shfl(t, k) * rd[k];
+        if (lane == k) s = sk;
+        if (lane < k) t = fma(-Lp[tri(k, lane)], sk, t);
+    }
+    return s;
+}
+
+struct NnlsStat {
+    int outer, inner, removed;
+};
+
+// min 1/2 x'Tx - c'x, x >= 0 over the atoms whose bit is set in `allowed` (bit s of lane l <-> atom
+// l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays.  mcap = number of rows of the
+// least-squares system (the reference stops growing the passive set at m).  Returns overflow flag.
+template <int NPL>
+__device__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
+                         unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st)
+{
+    int np = 0, iter = 0, overflow = 0;
+    unsigned inP = 0;
+    double xp = 0.0, zl = 0.0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) x[lane + 32 * s] = 0.0;
+    __syncwarp();
+    for (;;) {
+        if (np >= mcap) break;
+        if (np >= LC) { overflow = 1; break; }
+        // dual w = c - T[:,P] x_P on the zero set
+        double wl[NPL];
+        unsigned valid = 0;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int j = lane + 32 * s;
+            bool ok = (j < n) && ((allowed >> s) & 1u) && !((inP >> s) & 1u);
+            valid |= (ok ? 1u : 0u) << s;
+            wl[s] = ok ? c[j] : 0.0;
+        }
+        for (int k = 0; k < np; ++k) {
+            int pk = P[k];
+            double xk = x[pk];
+            const double *row = T + (size_t)pk * ldT;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s)
+                if ((valid >> s) & 1u) wl[s] = fma(-row[lane + 32 * s], xk, wl[s]);
+        }
+        // candidate selection
+        int j = -1;
+        double v = 0.0, d2 = 0.0, znew = 0.0;
+        for (;;) {
+            double bv = 0.0;
+            int bj = -1;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s)
+                if (((valid >> s) & 1u) && wl[s] > bv) { bv = wl[s]; bj = lane + 32 * s; }
+            warp_argmax(bv, bj);
+            if (bj < 0 || !(bv > 0.0)) { j = -1; break; }
+            j = bj;
+            double t = (lane < np) ? T[(size_t)P[lane] * ldT + j] : 0.0;
+            v = fwd_subst(Lp, rd, np, t, lane);
+            double vv = warp_sum(lane < np ? v * v : 0.0);
+            double vz = warp_sum(lane < np ? v * zl : 0.0);
+            d2 = T[(size_t)j * ldT + j] - vv;
+            bool ok = false;
+            if (d2 > 0.0) {
+                double unorm = sqrt(vv), dd = sqrt(d2);
+                double tt = unorm + dd * 0.01;
+                if (tt - unorm > 0.0) {
+                    znew = (c[j] - vz) / dd;
+                    ok = znew > 0.0;
+                }
+            }
+            if (ok) break;
+            // reject: drop j from this round's candidates
+            if ((j & 31) == lane) {
+#pragma unroll
+                for (int s = 0; s < NPL; ++s)
+                    if (s == (j >> 5)) wl[s] = 0.0;
+            }
+        }
+        if (j < 0) break;
+        // move j to the passive set: append a row to the factor
+        {
+            double dd = sqrt(d2);
+            if (lane < np) Lp[tri(np, lane)] = v;
+            if (lane == np) {
+                Lp[tri(np, np)] = dd;
+                rd[np] = 1.0 / dd;
+                P[np] = j;
+                zl = znew;
+                xp = 0.0;
+            }
+            if ((j & 31) == lane) inP |= 1u << (j >> 5);
+            ++np;
+            if (st) ++st->outer;
+        }
+        __syncwarp();
+        // secondary loop
+        double s = 0.0;
+        for (;;) {
+            if (++iter > itmax) goto done;
+            if (st) ++st->inner;
+            s = back_subst(Lp, rd, np, (lane < np) ? zl : 0.0, lane);
+            bool neg = (lane < np) && (s <= 0.0);
+            if (!__any_sync(FULL, neg)) break;
+            double tmin = INFINITY;
+            int cand = -1;
+            if (neg) {
+                double tt = -xp / (s - xp);
+                if (tt < 2.0) { tmin = tt; cand = lane; }
+            }
+            warp_argmin<true>(tmin, cand);
+            if (cand < 0) break;
+            if (lane < np) xp = fma(tmin, s - xp, xp);
+            if (lane == cand) xp = 0.0;
+            bool keep = (lane < np) && (xp > 0.0);
+            unsigned kmask = __ballot_sync(FULL, keep);
+            int myP = (lane < np) ? P[lane] : 0;
+            if (lane < np && !keep) x[myP] = 0.0;
+            int nnew = __popc(kmask);
+            if (st) st->removed += np - nnew;
+            unsigned src = __fns(kmask, 0, lane + 1);
+            bool has = lane < nnew;
+            int srcl = has ? (int)src : 0;
+            double xs = shfl(xp, srcl);
+            int ps = __shfl_sync(FULL, myP, srcl);
+            __syncwarp();
+            if (has) P[lane] = ps;
+            xp = has ? xs : 0.0;
+            np = nnew;
+            __syncwarp();
+            inP = 0;
+            for (int k = 0; k < np; ++k) {
+                int a = P[k];
+                if ((a & 31) == lane) inP |= 1u << (a >> 5);
+            }
+            if (np == 0) break;
+            // rebuild the factor and z = L^-1 c_P row by row
+            zl = 0.0;
+            for (int i = 0; i < np; ++i) {
+                int pi = P[i];
+                double t = (lane < i) ? T[(size_t)pi * ldT + P[lane]] : 0.0;
+                double vr = fwd_subst(Lp, rd, i, t, lane);
+                double vv = warp_sum(lane < i ? vr * vr : 0.0);
+                double vz = warp_sum(lane < i ? vr * zl : 0.0);
+                double dd2 = T[(size_t)pi * ldT + pi] - vv;
+                double dd = sqrt(dd2 > 0.0 ? dd2 : 1e-300);
+                if (lane < i) Lp[tri(i, lane)] = vr;
+                if (lane == i) {
+                    Lp[tri(i, i)] = dd;
+                    rd[i] = 1.0 / dd;
+                    zl = (c[pi] - vz) / dd;
+                }
+                __syncwarp();
+            }
+        }
+        if (lane < np) {
+            xp = s;
+            x[P[lane]] = s;
+        }
+        __syncwarp();
+    }
+done:
+    if (lane < np) x[P[lane]] = xp;
+    __syncwarp();
+    return overflow;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Non-negative LARS on G = T + ridge*I (ridge = max(lambda2, 1e-10)), correlations DtR (destroyed),
+// following oracle/amico_oracle.c::lars_core step by step.  Ltrue = min(rows, K) of the underlying
+// least-squares system.  x: per-warp shared output (exact zeros off-support).
+// Mi: packed upper inverse of G_SS; u, gs: LC doubles; ind: LC ints.
+__device__ __forceinline__ double sym_at(const double *Mi, int r, int c) { return Mi[r <= c ? tri(c, r) : tri(r, c)]; }
+
+template <int NPL>
+__device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in, int K, int Ltrue, double lambda1,
+                         double *DtR, double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane,
+                         int *steps_out)
+{
+    const double ridge = ridge_in > 1e-10 ? ridge_in : 1e-10;
+    int L = Ltrue < K ? Ltrue : K;
+    int overflow = 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) x[lane + 32 * s] = 0.0;
+    __syncwarp();
+    if (steps_out) *steps_out = 0;
+    if (L <= 0) return 0;
+    int cur;
+    {
+        double bv = 0.0;
+        int bi = -1;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            if (k < K) {
+                double v = DtR[k];
+                if (bi < 0 || v > bv) { bv = v; bi = k; }
+            }
+        }
+        warp_argmax(bv, bi);
+        if (fabs(bv) < lambda1) return 0;
+        cur = bi;
+    }
+    int newAtom = 1, iter = 0, na = 0;
+    double coef_l = 0.0;
+    int ind_l = -1;
+    unsigned act = 0;
+    const int length_path = 4 * L;
+    for (int i = 0; i < L; ++i) {
+        if (i < 0) break;  // the CPU path would read ind[-1] here; cannot happen with pos=true
+        ++iter;
+        if (newAtom) {
+            if (i >= LC) { overflow = 1; na = i; break; }
+            if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
+            if ((cur & 31) == lane) act |= 1u << (cur >> 5);
+            __syncwarp();
+            double g = 0.0;
+            if (lane <= i) {
+                g = T[(size_t)cur * ldT + ind_l];
+                if (lane == i) g = __dadd_rn(g, ridge);
+                gs[lane] = g;
+            }
+            __syncwarp();
+            if (i == 0) {
+                if (lane == 0) Mi[0] = 1.0 / g;
+            } else {
+                double ur = 0.0;
+                if (lane < i) {
+                    for (int c = 0; c < i; ++c) ur = madd(ur, sym_at(Mi, lane, c), gs[c]);
+                    u[lane] = ur;
+                }
+                __syncwarp();
+                double dot = 0.0;
+                for (int j = 0; j < i; ++j) dot = madd(dot, u[j], gs[j]);
+                double schur = 1.0 / __dsub_rn(gs[i], dot);
+                if (lane < i) {
+                    double su = __dmul_rn(schur, ur);
+                    for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = __dadd_rn(Mi[tri(k, lane)], __dmul_rn(su, u[k]));
+                    Mi[tri(i, lane)] = __dmul_rn(-schur, ur);
+                }
+                if (lane == i) Mi[tri(i, i)] = schur;
+            }
+            __syncwarp();
+        }
+        na = i + 1;
+        // path direction u = invGs * sign(DtR_S)
+        if (lane <= i) gs[lane] = DtR[ind_l] > 0.0 ? 1.0 : -1.0;
+        __syncwarp();
+        double ul = 0.0;
+        if (lane <= i) {
+            for (int c = 0; c <= i; ++c) ul = madd(ul, sym_at(Mi, lane, c), gs[c]);
+            u[lane] = ul;
+        }
+        __syncwarp();
+        // largest step before an active coefficient crosses zero (last index wins ties)
+        double step_max = INFINITY;
+        int fz = -1;
+        if (lane <= i) {
+            double r = -coef_l / ul;
+            if (r > 0.0) { step_max = r; fz = lane; }
+        }
+        warp_argmin<false>(step_max, fz);
+        if (fz < 0) step_max = INFINITY;
+        const double cc = fabs(DtR[ind[0]]);
+        // correlation slopes  (T + ridge I)[:, S] u
+        double sl[NPL];
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
+        for (int j = 0; j <= i; ++j) {
+            int aj = ind[j];
+            double uj = u[j];
+            const double *row = T + (size_t)aj * ldT;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) {
+                int k = lane + 32 * s;
+                if (k < K) {
+                    double gv = row[k];
+                    if (k == aj) gv = __dadd_rn(gv, ridge);
+                    sl[s] = madd(sl[s], gv, uj);
+                }
+            }
+        }
+        // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index
+        double tl[NPL];
+        double bt = INFINITY;
+        int bk = -1;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            tl[s] = INFINITY;
+            if (k < K) {
+                if (!((act >> s) & 1u) && sl[s] < 1.0) tl[s] = __ddiv_rn(__dsub_rn(cc, DtR[k]), __dsub_rn(1.0, sl[s]));
+                double at = fabs(tl[s]);
+                if (bk < 0 || at < bt) { bt = at; bk = k; }
+            }
+        }
+        warp_argmin<true>(bt, bk);
+        double step;
+        {
+            double mine = 0.0;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s)
+                if (s == (bk >> 5)) mine = tl[s];
+            step = shfl(mine, bk & 31);
+        }
+        cur = bk;
+        double coeff1 = 0.0, coeff2 = 0.0;
+        for (int j = 0; j <= i; ++j) {
+            double uj = u[j];
+            coeff1 = __dadd_rn(coeff1, DtR[ind[j]] > 0.0 ? uj : -uj);
+        }
+        for (int j = 0; j <= i; ++j) coeff2 = madd(coeff2, DtR[ind[j]], u[j]);
+        const double step_max2 = __dsub_rn(cc, lambda1);
+        step = fmin(fmin(step, step_max2), step_max);
+        if (step == INFINITY) break;
+        if (lane <= i) {
+            coef_l = madd(coef_l, step, ul);
+            if (coef_l < 0.0) coef_l = 0.0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            if (k < K) DtR[k] = __dsub_rn(DtR[k], __dmul_rn(step, sl[s]));
+        }
+        normX = __dadd_rn(normX, __dsub_rn(__dmul_rn(__dmul_rn(coeff1, step), step), __dmul_rn(__dmul_rn(2.0, coeff2), step)));
+        __syncwarp();
+        if (step == step_max) {
+            // remove active position z: shrink ind/coeffs and downdate the inverse
+            const int z = fz;
+            const int az = ind[z];
+            const double schur_r = Mi[tri(z, z)];
+            double uk = 0.0;
+            if (lane < i) uk = (lane < z) ? Mi[tri(z, lane)] : Mi[tri(lane + 1, z)];
+            __syncwarp();
+            if (lane < i) u[lane] = uk;
+            double cn = __shfl_down_sync(FULL, coef_l, 1);
+            int in_ = __shfl_down_sync(FULL, ind_l, 1);
+            if (lane >= z && lane < i) { coef_l = cn; ind_l = in_; }
+            if (lane == i) { coef_l = 0.0; ind_l = -1; }
+            if ((az & 31) == lane) act &= ~(1u << (az >> 5));
+            for (int j = z; j < i; ++j) {  // new column j <- old column j+1 without row z
+                double mv = 0.0;
+                if (lane <= j) mv = Mi[tri(j + 1, lane < z ? lane : lane + 1)];
+                __syncwarp();
+                if (lane <= j) Mi[tri(j, lane)] = mv;
+                __syncwarp();
+            }
+            if (lane <= i) ind[lane] = ind_l;
+            __syncwarp();
+            if (lane < i)
+                for (int k = lane; k < i; ++k)
+                    Mi[tri(k, lane)] = __dsub_rn(Mi[tri(k, lane)], __ddiv_rn(__dmul_rn(uk, u[k]), schur_r));
+            __syncwarp();
+            newAtom = 0;
+            na = i;
+            i -= 2;
+        } else {
+            newAtom = 1;
+        }
+        if (iter >= length_path - 1 || fabs(step) < 1e-15 || step == step_max2 || normX < 1e-15 || i == L - 1) break;
+    }
+    if (lane < na && ind_l >= 0) x[ind_l] = coef_l;
+    __syncwarp();
+    if (steps_out) *steps_out = iter;
+    return overflow;
+}
+
+}  // namespace amx
