@@ -1,0 +1,286 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against
+
+* the CPU oracle (oracle/amico_oracle.c) on the same seeded inputs,
+* the committed golden fixtures produced by the reference's own Cython glue (tests/golden/),
+* size-independent properties at the benchmark's full size.
+
+Bars: LUT indices and every lasso-only model (FreeWater, CylinderZeppelinBall, SANDI) BIT-EXACT against the
+oracle (same algorithm, same operation order); NODDI (its two NNLS stages run in Gram space)
+within the north-star tolerance |gpu - ref| <= 1e-4 * max(|ref|, 1e-3) on >= 99.9 % of the voxels.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from amico_b200 import synth
+from amico_b200.plan import Plan
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+TOL = 1e-4  # north-star: output maps within 1e-4 relative of the reference
+
+
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def rel_err(got, ref):
+    return np.abs(got - ref) / np.maximum(np.abs(ref), 1e-3)
+
+
+def pass_fraction(got, ref, tol=TOL):
+    return float((rel_err(got, ref) <= tol).all(axis=1).mean())
+
+
+def make_plan(P):
+    mid = "FreeWater" if P.model.startswith("FreeWater") else P.model
+    return Plan(mid, P.KERNELS, P.htable, P.params, dwi_idx=P.scheme.dwi_idx)
+
+
+def gpu_fit(P, **kw):
+    l1, l2 = orc().DEFAULT_LAMBDAS[P.model]
+    l1, l2 = kw.pop("lambda1", l1), kw.pop("lambda2", l2)
+    dirs = None if P.model == "SANDI" else np.array(P.DIRs, dtype=np.float64)
+    with make_plan(P) as plan:
+        res = plan.fit(P.y, dirs, l1, l2, **kw)
+        res["_counters"] = plan.last_counters()
+    res["_dirs"] = dirs
+    return res
+
+
+# ----------------------------------------------------------------------------------------------- LUT index
+def test_lut_index_bit_exact():
+    P = synth.make_problem(1, n_vox=8)
+    rng = np.random.default_rng(7)
+    v = rng.standard_normal((1_000_000, 3))
+    v /= np.linalg.norm(v, axis=1, keepdims=True)
+    edge = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1], [0, -0.0, 1], [1, -0.0, 0],
+                     [-1, -0.0, 0], [0, 0, 0], [1e-300, 1e-300, 1], [-1e-17, 0, 1], [0.6, -0.8, 0], [-0.6, 0.8, 0]], dtype=np.float64)
+    dirs = np.vstack([edge, v])
+    ref = orc().lut_indices(dirs, P.htable)
+    ref_flipped = dirs.copy()
+    neg = ref_flipped[:, 1] < 0
+    ref_flipped[neg] *= -1
+    with make_plan(P) as plan:
+        d = dirs.copy()
+        got = plan.lut_indices(d)
+    assert np.array_equal(got, ref)
+    assert np.array_equal(d, ref_flipped)  # hemisphere flip written back in place (lut.pyx:335-338)
+
+
+def test_lut_out_of_range_raises():
+    P = synth.make_problem(1, n_vox=64)
+    dirs = np.array(P.DIRs, dtype=np.float64)
+    dirs[17] = [np.nan, 0.3, 0.1]
+    with make_plan(P) as plan:
+        with pytest.raises(RuntimeError, match=r'"amico.lut.dir_to_lut_idx" index out of bounds'):
+            plan.fit(P.y, dirs, 0.0, 1e-3)
+        idx = plan.lut_indices(np.array(dirs))
+    assert idx[17] == -1
+
+
+# ----------------------------------------------------------------------------------------------- lasso-only models
+@pytest.mark.parametrize("cfg,model,n_vox", [(1, "FreeWater", 512), (1, "FreeWaterMouse", 3000), (5, "CylinderZeppelinBall", 4000),
+                                              (4, "SANDI", 20000)])
+def test_lasso_models_bit_exact_vs_oracle(cfg, model, n_vox):
+    P = synth.make_problem(cfg, n_vox=n_vox, model=model)
+    ref = orc().fit_problem(P, rmse=True, nrmse=True, extra=True, return_debug=True, nthreads=os.cpu_count())
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=True, debug=True)
+    assert got["_counters"]["launches"] >= 1 and got["_counters"]["overflow_voxels"] == 0
+    assert np.array_equal(got["lut"], ref["lut"]) or model == "SANDI"
+    assert np.array_equal(got["estimates"], ref["estimates"])
+    assert np.array_equal(got["rmse"], ref["rmse"])
+    assert np.array_equal(got["nrmse"], ref["nrmse"])
+    if "y_corrected" in ref:
+        assert np.array_equal(got["y_corrected"], ref["y_corrected"])
+    if model != "SANDI":
+        assert np.array_equal(got["_dirs"], ref["dirs"])
+
+
+# ----------------------------------------------------------------------------------------------- NODDI
+def test_noddi_vs_oracle():
+    P = synth.make_problem(2, n_vox=30000)
+    ref = orc().fit_problem(P, rmse=True, nrmse=True, extra=True, return_debug=True, nthreads=os.cpu_count())
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=True, debug=True)
+    assert got["_counters"]["overflow_voxels"] == 0
+    assert np.array_equal(got["lut"], ref["lut"])
+    frac = pass_fraction(got["estimates"], ref["estimates"])
+    sup = float((got["support"] == ref["support"]).mean())
+    rel = rel_err(got["estimates"], ref["estimates"])
+    print(f"NODDI pass fraction {frac:.5f}, support equality {sup:.5f}, p50 {np.median(rel):.2e}, p99 {np.percentile(rel, 99):.2e}")
+    assert frac >= 0.999
+    assert sup >= 0.999
+    ok = (rel <= TOL).all(axis=1)
+    assert np.abs(got["rmse"][ok] - ref["rmse"][ok]).max() < 1e-6
+    assert np.abs(got["nrmse"][ok] - ref["nrmse"][ok]).max() < 1e-6
+    assert np.abs(got["estimates_mod"][ok] - ref["estimates_mod"][ok]).max() < 1e-4
+
+
+def test_noddi_exvivo_vs_oracle():
+    P = synth.make_problem(2, n_vox=4000, seed=5)
+    P.params = dict(P.params, isExvivo=True)
+    ref = orc().fit_problem(P, nthreads=os.cpu_count())
+    got = gpu_fit(P)
+    assert got["estimates"].shape == (4000, 4)
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
+
+
+def test_noddi_known_answers():
+    """Noise-free voxels y = (1-f) A[:, j] + f a_iso must give NDI = IC_VFs[j % 12], ODI = IC_ODs[j // 12], FWF = f
+    (atom order: amico/models.pyx:773-780); an all-zero voxel gives (0, 1, 0) (models.pyx:945-965)."""
+    P = synth.make_problem(2, n_vox=600, seed=3)
+    K = P.KERNELS
+    lut = synth.lut_index_numpy(P.DIRs, P.htable)
+    rng = np.random.default_rng(1)
+    j = rng.integers(0, 144, 600)
+    f = rng.uniform(0.05, 0.6, 600)
+    y = (1 - f)[:, None] * K["wm"][j, lut, :].astype(np.float64) + f[:, None] * K["iso"].astype(np.float64)[None, :]
+    y[0] = 0.0
+    P.y = y  # float64 input path
+    got = gpu_fit(P)
+    ref = orc().fit_problem(P)
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.99
+    e = got["estimates"]
+    assert np.allclose(e[0], [0.0, 1.0, 0.0])
+    vf, od = P.params["IC_VFs"][j % 12], P.params["IC_ODs"][j // 12]
+    good = (np.abs(e[1:, 0] - vf[1:]) < 0.02) & (np.abs(e[1:, 1] - od[1:]) < 0.02) & (np.abs(e[1:, 2] - f[1:]) < 0.01)
+    assert good.mean() > 0.9
+
+
+# ----------------------------------------------------------------------------------------------- golden fixtures
+@pytest.mark.parametrize("name,cfg,model,n_vox,seed", [("freewater_cfg1", 1, "FreeWater", 512, None), ("freewater_mouse", 1, "FreeWaterMouse", 256, 11),
+                                                       ("noddi_cfg2", 2, "NODDI", 384, None), ("sandi_cfg4", 4, "SANDI", 512, None),
+                                                       ("czb_cfg5", 5, "CylinderZeppelinBall", 320, None)])
+def test_golden_reference_glue(name, cfg, model, n_vox, seed):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    P = synth.make_problem(cfg, n_vox=n_vox, model=model, seed=seed)
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=model in ("NODDI", "FreeWater", "FreeWaterMouse"))
+    if model == "NODDI":
+        assert pass_fraction(got["estimates"], g["estimates"]) >= 0.995
+        assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
+    else:
+        for k in ("estimates", "rmse", "nrmse", "y_corrected"):
+            if k in g.files:
+                assert np.array_equal(got[k], g[k]), k
+
+
+# ----------------------------------------------------------------------------------------------- edge cases
+def test_empty_and_tiny_inputs():
+    P = synth.make_problem(1, n_vox=3)
+    with make_plan(P) as plan:
+        r = plan.fit(P.y[:0], np.zeros((0, 3)), 0.0, 1e-3)
+        assert r["estimates"].shape == (0, 2)
+        ref = orc().fit_problem(P)
+        r = plan.fit(P.y, np.array(P.DIRs), 0.0, 1e-3)
+        assert np.array_equal(r["estimates"], ref["estimates"])
+        one = plan.fit(P.y[:1], np.array(P.DIRs[:1]), 0.0, 1e-3)
+        assert np.array_equal(one["estimates"], ref["estimates"][:1])
+
+
+def test_zero_signal_and_regularisation_sweep():
+    P = synth.make_problem(1, n_vox=400, seed=9)
+    P.y[::7] = 0.0
+    for l1, l2 in ((0.0, 1e-3), (0.05, 1e-3), (0.5, 0.0), (0.0, 4.0), (10.0, 1e-3)):
+        ref = orc().fit_problem(P, lambda1=l1, lambda2=l2)
+        got = gpu_fit(P, lambda1=l1, lambda2=l2)
+        assert np.array_equal(got["estimates"], ref["estimates"]), (l1, l2)
+
+
+def test_single_b0_scheme_rows():
+    """m == 1 + dwi_count selects rows 1..m-1 for NODDI stage 2 (amico/models.pyx:916-918)."""
+    scheme = synth.Scheme(np.vstack([np.zeros((1, 4)), np.hstack([synth.fibonacci_sphere(30), np.full((30, 1), 1000.0)]),
+                                     np.hstack([synth.fibonacci_sphere(30, 0.4), np.full((30, 1), 2500.0)])]))
+    lut = synth.lut_directions(500)
+    ht = synth.build_htable(lut)
+    K, p = synth.make_kernels("NODDI", scheme, lut)
+    y, dirs = synth.make_voxels("NODDI", K, ht, 3000, 42)
+    P = synth.Problem(0, "NODDI", scheme, lut, ht, K, p, y, dirs)
+    ref = orc().fit_problem(P, nthreads=os.cpu_count())
+    got = gpu_fit(P)
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
+
+
+def test_device_tensor_path_matches_host_path():
+    import torch
+    P = synth.make_problem(2, n_vox=5000, seed=21)
+    l1, l2 = orc().DEFAULT_LAMBDAS["NODDI"]
+    with make_plan(P) as plan:
+        host = plan.fit(P.y, np.array(P.DIRs), l1, l2, rmse=True)
+        y = torch.from_numpy(P.y).cuda()
+        d = torch.from_numpy(np.array(P.DIRs)).cuda()
+        dev = plan.fit(y, d, l1, l2, rmse=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(dev["estimates"].cpu().numpy(), host["estimates"])
+        assert np.array_equal(dev["rmse"].cpu().numpy(), host["rmse"])
+        # float64 signal gives the same maps as its float32 original
+        dev64 = plan.fit(y.double(), d, l1, l2)
+        assert np.array_equal(dev64["estimates"].cpu().numpy(), host["estimates"])
+
+
+def test_model_plugin_surface_end_to_end():
+    """The drop-in classes: model.fit(evaluation) with the attributes the reference's Evaluation provides."""
+    from amico_b200 import models
+
+    class Evaluation:
+        def __init__(self, P, cfg):
+            self.y = P.y.astype(np.float64)
+            self.DIRs = None if P.DIRs is None else np.array(P.DIRs, dtype=np.float64)
+            self.htable, self.KERNELS, self.nthreads, self._cfg = P.htable, P.KERNELS, 4, cfg
+
+        def get_config(self, k):
+            return self._cfg.get(k)
+
+    P = synth.make_problem(2, n_vox=2000, seed=2)
+    ev = Evaluation(P, {"doComputeRMSE": True, "doComputeNRMSE": False, "doSaveModulatedMaps": True})
+    m = models.NODDI()
+    m.scheme = P.scheme
+    m.set_solver()
+    before = ev.DIRs.copy()
+    res = m.fit(ev)
+    ref = orc().fit_problem(P, rmse=True, extra=True, return_debug=True)
+    assert set(res) == {"estimates", "rmse", "estimates_mod"}
+    assert res["estimates"].dtype == np.float64 and res["estimates"].shape == (2000, 3)
+    assert pass_fraction(res["estimates"], ref["estimates"]) >= 0.998
+    # contiguous float64 DIRs are flipped in place, exactly like the reference (SURVEY 8a quirk i)
+    assert np.array_equal(ev.DIRs, ref["dirs"]) and not np.array_equal(ev.DIRs, before)
+
+    P = synth.make_problem(4, n_vox=1000)
+    ev = Evaluation(P, {})
+    s = models.SANDI()
+    s.set_solver()
+    assert np.array_equal(s.fit(ev)["estimates"], orc().fit_problem(P)["estimates"])
+
+
+# ----------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_properties():
+    """BASELINE cfg2 at full size (1,048,576 voxels): invariants that need no oracle.
+
+    * permutation equivariance: fitting a shuffled volume gives the shuffled maps (binning by LUT index, tile
+      scheduling and atomics must not leak between voxels) -- bit-exact;
+    * hemisphere symmetry: d and -d give identical maps;
+    * range: NDI, ODI, FWF in [0, 1]; no NaN; zero workspace overflows;
+    * a 20k sample agrees with the oracle.
+    """
+    import torch
+    n = 128 * 128 * 64
+    P = synth.make_problem(2, n_vox=n)
+    l1, l2 = orc().DEFAULT_LAMBDAS["NODDI"]
+    with make_plan(P) as plan:
+        y = torch.from_numpy(P.y).cuda()
+        d = torch.from_numpy(np.array(P.DIRs)).cuda()
+        a = plan.fit(y, d, l1, l2)["estimates"]
+        cnt = plan.last_counters()
+        assert cnt["overflow_voxels"] == 0
+        perm = torch.randperm(n, device="cuda", generator=torch.Generator(device="cuda").manual_seed(0))
+        b = plan.fit(y[perm].contiguous(), (-d[perm]).contiguous(), l1, l2)["estimates"]
+        torch.cuda.synchronize()
+        assert torch.equal(a[perm], b)
+        assert bool(torch.isfinite(a).all())
+        assert float(a.min()) >= 0.0 and float(a.max()) <= 1.0 + 1e-12
+        idx = np.arange(0, n, n // 20000)[:20000]
+        Q = synth.Problem(P.cfg, P.model, P.scheme, P.lut_dirs, P.htable, P.KERNELS, P.params, P.y[idx], P.DIRs[idx])
+        ref = orc().fit_problem(Q, nthreads=os.cpu_count())
+        assert pass_fraction(a.cpu().numpy()[idx], ref["estimates"]) >= 0.999
