@@ -56,11 +56,13 @@ __global__ void k_scan_bins(const int *hist, int ndirs, int tile_v, int *offs, i
     int per = (ndirs + nt - 1) / nt;
     int b0 = tid * per, b1 = min(ndirs, b0 + per);
     int sum = 0, tsum = 0;
+    #pragma unroll 1
     for (int d = b0; d < b1; ++d) { sum += hist[d]; tsum += (hist[d] + tile_v - 1) / tile_v; }
     s_part[tid] = sum; s_tpart[tid] = tsum;
     __syncthreads();
     if (tid == 0) {
         int a = 0, t = 0;
+        #pragma unroll 1
         for (int i = 0; i < nt; ++i) {
             int v = s_part[i], tv = s_tpart[i];
             s_part[i] = a; s_tpart[i] = t;
@@ -71,6 +73,7 @@ __global__ void k_scan_bins(const int *hist, int ndirs, int tile_v, int *offs, i
     }
     __syncthreads();
     int a = s_part[tid], t = s_tpart[tid];
+    #pragma unroll 1
     for (int d = b0; d < b1; ++d) {
         offs[d] = a; cursor[d] = a; tile_offs[d] = t;
         a += hist[d]; t += (hist[d] + tile_v - 1) / tile_v;
@@ -92,6 +95,7 @@ __global__ void k_tiles(const int *hist, const int *offs, const int *tile_offs, 
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndirs) return;
     int c = hist[d], o = offs[d], t = tile_offs[d];
+    #pragma unroll 1
     for (int s = 0; s < c; s += tile_v, ++t) tiles[t] = make_int4(d, o + s, min(tile_v, c - s), 0);
 }
 
@@ -114,6 +118,7 @@ __global__ void k_build_slab(const float *__restrict__ rot0, int n0, const float
     int d = blockIdx.x;
     float *S = slab + (size_t)d * slab_stride;
     int n = n0 + n1 + (with_dot ? 1 : 0) + n_iso;
+    #pragma unroll 1
     for (int e = threadIdx.x; e < n * m; e += blockDim.x) {
         int k = e / m, r = e - k * m;
         float v;
@@ -124,6 +129,7 @@ __global__ void k_build_slab(const float *__restrict__ rot0, int n0, const float
         S[(size_t)r * n_pad + k] = v;
     }
     // zero the padding columns so that no uninitialised value is ever staged
+    #pragma unroll 1
     for (int e = threadIdx.x; e < (n_pad - n) * m; e += blockDim.x) {
         int r = e / (n_pad - n), k = n + e % (n_pad - n);
         S[(size_t)r * n_pad + k] = 0.0f;
@@ -133,6 +139,7 @@ __global__ void k_build_slab(const float *__restrict__ rot0, int n0, const float
 // SANDI: column-major double (m x n) -> row-major [r][k] double slab
 __global__ void k_build_slab_f64(const double *__restrict__ A, int m, int n, int n_pad, double *slab)
 {
+    #pragma unroll 1
     for (int e = threadIdx.x; e < m * n_pad; e += blockDim.x) {
         int r = e / n_pad, k = e - r * n_pad;
         slab[e] = k < n ? A[(size_t)k * m + r] : 0.0;
@@ -150,10 +157,12 @@ __global__ void k_gram(const TS *__restrict__ slab, size_t slab_stride, int n_pa
     int d = blockIdx.x;
     const TS *S = slab + (size_t)d * slab_stride;
     double *Gd = G + (size_t)d * G_stride;
+    #pragma unroll 1
     for (int e = threadIdx.x + blockIdx.y * blockDim.x; e < K * K; e += blockDim.x * gridDim.y) {
         int i = e / K, j = e - i * K;
         if (j < i) continue;
         double s = 0.0;
+        #pragma unroll 1
         for (int rr = 0; rr < nrows; ++rr) {
             int r = rows ? rows[rr] : rr;
             double ai = (double)S[(size_t)r * n_pad + i], aj = (double)S[(size_t)r * n_pad + j];
@@ -220,7 +229,7 @@ __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_
 
 // acc[s] += sum_r S[row(r)][lane+32s] * scale * yv[r]   (sequential in r, un-fused: matches the CPU order)
 template <int NPL, typename TS>
-__device__ __forceinline__ void at_y(const TS *S, int n_pad, int n, int nrows, const int *__restrict__ rows, const double *yv,
+__device__ __noinline__ void at_y(const TS *S, int n_pad, int n, int nrows, const int *__restrict__ rows, const double *yv,
                                      const double *__restrict__ norms, int ldn, int norms_const, double (&acc)[NPL], int lane)
 {
     double nk[NPL];
@@ -250,6 +259,7 @@ __device__ __forceinline__ void at_y(const TS *S, int n_pad, int n, int nrows, c
 __device__ __forceinline__ double seq_sumsq(const double *v, int n)
 {
     double s = 0.0;
+    #pragma unroll 1
     for (int i = 0; i < n; ++i) s = madd(s, v[i], v[i]);
     return s;
 }
@@ -258,10 +268,11 @@ __device__ __forceinline__ double seq_sumsq(const double *v, int n)
 template <int NPL, typename F>
 __device__ __forceinline__ void for_each_positive(const double *x, int n, int lane, F f)
 {
-#pragma unroll
+#pragma unroll 1
     for (int s = 0; s < NPL; ++s) {
         int j = lane + 32 * s;
         unsigned mask = __ballot_sync(FULL, j < n && x[j] > 0.0);
+        #pragma unroll 1
         while (mask) {
             int l = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -273,14 +284,16 @@ __device__ __forceinline__ void for_each_positive(const double *x, int n, int la
 
 // fit errors (amico/models.pyx:45-71): y_est = A x with the full dictionary; ws.y is overwritten
 template <int NPL, typename TS>
-__device__ __forceinline__ void fit_errors(const TS *S, int n_pad, int n, int m, double *yv, const double *x, unsigned flags,
+__device__ __noinline__ void fit_errors(const TS *S, int n_pad, int n, int m, double *yv, const double *x, unsigned flags,
                                            double *rmse_out, double *nrmse_out, int lane)
 {
     double den = 0.0;
     if (flags & FLAG_NRMSE) den = seq_sumsq(yv, m);
     __syncwarp();
+    #pragma unroll 1
     for (int i = lane; i < m; i += 32) {
         double ye = 0.0;
+        #pragma unroll 1
         for (int j = 0; j < n; ++j) {
             double xj = x[j];
             if (xj != 0.0) ye = madd(ye, (double)S[(size_t)i * n_pad + j], xj);
@@ -291,12 +304,14 @@ __device__ __forceinline__ void fit_errors(const TS *S, int n_pad, int n, int m,
     __syncwarp();
     if (flags & FLAG_RMSE) {
         double acc = 0.0;
+        #pragma unroll 1
         for (int i = 0; i < m; ++i) acc += yv[i] / (double)m;
         if (lane == 0) *rmse_out = sqrt(acc);
     }
     if (flags & FLAG_NRMSE) {
         double acc = 0.0;
         if (den > 1e-16) {
+            #pragma unroll 1
             for (int i = 0; i < m; ++i) acc += yv[i] / den;
             acc = sqrt(acc);
         }
@@ -355,9 +370,11 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             // ---- signal
             if (p.y_f64) {
                 const double *yg = (const double *)p.y + vox * m;
+                #pragma unroll 1
                 for (int i = lane; i < m; i += 32) ws.y[i] = yg[i];
             } else {
                 const float *yg = (const float *)p.y + vox * m;
+                #pragma unroll 1
                 for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
             }
             __syncwarp();
@@ -379,6 +396,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
                 const double xdot = p.exvivo ? ws.x[n - 2] : 0.0;
                 __syncwarp();
                 // stage 2: support selection on the normalised DWI rows (:914-926)
+                #pragma unroll 1
                 for (int jj = lane; jj < p.dc; jj += 32) {
                     int r = p.dwi_rows[jj];
                     double v2 = ws.y[r] - xiso * (double)S[(size_t)r * n_pad + (n - 1)];
@@ -496,11 +514,14 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             __syncwarp();
             if (p.support_out && lane == 0) p.support_out[vox] = support;
             if (p.coeff_out)
+                #pragma unroll 1
                 for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
             // FreeWater corrected DWI (:1263-1274) -- before fit_errors destroys ws.y? no: errors first use y.
             if (MODEL == MODEL_FREEWATER && (p.flags & FLAG_EXTRA)) {
+                #pragma unroll 1
                 for (int i = lane; i < m; i += 32) {
                     double fw = 0.0;
+                    #pragma unroll 1
                     for (int k = n - p.n_iso; k < n; ++k) fw = madd(fw, (double)S[(size_t)i * n_pad + k], ws.x[k]);
                     double cv = ws.y[i] - fw;
                     p.extra[vox * m + i] = cv < 0.0 ? 0.0 : cv;

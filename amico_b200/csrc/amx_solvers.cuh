@@ -21,6 +21,7 @@ namespace amx {
 __device__ __forceinline__ double fwd_subst(const double *Lp, const double *rd, int np, double t, int lane)
 {
     double v = 0.0;
+    #pragma unroll 1
     for (int k = 0; k < np; ++k) {
         double vk = shfl(t, k) * rd[k];
         if (lane == k) v = vk;
@@ -32,6 +33,7 @@ __device__ __forceinline__ double fwd_subst(const double *Lp, const double *rd, 
 __device__ __forceinline__ double back_subst(const double *Lp, const double *rd, int np, double t, int lane)
 {
     double s = 0.0;
+    #pragma unroll 1
     for (int k = np - 1; k >= 0; --k) {
         double sk = shfl(t, k) * rd[k];
         if (lane == k) s = sk;
@@ -48,7 +50,7 @@ struct NnlsStat {
 // l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays.  mcap = number of rows of the
 // least-squares system (the reference stops growing the passive set at m).  Returns overflow flag.
 template <int NPL>
-__device__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
+__device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
                          unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st)
 {
     int np = 0, iter = 0, overflow = 0;
@@ -70,6 +72,7 @@ __device__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap,
             valid |= (ok ? 1u : 0u) << s;
             wl[s] = ok ? c[j] : 0.0;
         }
+        #pragma unroll 1
         for (int k = 0; k < np; ++k) {
             int pk = P[k];
             double xk = x[pk];
@@ -164,6 +167,7 @@ __device__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap,
             np = nnew;
             __syncwarp();
             inP = 0;
+            #pragma unroll 1
             for (int k = 0; k < np; ++k) {
                 int a = P[k];
                 if ((a & 31) == lane) inP |= 1u << (a >> 5);
@@ -171,6 +175,7 @@ __device__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap,
             if (np == 0) break;
             // rebuild the factor and z = L^-1 c_P row by row
             zl = 0.0;
+            #pragma unroll 1
             for (int i = 0; i < np; ++i) {
                 int pi = P[i];
                 double t = (lane < i) ? T[(size_t)pi * ldT + P[lane]] : 0.0;
@@ -208,7 +213,7 @@ done:
 __device__ __forceinline__ double sym_at(const double *Mi, int r, int c) { return Mi[r <= c ? tri(c, r) : tri(r, c)]; }
 
 template <int NPL>
-__device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in, int K, int Ltrue, double lambda1,
+__device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in, int K, int Ltrue, double lambda1,
                          double *DtR, double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane,
                          int *steps_out)
 {
@@ -241,6 +246,7 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
     int ind_l = -1;
     unsigned act = 0;
     const int length_path = 4 * L;
+    #pragma unroll 1
     for (int i = 0; i < L; ++i) {
         if (i < 0) break;  // the CPU path would read ind[-1] here; cannot happen with pos=true
         ++iter;
@@ -261,15 +267,18 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
             } else {
                 double ur = 0.0;
                 if (lane < i) {
+                    #pragma unroll 1
                     for (int c = 0; c < i; ++c) ur = madd(ur, sym_at(Mi, lane, c), gs[c]);
                     u[lane] = ur;
                 }
                 __syncwarp();
                 double dot = 0.0;
+                #pragma unroll 1
                 for (int j = 0; j < i; ++j) dot = madd(dot, u[j], gs[j]);
                 double schur = 1.0 / __dsub_rn(gs[i], dot);
                 if (lane < i) {
                     double su = __dmul_rn(schur, ur);
+                    #pragma unroll 1
                     for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = __dadd_rn(Mi[tri(k, lane)], __dmul_rn(su, u[k]));
                     Mi[tri(i, lane)] = __dmul_rn(-schur, ur);
                 }
@@ -283,6 +292,7 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
         __syncwarp();
         double ul = 0.0;
         if (lane <= i) {
+            #pragma unroll 1
             for (int c = 0; c <= i; ++c) ul = madd(ul, sym_at(Mi, lane, c), gs[c]);
             u[lane] = ul;
         }
@@ -301,6 +311,7 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
         double sl[NPL];
 #pragma unroll
         for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
+        #pragma unroll 1
         for (int j = 0; j <= i; ++j) {
             int aj = ind[j];
             double uj = u[j];
@@ -340,10 +351,12 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
         }
         cur = bk;
         double coeff1 = 0.0, coeff2 = 0.0;
+        #pragma unroll 1
         for (int j = 0; j <= i; ++j) {
             double uj = u[j];
             coeff1 = __dadd_rn(coeff1, DtR[ind[j]] > 0.0 ? uj : -uj);
         }
+        #pragma unroll 1
         for (int j = 0; j <= i; ++j) coeff2 = madd(coeff2, DtR[ind[j]], u[j]);
         const double step_max2 = __dsub_rn(cc, lambda1);
         step = fmin(fmin(step, step_max2), step_max);
@@ -374,6 +387,7 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
             if (lane >= z && lane < i) { coef_l = cn; ind_l = in_; }
             if (lane == i) { coef_l = 0.0; ind_l = -1; }
             if ((az & 31) == lane) act &= ~(1u << (az >> 5));
+            #pragma unroll 1
             for (int j = z; j < i; ++j) {  // new column j <- old column j+1 without row z
                 double mv = 0.0;
                 if (lane <= j) mv = Mi[tri(j + 1, lane < z ? lane : lane + 1)];
@@ -384,6 +398,7 @@ __device__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in,
             if (lane <= i) ind[lane] = ind_l;
             __syncwarp();
             if (lane < i)
+                #pragma unroll 1
                 for (int k = lane; k < i; ++k)
                     Mi[tri(k, lane)] = __dsub_rn(Mi[tri(k, lane)], __ddiv_rn(__dmul_rn(uk, u[k]), schur_r));
             __syncwarp();

@@ -20,30 +20,40 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-// (value, index) arg-max; ties keep the lowest index.  idx < 0 marks "no candidate".
-__device__ __forceinline__ void warp_argmax(double &v, int &idx)
+// Order-preserving map double -> uint64 (NaN-free inputs): a < b  <=>  dkey(a) < dkey(b).
+__device__ __forceinline__ unsigned long long dkey(double v)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(FULL, v, o);
-        int oi = __shfl_xor_sync(FULL, idx, o);
-        bool take = (oi >= 0) && (idx < 0 || ov > v || (ov == v && oi < idx));
-        if (take) { v = ov; idx = oi; }
-    }
+    long long b = __double_as_longlong(v);
+    return b < 0 ? ~(unsigned long long)b : ((unsigned long long)b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dkey_inv(unsigned long long k)
+{
+    return __longlong_as_double((long long)((k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k));
 }
 
-// (value, index) arg-min; ties keep the lowest index when lowest_on_tie, else the highest.
-template <bool LOWEST>
-__device__ __forceinline__ void warp_argmin(double &v, int &idx)
+// (value, index) arg-extremum over the lanes with idx >= 0, on the integer reduction unit (REDUX): three
+// warp-wide reductions instead of a 5-step shuffle butterfly.  Ties keep the lowest (LOW) or highest index.
+// All lanes receive the winner; idx < 0 when no lane had a candidate.
+template <bool MAX, bool LOW>
+__device__ __forceinline__ void warp_argext(double &v, int &idx)
 {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        double ov = __shfl_xor_sync(FULL, v, o);
-        int oi = __shfl_xor_sync(FULL, idx, o);
-        bool take = (oi >= 0) && (idx < 0 || ov < v || (ov == v && (LOWEST ? oi < idx : oi > idx)));
-        if (take) { v = ov; idx = oi; }
-    }
+    unsigned long long k = idx >= 0 ? (MAX ? dkey(v) : ~dkey(v)) : 0ull;
+    unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    unsigned hm = __reduce_max_sync(FULL, hi);
+    unsigned lm = __reduce_max_sync(FULL, hi == hm ? lo : 0u);
+    bool win = idx >= 0 && hi == hm && lo == lm;
+    int widx = LOW ? __reduce_min_sync(FULL, win ? idx : 0x7fffffff) : __reduce_max_sync(FULL, win ? idx : -1);
+    unsigned long long km = ((unsigned long long)hm << 32) | lm;
+    bool none = km == 0ull;
+    if (!MAX) km = ~km;
+    v = dkey_inv(km);
+    idx = none ? -1 : widx;
 }
+// arg-max, ties -> lowest index
+__device__ __forceinline__ void warp_argmax(double &v, int &idx) { warp_argext<true, true>(v, idx); }
+// arg-min, ties -> lowest (LOWEST) or highest index
+template <bool LOWEST>
+__device__ __forceinline__ void warp_argmin(double &v, int &idx) { warp_argext<false, LOWEST>(v, idx); }
 
 // un-fused multiply-add: the reference CPU arithmetic (x86-64, no FMA contraction) rounds the product first
 __device__ __forceinline__ double madd(double s, double a, double b) { return __dadd_rn(s, __dmul_rn(a, b)); }
