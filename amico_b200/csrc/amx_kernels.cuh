@@ -227,32 +227,40 @@ __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_
     return w;
 }
 
-// acc[s] += sum_r S[row(r)][lane+32s] * scale * yv[r]   (sequential in r, un-fused: matches the CPU order)
-template <int NPL, typename TS>
+// out[lane+32s] = sum_r S[row(r)][lane+32s] * scale * yv[r], sequential in r like the CPU loop.  Columns beyond n read
+// whatever follows in the slab (in bounds: the slab is padded by NA elements) and produce values nobody uses.
+//   FUSED : products are exact in fp64 (fp32-valued dictionary times fp32-valued signal), so fma == mul + add bit for bit;
+//   SCALED: NODDI stage 2, column-normalised DWI rows: a = fl(S * norm) first, exactly like the reference's A2.
+template <int NPL, typename TS, bool FUSED, bool SCALED>
 __device__ __noinline__ void at_y(const TS *S, int n_pad, int n, int nrows, const int *__restrict__ rows, const double *yv,
-                                     const double *__restrict__ norms, int ldn, int norms_const, double (&acc)[NPL], int lane)
+                                  const double *__restrict__ norms, int ldn, int norms_const, double *out, int lane)
 {
-    double nk[NPL];
+    double acc[NPL], nk[NPL];
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
         acc[s] = 0.0;
         nk[s] = 1.0;
-        if (norms && norms_const && lane + 32 * s < n) nk[s] = norms[lane + 32 * s];
+        if (SCALED && norms_const && lane + 32 * s < n) nk[s] = norms[lane + 32 * s];
     }
-#pragma unroll 2
+#pragma unroll 4
     for (int rr = 0; rr < nrows; ++rr) {
-        int r = rows ? rows[rr] : rr;
-        double yr = yv[rr];
+        const int r = SCALED ? rows[rr] : rr;
+        const double yr = yv[rr];
         const TS *row = S + (size_t)r * n_pad + lane;
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
-            if (lane + 32 * s < n) {
-                double a = (double)row[32 * s];
-                if (norms) a = __dmul_rn(a, norms_const ? nk[s] : norms[(size_t)rr * ldn + lane + 32 * s]);
-                acc[s] = madd(acc[s], a, yr);
+            double a = (double)row[32 * s];
+            if (SCALED) {
+                double sc = nk[s];
+                if (!norms_const) sc = (lane + 32 * s < n) ? norms[(size_t)rr * ldn + lane + 32 * s] : 0.0;
+                a = __dmul_rn(a, sc);
             }
+            acc[s] = FUSED ? fma(a, yr, acc[s]) : madd(acc[s], a, yr);
         }
     }
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) out[lane + 32 * s] = acc[s];
+    __syncwarp();
 }
 
 // sum_i v[i]^2 in index order (all lanes compute the same value)
@@ -379,15 +387,12 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             }
             __syncwarp();
             int overflow = 0, support = 0;
-            double acc[NPL];
 
             if (MODEL == MODEL_NODDI) {
                 const int n_wm = p.n_wm;
                 // stage 1: isotropic fraction (amico/models.pyx:911)
-                at_y<NPL, TS>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, acc, lane);
-#pragma unroll
-                for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = acc[s];
-                __syncwarp();
+                if (p.y_f64) at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.c1, lane);
+                else at_y<NPL, TS, true, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.c1, lane);
                 unsigned all = 0;
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
@@ -405,10 +410,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
                 }
                 __syncwarp();
                 const double normX = seq_sumsq(ws.y2, p.dc);
-                at_y<NPL, TS>(S, n_pad, n_wm, p.dc, p.dwi_rows, ws.y2, p.norms, n_wm, p.norms_const, acc, lane);
-#pragma unroll
-                for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = acc[s];
-                __syncwarp();
+                at_y<NPL, TS, false, true>(S, n_pad, n_wm, p.dc, p.dwi_rows, ws.y2, p.norms, n_wm, p.norms_const, ws.dtr, lane);
                 overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, normX,
                                            ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
                 // stage 3: debias on the support (:929-942)
@@ -452,10 +454,8 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             } else {
                 // single elastic-net fit on the full dictionary (:615, :1238, :1569)
                 const double normX = seq_sumsq(ws.y, m);
-                at_y<NPL, TS>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, acc, lane);
-#pragma unroll
-                for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = acc[s];
-                __syncwarp();
+                if (p.y_f64 || sizeof(TS) == 8) at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
+                else at_y<NPL, TS, true, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
                 overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n, m < n ? m : n, p.lambda1, ws.dtr, normX, ws.mat, ws.u,
                                            ws.gs, ws.P, ws.x, lane, nullptr);
                 for_each_positive<NPL>(ws.x, n, lane, [&](int, double) { ++support; });

@@ -72,7 +72,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             valid |= (ok ? 1u : 0u) << s;
             wl[s] = ok ? c[j] : 0.0;
         }
-        #pragma unroll 1
+#pragma unroll 1
         for (int k = 0; k < np; ++k) {
             int pk = P[k];
             double xk = x[pk];
@@ -311,7 +311,7 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
         double sl[NPL];
 #pragma unroll
         for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
-        #pragma unroll 1
+#pragma unroll 1
         for (int j = 0; j <= i; ++j) {
             int aj = ind[j];
             double uj = u[j];
