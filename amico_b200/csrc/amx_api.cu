@@ -76,7 +76,7 @@ struct amx_plan {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
-    DevBuf lut, order, bins, tiles, status, st_y, st_dirs, st_est, st_rmse, st_nrmse, st_extra, st_sup, st_coef;
+    DevBuf lut, order, bins, tiles, status, scratch, st_y, st_dirs, st_est, st_rmse, st_nrmse, st_extra, st_sup, st_coef;
     int max_smem = 0, sm_count = 0;
     // last-call records
     double last_ms[8] = {0};
@@ -113,6 +113,9 @@ int plan_common_init(amx_plan *pl, int device)
 void slab_geometry(amx_plan *pl, size_t elem)
 {
     pl->n_pad = pl->n | 1;  // odd row stride: conflict-free for both lane-per-atom and lane-per-row access
+    // NODDI feeds DMMA B-fragments from the slab (lane -> row lane%4, column lane/4): stride = 8 (mod 16) words
+    // makes those 32 addresses hit 32 distinct banks
+    if (pl->model == AMX_MODEL_NODDI) pl->n_pad = ((pl->n + 7) & ~15) + 8 >= pl->n ? ((pl->n + 7) & ~15) + 8 : ((pl->n + 23) & ~15) + 8;
     size_t bytes = (size_t)pl->m * pl->n_pad * elem;
     bytes = (bytes + 127) & ~(size_t)127;
     pl->slab_bytes = (unsigned)bytes;
@@ -195,7 +198,7 @@ int amx_plan_destroy(amx_plan *pl)
     void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
-    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->st_y, &pl->st_dirs, &pl->st_est,
+    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->st_y, &pl->st_dirs, &pl->st_est,
                       &pl->st_rmse, &pl->st_nrmse, &pl->st_extra, &pl->st_sup, &pl->st_coef};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : pl->ev) if (ev) cudaEventDestroy(ev);
@@ -340,10 +343,10 @@ int amx_plan_info(const amx_plan *pl, int *model, int *m, int *n_atoms, int *n_m
 
 namespace {
 
-template <int MODEL, int NPL, typename TS>
+template <int MODEL, int NPL, typename TS, bool BATCHED = false>
 int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
-    auto kern = k_fit<MODEL, NPL, TS>;
+    auto kern = k_fit<MODEL, NPL, TS, BATCHED>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, block, smem, st>>>(p);
     CK(cudaGetLastError());
@@ -353,6 +356,14 @@ int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_
 template <int MODEL, typename TS>
 int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
+    if (MODEL == MODEL_NODDI && p.batched) {
+        switch (npl) {
+        case 1: return launch_fit<MODEL_NODDI, 1, float, true>(p, grid, block, smem, st);
+        case 2: return launch_fit<MODEL_NODDI, 2, float, true>(p, grid, block, smem, st);
+        case 3: case 4: return launch_fit<MODEL_NODDI, 4, float, true>(p, grid, block, smem, st);
+        case 5: return launch_fit<MODEL_NODDI, 5, float, true>(p, grid, block, smem, st);
+        }
+    }
     switch (npl) {
     case 1: return launch_fit<MODEL, 1, TS>(p, grid, block, smem, st);
     case 2: return launch_fit<MODEL, 2, TS>(p, grid, block, smem, st);
@@ -435,7 +446,9 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.Rs = pl->d_Rs; p.sandi_norms = pl->d_sandi_norms; p.d_in = pl->d_d_in; p.d_isos = pl->d_d_isos;
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
-    p.m_pad = (pl->m + 1) & ~1; p.dc_pad = (pl->dc + 1) & ~1;
+    p.batched = (pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1)) ? 1 : 0;
+    p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
+    if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad);
 
     // shared-memory budget: [header 128][slab (optional)][nwarps x workspace]
@@ -456,6 +469,10 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
     int grid = std::max(1, std::min(n_tiles, pl->sm_count * ctas_per_sm));
 
+    if (p.batched) {
+        CK(pl->scratch.reserve((size_t)grid * nwarps * 2 * BV * p.NA * sizeof(double)));
+        p.scratch = (double *)pl->scratch.p;
+    }
     int rc;
     switch (pl->model) {
     case AMX_MODEL_NODDI: rc = dispatch_npl<MODEL_NODDI, float>(pl->npl, p, grid, nwarps * 32, smem, st); break;

@@ -202,14 +202,17 @@ struct FitParams {
     // launch geometry
     int nwarps; unsigned ws_doubles; unsigned slab_smem_off, ws_smem_off;
     int m_pad, dc_pad;
+    double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
+    int batched;
 };
 
 struct WarpWS {
-    double *c1, *dtr, *x, *mat, *rd, *u, *gs, *y, *y2;
+    double *c1, *dtr, *x, *mat, *rd, *u, *gs, *bx, *y, *y2;
     int *P;
 };
 
-__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad) { return 3u * NA + TRI + 3 * LC + LC / 2 + m_pad + dc_pad; }
+constexpr int BV = 8;  // voxels per DMMA micro-batch (the M of m8n8k4)
+__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad) { return 3u * NA + TRI + 3 * LC + LC / 2 + 3 * BV + m_pad + dc_pad; }
 
 __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad)
 {
@@ -222,6 +225,7 @@ __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_
     w.u = base; base += LC;
     w.gs = base; base += LC;
     w.P = (int *)base; base += LC / 2;
+    w.bx = base; base += 3 * BV;  // per-batch x_iso, x_dot, ||y2||^2
     w.y = base; base += m_pad;
     w.y2 = base;
     return w;
@@ -290,6 +294,132 @@ __device__ __forceinline__ void for_each_positive(const double *x, int n, int la
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// FP64 tensor-core micro-GEMM: C[8 voxels][8 NT atoms] = Y[8][rows] * A_d[rows][atoms] with mma.sync m8n8k4 (DMMA).
+// The eight voxels of a batch share the direction (same tile), so A_d^T Y is a genuine dense contraction.
+// Fragment layout (PTX ISA, m8n8k4 .f64): A row-major: lane holds A[lane/4][lane%4]; B: lane holds B[k=lane%4][n=lane/4];
+// C: lane holds C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+// c1[v][k] = sum_r y_v[r] A[r][k] for the batch's voxels -> out[v * NA + k]   (NODDI stage 1 / stage 3 right-hand side)
+template <int NT, typename TS>
+__device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *y, int y_f64, long long myvox, bool vvalid,
+                                     double *out, int NA, int lane)
+{
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const int kk = lane & 3, g = lane >> 2;
+    const float *yf = (const float *)y + myvox * m;
+    const double *yd = (const double *)y + myvox * m;
+#pragma unroll 1
+    for (int r0 = 0; r0 < m; r0 += 4) {
+        const int r = r0 + kk;
+        const bool rv = r < m;
+        double a = 0.0;
+        if (rv && vvalid) a = y_f64 ? yd[r] : (double)yf[r];
+        const TS *row = S + (size_t)(rv ? r : m - 1) * n_pad + g;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
+    }
+    double *o = out + (size_t)g * NA + 2 * kk;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+    __syncwarp();
+}
+
+// NODDI stage 2 right-hand side for the batch: y2 = max(y_R - x_iso iso_R [- x_dot], 0) (amico/models.pyx:918-925),
+// c2[v][k] = sum_j (A[R_j][k] norms[j][k]) y2_v[j]; also ||y2_v||^2 -> normx[v].
+template <int NT, typename TS, bool NC>
+__device__ __noinline__ void gemm_c2(const TS *S, int n_pad, int n, int n_wm, int dc, const int *__restrict__ rows, const void *y,
+                                     int y_f64, int m, long long myvox, bool vvalid, double xiso, double xdot, int exvivo,
+                                     const double *__restrict__ norms, int ldn, double *out, int NA, double *normx, int lane)
+{
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    const int kk = lane & 3, g = lane >> 2;
+    const float *yf = (const float *)y + myvox * m;
+    const double *yd = (const double *)y + myvox * m;
+    double nx = 0.0;
+#pragma unroll 1
+    for (int j0 = 0; j0 < dc; j0 += 4) {
+        const int jj = j0 + kk;
+        const bool jv = jj < dc;
+        const int r = rows[jv ? jj : dc - 1];
+        const TS *row = S + (size_t)r * n_pad;
+        double a = 0.0;
+        if (jv && vvalid) {
+            a = (y_f64 ? yd[r] : (double)yf[r]) - xiso * (double)row[n - 1];
+            if (exvivo) a = a - xdot * 1.0;
+            a = a < 0.0 ? 0.0 : a;
+        }
+        nx = fma(a, a, nx);
+        row += g;
+        if (NC) {
+#pragma unroll
+            for (int t = 0; t < NT; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
+        } else {
+            const double *nr = norms + (size_t)(jv ? jj : dc - 1) * ldn + g;
+#pragma unroll
+            for (int t = 0; t < NT; ++t) {
+                const double sc = (g + 8 * t < n_wm) ? nr[8 * t] : 0.0;
+                dmma(acc[t][0], acc[t][1], a, __dmul_rn((double)row[8 * t], sc));
+            }
+        }
+    }
+    nx += __shfl_xor_sync(FULL, nx, 1);
+    nx += __shfl_xor_sync(FULL, nx, 2);
+    if (kk == 0) normx[g] = nx;
+    double *o = out + (size_t)g * NA + 2 * kk;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+        double c0 = acc[t][0], c1 = acc[t][1];
+        if (NC) {
+            const int k0 = 8 * t + 2 * kk;
+            c0 = (k0 < n_wm) ? c0 * norms[k0] : 0.0;
+            c1 = (k0 + 1 < n_wm) ? c1 * norms[k0 + 1] : 0.0;
+        }
+        *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(c0, c1);
+    }
+    __syncwarp();
+}
+
+// NODDI maps from the final coefficients (amico/models.pyx:945-979); all lanes compute, lane 0 stores
+template <int NPL>
+__device__ __noinline__ void noddi_maps(const float *__restrict__ icvf, const float *__restrict__ kappa, int n, int n_wm, int exvivo,
+                                        unsigned flags, double *e, double *emod, const double *x, int lane)
+{
+    double s_all = 0.0;
+    for_each_positive<NPL>(x, n, lane, [&](int, double xj) { s_all += xj; });
+    s_all += 1e-16;
+    double s_wm = 0.0;
+    for_each_positive<NPL>(x, n_wm, lane, [&](int, double xj) { s_wm += xj / s_all; });
+    s_wm += 1e-16;
+    double f1 = 0.0, f2 = 0.0, k1 = 0.0;
+    for_each_positive<NPL>(x, n_wm, lane, [&](int j, double xj) {
+        float ic = icvf[j];
+        f1 += (double)ic * xj / s_all / s_wm;
+        f2 += (double)((float)(1.0 - (double)ic)) * xj / s_all / s_wm;
+        k1 += (double)kappa[j] * xj / s_all / s_wm;
+    });
+    const double ndi = f1 / (f1 + f2 + 1e-16);
+    const double odi = 2.0 / 3.14159265358979323846 * atan2(1.0, k1);
+    const double fwf = x[n - 1] / s_all;
+    if (lane == 0) {
+        e[0] = ndi; e[1] = odi; e[2] = fwf;
+        if (exvivo) e[3] = x[n - 2] / s_all;
+        if (flags & FLAG_EXTRA) {
+            double tf = 1.0 - fwf;
+            emod[0] = ndi * tf;
+            emod[1] = odi * tf;
+        }
+    }
+}
+
 // fit errors (amico/models.pyx:45-71): y_est = A x with the full dictionary; ws.y is overwritten
 template <int NPL, typename TS>
 __device__ __noinline__ void fit_errors(const TS *S, int n_pad, int n, int m, double *yv, const double *x, unsigned flags,
@@ -327,7 +457,7 @@ __device__ __noinline__ void fit_errors(const TS *S, int n_pad, int n, int m, do
     }
 }
 
-template <int MODEL, int NPL, typename TS>
+template <int MODEL, int NPL, typename TS, bool BATCHED>
 __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -360,18 +490,105 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             if (threadIdx.x == 0) {
                 mbar_expect_tx(mbar, p.slab_bytes);
                 bulk_g2s(s_slab, Sg, p.slab_bytes, mbar);
-                *s_next = p.nwarps;
+                *s_next = p.nwarps * (BATCHED ? BV : 1);
             }
             mbar_wait(mbar, phase);
             phase ^= 1;
             S = s_slab;
         } else if (threadIdx.x == 0) {
-            *s_next = p.nwarps;
+            *s_next = p.nwarps * (BATCHED ? BV : 1);
         }
         __syncthreads();
         const double *T1 = p.T1 ? p.T1 + (size_t)dir * p.T1_stride : nullptr;
         const double *T2 = p.T2 + (size_t)dir * p.T2_stride;
 
+        if (BATCHED) {
+            // ---- NODDI, 8-voxel micro-batches: both A^T y products of a batch on the FP64 tensor pipe (DMMA)
+            constexpr int NT = 4 * NPL;
+            const int n_wm = p.n_wm, NA = p.NA;
+            double *scr1 = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)(2 * BV) * NA;
+            double *scr2 = scr1 + (size_t)BV * NA;
+            const int g = lane >> 2;
+            unsigned all = 0;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
+            int base = warp * BV;
+            while (base < tile.z) {
+                const int nb = min(BV, tile.z - base);
+                const bool vvalid = g < nb;
+                const long long myvox = (long long)p.order[tile.y + base + (vvalid ? g : 0)];
+                gemm_c1<NT, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr1, NA, lane);
+                // stage 1 per voxel: isotropic fraction (amico/models.pyx:911)
+                #pragma unroll 1
+                for (int v = 0; v < nb; ++v) {
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr1[(size_t)v * NA + lane + 32 * s];
+                    __syncwarp();
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
+                    if (lane == 0) {
+                        ws.bx[v] = ws.x[n - 1];
+                        ws.bx[BV + v] = p.exvivo ? ws.x[n - 2] : 0.0;
+                    }
+                    if (ov) ++n_overflow;
+                    __syncwarp();
+                }
+                // stage 2 right-hand sides for the whole batch (:914-925)
+                if (p.norms_const)
+                    gemm_c2<NT, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
+                                          ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
+                else
+                    gemm_c2<NT, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
+                                           ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
+                #pragma unroll 1
+                for (int v = 0; v < nb; ++v) {
+                    const long long vox = (long long)p.order[tile.y + base + v];
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr2[(size_t)v * NA + lane + 32 * s];
+                    __syncwarp();
+                    int overflow = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr,
+                                                  ws.bx[2 * BV + v], ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
+                    // stage 3: debias on the support (:929-942)
+                    unsigned allowed = 0;
+                    int support = 0;
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        int j = lane + 32 * s;
+                        bool on = (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n);
+                        allowed |= (on ? 1u : 0u) << s;
+                        support += __popc(__ballot_sync(FULL, on));
+                        ws.c1[j] = scr1[(size_t)v * NA + j];
+                    }
+                    __syncwarp();
+                    overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
+                    noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
+                                    (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
+                    if (p.support_out && lane == 0) p.support_out[vox] = support;
+                    if (p.coeff_out)
+                        for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
+                    if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {
+                        if (p.y_f64) {
+                            const double *yg = (const double *)p.y + vox * m;
+                            #pragma unroll 1
+                            for (int i = lane; i < m; i += 32) ws.y[i] = yg[i];
+                        } else {
+                            const float *yg = (const float *)p.y + vox * m;
+                            #pragma unroll 1
+                            for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
+                        }
+                        __syncwarp();
+                        fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
+                                            p.nrmse ? p.nrmse + vox : nullptr, lane);
+                    }
+                    if (overflow) ++n_overflow;
+                    __syncwarp();
+                }
+                int nv = 0;
+                if (lane == 0) nv = atomicAdd(s_next, BV);
+                base = __shfl_sync(FULL, nv, 0);
+            }
+            __syncthreads();
+            continue;
+        }
         int v = warp;
         while (v < tile.z) {
             const long long vox = p.order ? (long long)p.order[tile.y + v] : (long long)tile.y + v;
@@ -388,7 +605,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             __syncwarp();
             int overflow = 0, support = 0;
 
-            if (MODEL == MODEL_NODDI) {
+            if (MODEL == MODEL_NODDI && !BATCHED) {
                 const int n_wm = p.n_wm;
                 // stage 1: isotropic fraction (amico/models.pyx:911)
                 if (p.y_f64) at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.c1, lane);
@@ -424,34 +641,9 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
                 }
                 __syncwarp();
                 overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
-                // maps (:945-967)
-                double s_all = 0.0;
-                for_each_positive<NPL>(ws.x, n, lane, [&](int, double xj) { s_all += xj; });
-                s_all += 1e-16;
-                double s_wm = 0.0;
-                for_each_positive<NPL>(ws.x, n_wm, lane, [&](int, double xj) { s_wm += xj / s_all; });
-                s_wm += 1e-16;
-                double f1 = 0.0, f2 = 0.0, k1 = 0.0;
-                for_each_positive<NPL>(ws.x, n_wm, lane, [&](int j, double xj) {
-                    float ic = p.icvf[j];
-                    f1 += (double)ic * xj / s_all / s_wm;
-                    f2 += (double)((float)(1.0 - (double)ic)) * xj / s_all / s_wm;
-                    k1 += (double)p.kappa[j] * xj / s_all / s_wm;
-                });
-                const double ndi = f1 / (f1 + f2 + 1e-16);
-                const double odi = 2.0 / 3.14159265358979323846 * atan2(1.0, k1);
-                const double fwf = ws.x[n - 1] / s_all;
-                if (lane == 0) {
-                    double *e = p.est + vox * p.n_maps;
-                    e[0] = ndi; e[1] = odi; e[2] = fwf;
-                    if (p.exvivo) e[3] = ws.x[n - 2] / s_all;
-                    if (p.flags & FLAG_EXTRA) {
-                        double tf = 1.0 - fwf;
-                        p.extra[2 * vox] = ndi * tf;
-                        p.extra[2 * vox + 1] = odi * tf;
-                    }
-                }
-            } else {
+                noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
+                                (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
+            } else if (MODEL != MODEL_NODDI) {
                 // single elastic-net fit on the full dictionary (:615, :1238, :1569)
                 const double normX = seq_sumsq(ws.y, m);
                 if (p.y_f64 || sizeof(TS) == 8) at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
