@@ -343,10 +343,20 @@ int amx_plan_info(const amx_plan *pl, int *model, int *m, int *n_atoms, int *n_m
 
 namespace {
 
-template <int MODEL, int NPL, typename TS, bool BATCHED = false>
+template <int NPL>
+int launch_noddi_batched(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+{
+    auto kern = k_fit_noddi_batched<NPL, float>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return AMX_OK;
+}
+
+template <int MODEL, int NPL, typename TS>
 int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
-    auto kern = k_fit<MODEL, NPL, TS, BATCHED>;
+    auto kern = k_fit<MODEL, NPL, TS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, block, smem, st>>>(p);
     CK(cudaGetLastError());
@@ -358,10 +368,10 @@ int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, 
 {
     if (MODEL == MODEL_NODDI && p.batched) {
         switch (npl) {
-        case 1: return launch_fit<MODEL_NODDI, 1, float, true>(p, grid, block, smem, st);
-        case 2: return launch_fit<MODEL_NODDI, 2, float, true>(p, grid, block, smem, st);
-        case 3: case 4: return launch_fit<MODEL_NODDI, 4, float, true>(p, grid, block, smem, st);
-        case 5: return launch_fit<MODEL_NODDI, 5, float, true>(p, grid, block, smem, st);
+        case 1: return launch_noddi_batched<1>(p, grid, block, smem, st);
+        case 2: return launch_noddi_batched<2>(p, grid, block, smem, st);
+        case 3: case 4: return launch_noddi_batched<4>(p, grid, block, smem, st);
+        case 5: return launch_noddi_batched<5>(p, grid, block, smem, st);
         }
     }
     switch (npl) {
@@ -378,7 +388,8 @@ int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, 
 int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launches)
 {
     const long long n_vox = a->n_vox;
-    const int tile_v = std::max(1, env_int("AMX_TILE_VOX", 256));
+    const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
+    const int tile_v = batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
     const bool rotated = pl->model != AMX_MODEL_SANDI;
     const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
     CK(pl->status.reserve(64));
@@ -446,7 +457,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.Rs = pl->d_Rs; p.sandi_norms = pl->d_sandi_norms; p.d_in = pl->d_d_in; p.d_isos = pl->d_d_isos;
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
-    p.batched = (pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1)) ? 1 : 0;
+    p.batched = batched ? 1 : 0;
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad);
@@ -456,7 +467,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     const size_t budget = (size_t)pl->max_smem;
     const int want_warps = std::min(16, std::max(1, env_int("AMX_WARPS", 16)));
     const int min_staged_warps = std::max(1, env_int("AMX_MIN_STAGED_WARPS", 8));
-    bool staged = env_int("AMX_NO_TMA", 0) == 0 && 128 + (size_t)pl->slab_bytes + ws_bytes * min_staged_warps <= budget;
+    bool staged = !batched && env_int("AMX_NO_TMA", 0) == 0 && 128 + (size_t)pl->slab_bytes + ws_bytes * min_staged_warps <= budget;
     size_t fixed = 128 + (staged ? pl->slab_bytes : 0);
     int nwarps = (int)std::min<size_t>(want_warps, (budget - fixed) / ws_bytes);
     if (nwarps < 1) return fail(AMX_E_INVALID, "per-warp workspace (%zu B) does not fit in shared memory (m=%d, n=%d)", ws_bytes, pl->m, pl->n);

@@ -457,7 +457,7 @@ __device__ __noinline__ void fit_errors(const TS *S, int n_pad, int n, int m, do
     }
 }
 
-template <int MODEL, int NPL, typename TS, bool BATCHED>
+template <int MODEL, int NPL, typename TS>
 __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -490,105 +490,18 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             if (threadIdx.x == 0) {
                 mbar_expect_tx(mbar, p.slab_bytes);
                 bulk_g2s(s_slab, Sg, p.slab_bytes, mbar);
-                *s_next = p.nwarps * (BATCHED ? BV : 1);
+                *s_next = p.nwarps;
             }
             mbar_wait(mbar, phase);
             phase ^= 1;
             S = s_slab;
         } else if (threadIdx.x == 0) {
-            *s_next = p.nwarps * (BATCHED ? BV : 1);
+            *s_next = p.nwarps;
         }
         __syncthreads();
         const double *T1 = p.T1 ? p.T1 + (size_t)dir * p.T1_stride : nullptr;
         const double *T2 = p.T2 + (size_t)dir * p.T2_stride;
 
-        if (BATCHED) {
-            // ---- NODDI, 8-voxel micro-batches: both A^T y products of a batch on the FP64 tensor pipe (DMMA)
-            constexpr int NT = 4 * NPL;
-            const int n_wm = p.n_wm, NA = p.NA;
-            double *scr1 = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)(2 * BV) * NA;
-            double *scr2 = scr1 + (size_t)BV * NA;
-            const int g = lane >> 2;
-            unsigned all = 0;
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
-            int base = warp * BV;
-            while (base < tile.z) {
-                const int nb = min(BV, tile.z - base);
-                const bool vvalid = g < nb;
-                const long long myvox = (long long)p.order[tile.y + base + (vvalid ? g : 0)];
-                gemm_c1<NT, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr1, NA, lane);
-                // stage 1 per voxel: isotropic fraction (amico/models.pyx:911)
-                #pragma unroll 1
-                for (int v = 0; v < nb; ++v) {
-#pragma unroll
-                    for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr1[(size_t)v * NA + lane + 32 * s];
-                    __syncwarp();
-                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
-                    if (lane == 0) {
-                        ws.bx[v] = ws.x[n - 1];
-                        ws.bx[BV + v] = p.exvivo ? ws.x[n - 2] : 0.0;
-                    }
-                    if (ov) ++n_overflow;
-                    __syncwarp();
-                }
-                // stage 2 right-hand sides for the whole batch (:914-925)
-                if (p.norms_const)
-                    gemm_c2<NT, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
-                                          ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
-                else
-                    gemm_c2<NT, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
-                                           ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
-                #pragma unroll 1
-                for (int v = 0; v < nb; ++v) {
-                    const long long vox = (long long)p.order[tile.y + base + v];
-#pragma unroll
-                    for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr2[(size_t)v * NA + lane + 32 * s];
-                    __syncwarp();
-                    int overflow = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr,
-                                                  ws.bx[2 * BV + v], ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
-                    // stage 3: debias on the support (:929-942)
-                    unsigned allowed = 0;
-                    int support = 0;
-#pragma unroll
-                    for (int s = 0; s < NPL; ++s) {
-                        int j = lane + 32 * s;
-                        bool on = (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n);
-                        allowed |= (on ? 1u : 0u) << s;
-                        support += __popc(__ballot_sync(FULL, on));
-                        ws.c1[j] = scr1[(size_t)v * NA + j];
-                    }
-                    __syncwarp();
-                    overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
-                    noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
-                                    (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
-                    if (p.support_out && lane == 0) p.support_out[vox] = support;
-                    if (p.coeff_out)
-                        for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
-                    if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {
-                        if (p.y_f64) {
-                            const double *yg = (const double *)p.y + vox * m;
-                            #pragma unroll 1
-                            for (int i = lane; i < m; i += 32) ws.y[i] = yg[i];
-                        } else {
-                            const float *yg = (const float *)p.y + vox * m;
-                            #pragma unroll 1
-                            for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
-                        }
-                        __syncwarp();
-                        fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
-                                            p.nrmse ? p.nrmse + vox : nullptr, lane);
-                    }
-                    if (overflow) ++n_overflow;
-                    __syncwarp();
-                }
-                int nv = 0;
-                if (lane == 0) nv = atomicAdd(s_next, BV);
-                base = __shfl_sync(FULL, nv, 0);
-            }
-            __syncthreads();
-            continue;
-        }
         int v = warp;
         while (v < tile.z) {
             const long long vox = p.order ? (long long)p.order[tile.y + v] : (long long)tile.y + v;
@@ -605,7 +518,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             __syncwarp();
             int overflow = 0, support = 0;
 
-            if (MODEL == MODEL_NODDI && !BATCHED) {
+            if (MODEL == MODEL_NODDI) {
                 const int n_wm = p.n_wm;
                 // stage 1: isotropic fraction (amico/models.pyx:911)
                 if (p.y_f64) at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.c1, lane);
@@ -731,6 +644,108 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             v = __shfl_sync(FULL, nv, 0);
         }
         __syncthreads();
+    }
+    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NODDI, batched: every warp is an independent worker pulling 8-voxel batches (same LUT direction) from a global
+// queue.  Per batch both A^T y products run on the FP64 tensor pipe (DMMA m8n8k4, M = the 8 voxels), their results
+// go through a warp-private L2-resident scratch, and the three active-set stages run per voxel as in k_fit.
+// Dictionary B-fragments stream from the per-direction slab in global memory (read once per batch and stage:
+// ~14 KB/voxel of L2 traffic), which keeps shared memory for solver state and L1 for the Gram rows.
+template <int NPL, typename TS>
+__global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad);
+    constexpr int NT = 4 * NPL;
+    const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
+    double *scr1 = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)(2 * BV) * NA;
+    double *scr2 = scr1 + (size_t)BV * NA;
+    const int g = lane >> 2;
+    unsigned all = 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
+    long long n_overflow = 0;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(p.tile_counter, 1);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= p.n_tiles) break;
+        const int4 tile = p.tiles[b];
+        const int nb = tile.z;  // <= BV
+        const TS *S = (const TS *)p.slab + (size_t)tile.x * p.slab_stride;
+        const double *T1 = p.T1 + (size_t)tile.x * p.T1_stride;
+        const double *T2 = p.T2 + (size_t)tile.x * p.T2_stride;
+        const bool vvalid = g < nb;
+        const long long myvox = (long long)p.order[tile.y + (vvalid ? g : 0)];
+        gemm_c1<NT, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr1, NA, lane);
+        // stage 1 per voxel: isotropic fraction (amico/models.pyx:911)
+        #pragma unroll 1
+        for (int v = 0; v < nb; ++v) {
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr1[(size_t)v * NA + lane + 32 * s];
+            __syncwarp();
+            int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
+            if (lane == 0) {
+                ws.bx[v] = ws.x[n - 1];
+                ws.bx[BV + v] = p.exvivo ? ws.x[n - 2] : 0.0;
+            }
+            if (ov) ++n_overflow;
+            __syncwarp();
+        }
+        // stage 2 right-hand sides for the whole batch (:914-925)
+        if (p.norms_const)
+            gemm_c2<NT, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
+                                  ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
+        else
+            gemm_c2<NT, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
+                                   ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
+        #pragma unroll 1
+        for (int v = 0; v < nb; ++v) {
+            const long long vox = (long long)p.order[tile.y + v];
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr2[(size_t)v * NA + lane + 32 * s];
+            __syncwarp();
+            int overflow = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr,
+                                          ws.bx[2 * BV + v], ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
+            // stage 3: debias on the support (:929-942)
+            unsigned allowed = 0;
+            int support = 0;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) {
+                int j = lane + 32 * s;
+                bool on = (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n);
+                allowed |= (on ? 1u : 0u) << s;
+                support += __popc(__ballot_sync(FULL, on));
+                ws.c1[j] = scr1[(size_t)v * NA + j];
+            }
+            __syncwarp();
+            overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
+            noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
+                            (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
+            if (p.support_out && lane == 0) p.support_out[vox] = support;
+            if (p.coeff_out)
+                for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
+            if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {
+                if (p.y_f64) {
+                    const double *yg = (const double *)p.y + vox * m;
+                    #pragma unroll 1
+                    for (int i = lane; i < m; i += 32) ws.y[i] = yg[i];
+                } else {
+                    const float *yg = (const float *)p.y + vox * m;
+                    #pragma unroll 1
+                    for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
+                }
+                __syncwarp();
+                fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
+                                    p.nrmse ? p.nrmse + vox : nullptr, lane);
+            }
+            if (overflow) ++n_overflow;
+            __syncwarp();
+        }
     }
     if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
 }

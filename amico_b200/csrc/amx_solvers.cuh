@@ -72,14 +72,26 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             valid |= (ok ? 1u : 0u) << s;
             wl[s] = ok ? c[j] : 0.0;
         }
-#pragma unroll 1
-        for (int k = 0; k < np; ++k) {
-            int pk = P[k];
-            double xk = x[pk];
-            const double *row = T + (size_t)pk * ldT;
+        {   // rows of T are L2-resident: keep the next row in flight while the current one is consumed
+            double nxt[NPL];
+            const double *row = T + (size_t)(np > 0 ? P[0] : 0) * ldT;
 #pragma unroll
-            for (int s = 0; s < NPL; ++s)
-                if ((valid >> s) & 1u) wl[s] = fma(-row[lane + 32 * s], xk, wl[s]);
+            for (int s = 0; s < NPL; ++s) nxt[s] = (np > 0 && ((valid >> s) & 1u)) ? row[lane + 32 * s] : 0.0;
+#pragma unroll 1
+            for (int k = 0; k < np; ++k) {
+                double cur[NPL];
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) cur[s] = nxt[s];
+                const double xk = x[P[k]];
+                if (k + 1 < np) {
+                    row = T + (size_t)P[k + 1] * ldT;
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s)
+                        if ((valid >> s) & 1u) nxt[s] = row[lane + 32 * s];
+                }
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) wl[s] = fma(-cur[s], xk, wl[s]);
+            }
         }
         // candidate selection
         int j = -1;
@@ -155,6 +167,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             int myP = (lane < np) ? P[lane] : 0;
             if (lane < np && !keep) x[myP] = 0.0;
             int nnew = __popc(kmask);
+            const int np_old = np;
             if (st) st->removed += np - nnew;
             unsigned src = __fns(kmask, 0, lane + 1);
             bool has = lane < nnew;
@@ -173,24 +186,51 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                 if ((a & 31) == lane) inP |= 1u << (a >> 5);
             }
             if (np == 0) break;
-            // rebuild the factor and z = L^-1 c_P row by row
-            zl = 0.0;
-            #pragma unroll 1
-            for (int i = 0; i < np; ++i) {
-                int pi = P[i];
-                double t = (lane < i) ? T[(size_t)pi * ldT + P[lane]] : 0.0;
-                double vr = fwd_subst(Lp, rd, i, t, lane);
-                double vv = warp_sum(lane < i ? vr * vr : 0.0);
-                double vz = warp_sum(lane < i ? vr * zl : 0.0);
-                double dd2 = T[(size_t)pi * ldT + pi] - vv;
-                double dd = sqrt(dd2 > 0.0 ? dd2 : 1e-300);
-                if (lane < i) Lp[tri(i, lane)] = vr;
-                if (lane == i) {
-                    Lp[tri(i, i)] = dd;
-                    rd[i] = 1.0 / dd;
-                    zl = (c[pi] - vz) / dd;
+            // Cholesky downdate (column deletion) by Givens rotations, one removed position at a time, highest first;
+            // z = L^-1 c_P is rotated along (the reference updates its QR the same way)
+            {
+                unsigned rmask = ~kmask & (np_old >= 32 ? 0xffffffffu : ((1u << np_old) - 1u));
+                int pn = np_old;
+                while (rmask) {
+                    const int q = 31 - __clz(rmask);
+                    rmask &= ~(1u << q);
+                    // rows q+1.. move up one slot; the element beyond a row's packed capacity stays in register e
+                    double e = 0.0;
+                    const bool mine = (lane >= q) && (lane < pn - 1);
+#pragma unroll 1
+                    for (int col = 0; col < pn; ++col) {
+                        const bool act = mine && (col <= lane + 1);
+                        double lv = 0.0;
+                        if (act) lv = Lp[tri(lane + 1, col)];
+                        __syncwarp();
+                        if (act) {
+                            if (col <= lane) Lp[tri(lane, col)] = lv;
+                            else e = lv;
+                        }
+                    }
+                    __syncwarp();
+#pragma unroll 1
+                    for (int r = q; r < pn - 1; ++r) {
+                        const double a = Lp[tri(r, r)];
+                        const double b = shfl(e, r);
+                        const double ir = 1.0 / sqrt(fma(a, a, b * b));
+                        const double cs = a * ir, sn = b * ir;
+                        if (lane >= r && lane < pn - 1) {
+                            const double u1 = (lane == r) ? a : Lp[tri(lane, r)];
+                            const double u2 = (lane == r) ? e : Lp[tri(lane, r + 1)];
+                            const double n1 = fma(cs, u1, sn * u2), n2 = fma(cs, u2, -sn * u1);
+                            Lp[tri(lane, r)] = n1;
+                            if (lane > r) Lp[tri(lane, r + 1)] = n2;
+                            else rd[r] = 1.0 / n1;
+                        }
+                        const double zr = shfl(zl, r), zr1 = shfl(zl, r + 1);
+                        if (lane == r) zl = fma(cs, zr, sn * zr1);
+                        else if (lane == r + 1) zl = fma(cs, zr1, -sn * zr);
+                        __syncwarp();
+                    }
+                    if (lane >= pn - 1) zl = 0.0;
+                    --pn;
                 }
-                __syncwarp();
             }
         }
         if (lane < np) {

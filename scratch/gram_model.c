@@ -91,8 +91,27 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
             if (jj < 0) break;
             for (a = 0; a < np_; ++a) x[P[a]] += alpha * (s[a] - x[P[a]]);
             x[P[jj]] = 0;
-            { int q = 0; for (a = 0; a < np_; ++a) { if (x[P[a]] <= 0) { inP[P[a]] = 0; x[P[a]] = 0; ++nrem; } else P[q++] = P[a]; } np_ = q; }
+            int removed[CAP], nremoved = 0, oldnp = np_;
+            { int q = 0; for (a = 0; a < np_; ++a) { if (x[P[a]] <= 0) { inP[P[a]] = 0; x[P[a]] = 0; ++nrem; removed[nremoved++] = a; } else P[q++] = P[a]; } np_ = q; }
             if (np_ == 0) break;
+            if (mode & 4) {
+                /* Givens downdate: rem[] holds removed positions (ascending) of the OLD ordering */
+                for (int ri = nremoved - 1; ri >= 0; --ri) {
+                    int q = removed[ri], pn = oldnp;  /* current size before this removal */
+                    /* delete row q */
+                    for (int r2 = q; r2 < pn - 1; ++r2) { for (int c2 = 0; c2 <= r2 + 1; ++c2) L[r2][c2] = L[r2 + 1][c2]; }
+                    for (int r2 = q; r2 < pn - 1; ++r2) {
+                        double a_ = L[r2][r2], b_ = L[r2][r2 + 1], rho = sqrt(a_ * a_ + b_ * b_), cs = a_ / rho, sn = b_ / rho;
+                        for (int i2 = r2; i2 < pn - 1; ++i2) {
+                            double u1 = L[i2][r2], u2 = L[i2][r2 + 1];
+                            L[i2][r2] = cs * u1 + sn * u2; L[i2][r2 + 1] = -sn * u1 + cs * u2;
+                        }
+                        double z1 = z[r2], z2 = z[r2 + 1];
+                        z[r2] = cs * z1 + sn * z2; z[r2 + 1] = -sn * z1 + cs * z2;
+                    }
+                    oldnp = pn - 1;
+                }
+            } else
             chol_rebuild(H, ld, P, np_, L, c, z);
         }
         for (a = 0; a < np_; ++a) x[P[a]] = s[a];
