@@ -76,7 +76,7 @@ struct amx_plan {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
-    DevBuf lut, order, bins, tiles, status, scratch, st_y, st_dirs, st_est, st_rmse, st_nrmse, st_extra, st_sup, st_coef;
+    DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, st_y, st_dirs, st_est, st_rmse, st_nrmse, st_extra, st_sup, st_coef;
     int max_smem = 0, sm_count = 0;
     // last-call records
     double last_ms[8] = {0};
@@ -198,7 +198,7 @@ int amx_plan_destroy(amx_plan *pl)
     void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
-    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->st_y, &pl->st_dirs, &pl->st_est,
+    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask, &pl->st_y, &pl->st_dirs, &pl->st_est,
                       &pl->st_rmse, &pl->st_nrmse, &pl->st_extra, &pl->st_sup, &pl->st_coef};
     for (DevBuf *b : bufs) b->release();
     for (auto &ev : pl->ev) if (ev) cudaEventDestroy(ev);
@@ -353,6 +353,22 @@ int launch_noddi_batched(const FitParams &p, int grid, int block, size_t smem, c
     return AMX_OK;
 }
 
+template <int NPL>
+int launch_noddi_split(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+{
+    auto k1 = k_noddi_stage<1, NPL, float>;
+    auto k2 = k_noddi_stage<2, NPL, float>;
+    auto k3 = k_noddi_stage<3, NPL, float>;
+    CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k1<<<grid, block, smem, st>>>(p);
+    k2<<<grid, block, smem, st>>>(p);
+    k3<<<grid, block, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return AMX_OK;
+}
+
 template <int MODEL, int NPL, typename TS>
 int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
@@ -366,6 +382,14 @@ int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_
 template <int MODEL, typename TS>
 int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
+    if (MODEL == MODEL_NODDI && p.batched == 2) {
+        switch (npl) {
+        case 1: return launch_noddi_split<1>(p, grid, block, smem, st);
+        case 2: return launch_noddi_split<2>(p, grid, block, smem, st);
+        case 3: case 4: return launch_noddi_split<4>(p, grid, block, smem, st);
+        case 5: return launch_noddi_split<5>(p, grid, block, smem, st);
+        }
+    }
     if (MODEL == MODEL_NODDI && p.batched) {
         switch (npl) {
         case 1: return launch_noddi_batched<1>(p, grid, block, smem, st);
@@ -457,7 +481,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.Rs = pl->d_Rs; p.sandi_norms = pl->d_sandi_norms; p.d_in = pl->d_d_in; p.d_isos = pl->d_d_isos;
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
-    p.batched = batched ? 1 : 0;
+    p.batched = batched ? (env_int("AMX_NODDI_SPLIT", 1) ? 2 : 1) : 0;
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad);
@@ -483,6 +507,10 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     if (p.batched) {
         CK(pl->scratch.reserve((size_t)grid * nwarps * 2 * BV * p.NA * sizeof(double)));
         p.scratch = (double *)pl->scratch.p;
+        CK(pl->xiso.reserve((size_t)n_vox * 2 * sizeof(double)));
+        CK(pl->supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
+        p.xiso = (double *)pl->xiso.p;
+        p.supmask = (unsigned *)pl->supmask.p;
     }
     int rc;
     switch (pl->model) {
@@ -492,7 +520,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     default: rc = dispatch_npl<MODEL_SANDI, double>(pl->npl, p, grid, nwarps * 32, smem, st); break;
     }
     if (rc) return rc;
-    *launches += 1;
+    *launches += (p.batched == 2) ? 3 : 1;
     CK(cudaEventRecord(pl->ev[2], st));
     pl->last_cnt[1] = n_tiles;
     pl->last_cnt[3] = (int64_t)smem;

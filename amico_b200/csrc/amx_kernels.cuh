@@ -204,6 +204,8 @@ struct FitParams {
     int m_pad, dc_pad;
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
+    double *xiso;        // split NODDI path: [n_vox][2] (x_iso, x_dot) by sorted position
+    unsigned *supmask;   // split NODDI path: [n_vox][NPL] stage-2 support, word s bit l <-> atom l + 32 s
 };
 
 struct WarpWS {
@@ -326,8 +328,10 @@ __device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *
         for (int t = 0; t < NT; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
     }
     double *o = out + (size_t)g * NA + 2 * kk;
+    if (vvalid) {
 #pragma unroll
-    for (int t = 0; t < NT; ++t) *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+        for (int t = 0; t < NT; ++t) *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+    }
     __syncwarp();
 }
 
@@ -373,7 +377,7 @@ __device__ __noinline__ void gemm_c2(const TS *S, int n_pad, int n, int n_wm, in
     }
     nx += __shfl_xor_sync(FULL, nx, 1);
     nx += __shfl_xor_sync(FULL, nx, 2);
-    if (kk == 0) normx[g] = nx;
+    if (kk == 0) normx[g] = nx;  // g < BV always
     double *o = out + (size_t)g * NA + 2 * kk;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
@@ -745,6 +749,119 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
             }
             if (overflow) ++n_overflow;
             __syncwarp();
+        }
+    }
+    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
+}
+
+// ------------------------------------------------------------------------------------------------
+// NODDI as three stage kernels over the same batch queue (STAGE 1: NNLS for the isotropic fraction, 2: LARS support
+// selection, 3: NNLS on the support + maps).  Same arithmetic as k_fit_noddi_batched; the split exists because the
+// fused kernel's ~90 KB of SASS thrashes the instruction cache once 16 independent warps per SM sit in different
+// solvers (ncu: `no_instruction` was the top stall).  Each stage kernel keeps one solver hot.  Between stages only
+// 16 B (x_iso, x_dot) + 4 NPL B (support mask) per voxel travel through HBM; stage 3 recomputes c1 = A^T y on the
+// tensor pipe instead of storing 1.2 KB per voxel.
+template <int STAGE, int NPL, typename TS>
+__global__ void __launch_bounds__(512, 1) k_noddi_stage(const FitParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad);
+    constexpr int NT = 4 * NPL;
+    const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
+    double *scr = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)BV * NA;
+    const int g = lane >> 2;
+    unsigned all = 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
+    long long n_overflow = 0;
+    int *counter = p.tile_counter + (STAGE - 1);
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1);
+        b = __shfl_sync(FULL, b, 0);
+        if (b >= p.n_tiles) break;
+        const int4 tile = p.tiles[b];
+        const int nb = tile.z;  // <= BV
+        const TS *S = (const TS *)p.slab + (size_t)tile.x * p.slab_stride;
+        const bool vvalid = g < nb;
+        const long long mypos = tile.y + (vvalid ? g : 0);
+        const long long myvox = (long long)p.order[mypos];
+        if (STAGE == 2) {
+            const double *T2 = p.T2 + (size_t)tile.x * p.T2_stride;
+            const double xi = p.xiso[2 * mypos], xd = p.xiso[2 * mypos + 1];
+            if (p.norms_const)
+                gemm_c2<NT, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms,
+                                      n_wm, scr, NA, ws.bx, lane);
+            else
+                gemm_c2<NT, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms,
+                                       n_wm, scr, NA, ws.bx, lane);
+            #pragma unroll 1
+            for (int v = 0; v < nb; ++v) {
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
+                __syncwarp();
+                int ov = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat,
+                                        ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) {
+                    const int j = lane + 32 * s;
+                    const unsigned w = __ballot_sync(FULL, (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n));
+                    if (lane == s) p.supmask[(size_t)(tile.y + v) * NPL + s] = w;
+                }
+                if (ov) ++n_overflow;
+                __syncwarp();
+            }
+        } else {
+            const double *T1 = p.T1 + (size_t)tile.x * p.T1_stride;
+            gemm_c1<NT, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane);
+            #pragma unroll 1
+            for (int v = 0; v < nb; ++v) {
+                const long long pos = tile.y + v;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
+                __syncwarp();
+                if (STAGE == 1) {  // isotropic fraction (amico/models.pyx:911)
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
+                    if (lane == 0) {
+                        p.xiso[2 * pos] = ws.x[n - 1];
+                        p.xiso[2 * pos + 1] = p.exvivo ? ws.x[n - 2] : 0.0;
+                    }
+                    if (ov) ++n_overflow;
+                } else {  // debias on the support (:929-942), maps
+                    const long long vox = (long long)p.order[pos];
+                    unsigned allowed = 0;
+                    int support = 0;
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        const unsigned w = p.supmask[(size_t)pos * NPL + s];
+                        allowed |= ((w >> lane) & 1u) << s;
+                        support += __popc(w);
+                    }
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
+                    noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
+                                    (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
+                    if (p.support_out && lane == 0) p.support_out[vox] = support;
+                    if (p.coeff_out)
+                        for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
+                    if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {
+                        if (p.y_f64) {
+                            const double *yg = (const double *)p.y + vox * m;
+                            #pragma unroll 1
+                            for (int i = lane; i < m; i += 32) ws.y[i] = yg[i];
+                        } else {
+                            const float *yg = (const float *)p.y + vox * m;
+                            #pragma unroll 1
+                            for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
+                        }
+                        __syncwarp();
+                        fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
+                                            p.nrmse ? p.nrmse + vox : nullptr, lane);
+                    }
+                    if (ov) ++n_overflow;
+                }
+                __syncwarp();
+            }
         }
     }
     if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);

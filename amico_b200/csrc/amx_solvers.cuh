@@ -72,25 +72,25 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             valid |= (ok ? 1u : 0u) << s;
             wl[s] = ok ? c[j] : 0.0;
         }
-        {   // rows of T are L2-resident: keep the next row in flight while the current one is consumed
-            double nxt[NPL];
-            const double *row = T + (size_t)(np > 0 ? P[0] : 0) * ldT;
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) nxt[s] = (np > 0 && ((valid >> s) & 1u)) ? row[lane + 32 * s] : 0.0;
+        {   // rows of T are L2-resident (~300 cycles): fetch GD rows at a time
+            constexpr int GD = (NPL <= 2) ? 4 : 3;
 #pragma unroll 1
-            for (int k = 0; k < np; ++k) {
-                double cur[NPL];
+            for (int k0 = 0; k0 < np; k0 += GD) {
+                double gq[GD][NPL];
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) cur[s] = nxt[s];
-                const double xk = x[P[k]];
-                if (k + 1 < np) {
-                    row = T + (size_t)P[k + 1] * ldT;
+                for (int q = 0; q < GD; ++q) {
+                    const double *row = T + (size_t)P[min(k0 + q, np - 1)] * ldT;
 #pragma unroll
-                    for (int s = 0; s < NPL; ++s)
-                        if ((valid >> s) & 1u) nxt[s] = row[lane + 32 * s];
+                    for (int s = 0; s < NPL; ++s) gq[q][s] = ((valid >> s) & 1u) ? row[lane + 32 * s] : 0.0;
                 }
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) wl[s] = fma(-cur[s], xk, wl[s]);
+                for (int q = 0; q < GD; ++q) {
+                    if (k0 + q < np) {
+                        const double xk = x[P[k0 + q]];
+#pragma unroll
+                        for (int s = 0; s < NPL; ++s) wl[s] = fma(-gq[q][s], xk, wl[s]);
+                    }
+                }
             }
         }
         // candidate selection
@@ -351,18 +351,29 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
         double sl[NPL];
 #pragma unroll
         for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
+        // The Gram rows are L2-resident (~300 cycles): fetch GD rows at a time, then accumulate them in path order.
+        constexpr int GD = (NPL <= 2) ? 4 : 3;
 #pragma unroll 1
-        for (int j = 0; j <= i; ++j) {
-            int aj = ind[j];
-            double uj = u[j];
-            const double *row = T + (size_t)aj * ldT;
+        for (int j0 = 0; j0 <= i; j0 += GD) {
+            double gq[GD][NPL];
+            int aq[GD];
 #pragma unroll
-            for (int s = 0; s < NPL; ++s) {
-                int k = lane + 32 * s;
-                if (k < K) {
-                    double gv = row[k];
-                    if (k == aj) gv = __dadd_rn(gv, ridge);
-                    sl[s] = madd(sl[s], gv, uj);
+            for (int q = 0; q < GD; ++q) {
+                aq[q] = ind[min(j0 + q, i)];
+                const double *row = T + (size_t)aq[q] * ldT;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) gq[q][s] = (lane + 32 * s < K) ? row[lane + 32 * s] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < GD; ++q) {
+                if (j0 + q <= i) {
+                    const double uj = u[j0 + q];
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        double gv = gq[q][s];
+                        if (lane + 32 * s == aq[q]) gv = __dadd_rn(gv, ridge);
+                        if (lane + 32 * s < K) sl[s] = madd(sl[s], gv, uj);
+                    }
                 }
             }
         }
