@@ -353,12 +353,12 @@ int launch_noddi_batched(const FitParams &p, int grid, int block, size_t smem, c
     return AMX_OK;
 }
 
-template <int NPL>
-int launch_noddi_split(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+template <int NPL, int MAXT>
+int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
-    auto k1 = k_noddi_stage<1, NPL, float>;
-    auto k2 = k_noddi_stage<2, NPL, float>;
-    auto k3 = k_noddi_stage<3, NPL, float>;
+    auto k1 = k_noddi_stage<1, NPL, float, MAXT>;
+    auto k2 = k_noddi_stage<2, NPL, float, MAXT>;
+    auto k3 = k_noddi_stage<3, NPL, float, MAXT>;
     CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -367,6 +367,13 @@ int launch_noddi_split(const FitParams &p, int grid, int block, size_t smem, cud
     k3<<<grid, block, smem, st>>>(p);
     CK(cudaGetLastError());
     return AMX_OK;
+}
+
+template <int NPL>
+int launch_noddi_split(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+{
+    if (block > 512) return launch_noddi_split_t<NPL, 768>(p, grid, block, smem, st);
+    return launch_noddi_split_t<NPL, 512>(p, grid, block, smem, st);
 }
 
 template <int MODEL, int NPL, typename TS>
@@ -484,12 +491,13 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.batched = batched ? (env_int("AMX_NODDI_SPLIT", 1) ? 2 : 1) : 0;
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
-    p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad);
+    p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);
 
     // shared-memory budget: [header 128][slab (optional)][nwarps x workspace]
     const size_t ws_bytes = (size_t)p.ws_doubles * sizeof(double);
     const size_t budget = (size_t)pl->max_smem;
-    const int want_warps = std::min(16, std::max(1, env_int("AMX_WARPS", 16)));
+    const int max_warps = (batched && env_int("AMX_NODDI_SPLIT", 1)) ? 24 : 16;
+    const int want_warps = std::min(max_warps, std::max(1, env_int("AMX_WARPS", max_warps)));
     const int min_staged_warps = std::max(1, env_int("AMX_MIN_STAGED_WARPS", 8));
     bool staged = !batched && env_int("AMX_NO_TMA", 0) == 0 && 128 + (size_t)pl->slab_bytes + ws_bytes * min_staged_warps <= budget;
     size_t fixed = 128 + (staged ? pl->slab_bytes : 0);
@@ -500,7 +508,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.ws_smem_off = (unsigned)fixed;
     p.nwarps = nwarps;
     const size_t smem = fixed + ws_bytes * nwarps;
-    int ctas_per_sm = std::max(1, (int)std::min<size_t>(budget / smem, (size_t)(16 / nwarps)));
+    int ctas_per_sm = std::max(1, (int)std::min<size_t>(budget / smem, (size_t)std::max(1, 16 / nwarps)));
     if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
     int grid = std::max(1, std::min(n_tiles, pl->sm_count * ctas_per_sm));
 

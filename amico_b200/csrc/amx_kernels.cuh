@@ -214,13 +214,14 @@ struct WarpWS {
 };
 
 constexpr int BV = 8;  // voxels per DMMA micro-batch (the M of m8n8k4)
-__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad) { return 3u * NA + TRI + 3 * LC + LC / 2 + 3 * BV + m_pad + dc_pad; }
+// alias: the stage kernels never need c1 and dtr at the same time -> one array
+__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad, int alias = 0) { return (alias ? 2u : 3u) * NA + TRI + 3 * LC + LC / 2 + 3 * BV + m_pad + dc_pad; }
 
-__device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad)
+__device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad, int alias = 0)
 {
     WarpWS w;
     w.c1 = base; base += NA;
-    w.dtr = base; base += NA;
+    w.dtr = alias ? w.c1 : base; base += alias ? 0 : NA;
     w.x = base; base += NA;
     w.mat = base; base += TRI;
     w.rd = base; base += LC;
@@ -307,87 +308,95 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 // c1[v][k] = sum_r y_v[r] A[r][k] for the batch's voxels -> out[v * NA + k]   (NODDI stage 1 / stage 3 right-hand side)
-template <int NT, typename TS>
+template <int NT, int TP, typename TS>
 __device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *y, int y_f64, long long myvox, bool vvalid,
                                      double *out, int NA, int lane)
 {
-    double acc[NT][2];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
     const int kk = lane & 3, g = lane >> 2;
     const float *yf = (const float *)y + myvox * m;
     const double *yd = (const double *)y + myvox * m;
 #pragma unroll 1
-    for (int r0 = 0; r0 < m; r0 += 4) {
-        const int r = r0 + kk;
-        const bool rv = r < m;
-        double a = 0.0;
-        if (rv && vvalid) a = y_f64 ? yd[r] : (double)yf[r];
-        const TS *row = S + (size_t)(rv ? r : m - 1) * n_pad + g;
+    for (int t0 = 0; t0 < NT; t0 += TP) {
+        double acc[TP][2];
 #pragma unroll
-        for (int t = 0; t < NT; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
-    }
-    double *o = out + (size_t)g * NA + 2 * kk;
-    if (vvalid) {
+        for (int t = 0; t < TP; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 1
+        for (int r0 = 0; r0 < m; r0 += 4) {
+            const int r = r0 + kk;
+            const bool rv = r < m;
+            double a = 0.0;
+            if (rv && vvalid) a = y_f64 ? yd[r] : (double)yf[r];
+            const TS *row = S + (size_t)(rv ? r : m - 1) * n_pad + g + 8 * t0;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+            for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
+        }
+        double *o = out + (size_t)g * NA + 2 * kk + 8 * t0;
+        if (vvalid) {
+#pragma unroll
+            for (int t = 0; t < TP; ++t) *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(acc[t][0], acc[t][1]);
+        }
     }
     __syncwarp();
 }
 
 // NODDI stage 2 right-hand side for the batch: y2 = max(y_R - x_iso iso_R [- x_dot], 0) (amico/models.pyx:918-925),
 // c2[v][k] = sum_j (A[R_j][k] norms[j][k]) y2_v[j]; also ||y2_v||^2 -> normx[v].
-template <int NT, typename TS, bool NC>
+template <int NT, int TP, typename TS, bool NC>
 __device__ __noinline__ void gemm_c2(const TS *S, int n_pad, int n, int n_wm, int dc, const int *__restrict__ rows, const void *y,
                                      int y_f64, int m, long long myvox, bool vvalid, double xiso, double xdot, int exvivo,
                                      const double *__restrict__ norms, int ldn, double *out, int NA, double *normx, int lane)
 {
-    double acc[NT][2];
-#pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
     const int kk = lane & 3, g = lane >> 2;
     const float *yf = (const float *)y + myvox * m;
     const double *yd = (const double *)y + myvox * m;
-    double nx = 0.0;
 #pragma unroll 1
-    for (int j0 = 0; j0 < dc; j0 += 4) {
-        const int jj = j0 + kk;
-        const bool jv = jj < dc;
-        const int r = rows[jv ? jj : dc - 1];
-        const TS *row = S + (size_t)r * n_pad;
-        double a = 0.0;
-        if (jv && vvalid) {
-            a = (y_f64 ? yd[r] : (double)yf[r]) - xiso * (double)row[n - 1];
-            if (exvivo) a = a - xdot * 1.0;
-            a = a < 0.0 ? 0.0 : a;
-        }
-        nx = fma(a, a, nx);
-        row += g;
-        if (NC) {
+    for (int t0 = 0; t0 < NT; t0 += TP) {
+        double acc[TP][2];
 #pragma unroll
-            for (int t = 0; t < NT; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
-        } else {
-            const double *nr = norms + (size_t)(jv ? jj : dc - 1) * ldn + g;
+        for (int t = 0; t < TP; ++t) acc[t][0] = acc[t][1] = 0.0;
+        double nx = 0.0;
+#pragma unroll 1
+        for (int j0 = 0; j0 < dc; j0 += 4) {
+            const int jj = j0 + kk;
+            const bool jv = jj < dc;
+            const int r = rows[jv ? jj : dc - 1];
+            const TS *row = S + (size_t)r * n_pad;
+            double a = 0.0;
+            if (jv && vvalid) {
+                a = (y_f64 ? yd[r] : (double)yf[r]) - xiso * (double)row[n - 1];
+                if (exvivo) a = a - xdot * 1.0;
+                a = a < 0.0 ? 0.0 : a;
+            }
+            nx = fma(a, a, nx);
+            row += g + 8 * t0;
+            if (NC) {
 #pragma unroll
-            for (int t = 0; t < NT; ++t) {
-                const double sc = (g + 8 * t < n_wm) ? nr[8 * t] : 0.0;
-                dmma(acc[t][0], acc[t][1], a, __dmul_rn((double)row[8 * t], sc));
+                for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
+            } else {
+                const double *nr = norms + (size_t)(jv ? jj : dc - 1) * ldn + g + 8 * t0;
+#pragma unroll
+                for (int t = 0; t < TP; ++t) {
+                    const double sc = (g + 8 * (t0 + t) < n_wm) ? nr[8 * t] : 0.0;
+                    dmma(acc[t][0], acc[t][1], a, __dmul_rn((double)row[8 * t], sc));
+                }
             }
         }
-    }
-    nx += __shfl_xor_sync(FULL, nx, 1);
-    nx += __shfl_xor_sync(FULL, nx, 2);
-    if (kk == 0) normx[g] = nx;  // g < BV always
-    double *o = out + (size_t)g * NA + 2 * kk;
-#pragma unroll
-    for (int t = 0; t < NT; ++t) {
-        double c0 = acc[t][0], c1 = acc[t][1];
-        if (NC) {
-            const int k0 = 8 * t + 2 * kk;
-            c0 = (k0 < n_wm) ? c0 * norms[k0] : 0.0;
-            c1 = (k0 + 1 < n_wm) ? c1 * norms[k0 + 1] : 0.0;
+        if (t0 == 0) {
+            nx += __shfl_xor_sync(FULL, nx, 1);
+            nx += __shfl_xor_sync(FULL, nx, 2);
+            if (kk == 0) normx[g] = nx;  // g < BV always
         }
-        *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(c0, c1);
+        double *o = out + (size_t)g * NA + 2 * kk + 8 * t0;
+#pragma unroll
+        for (int t = 0; t < TP; ++t) {
+            double c0 = acc[t][0], c1 = acc[t][1];
+            if (NC) {
+                const int k0 = 8 * (t0 + t) + 2 * kk;
+                c0 = (k0 < n_wm) ? c0 * norms[k0] : 0.0;
+                c1 = (k0 + 1 < n_wm) ? c1 * norms[k0 + 1] : 0.0;
+            }
+            if (vvalid) *reinterpret_cast<double2 *>(o + 8 * t) = make_double2(c0, c1);
+        }
     }
     __syncwarp();
 }
@@ -664,7 +673,7 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad);
-    constexpr int NT = 4 * NPL;
+    constexpr int NT = 4 * NPL, TP = NT;
     const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
     double *scr1 = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)(2 * BV) * NA;
     double *scr2 = scr1 + (size_t)BV * NA;
@@ -685,7 +694,7 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
         const double *T2 = p.T2 + (size_t)tile.x * p.T2_stride;
         const bool vvalid = g < nb;
         const long long myvox = (long long)p.order[tile.y + (vvalid ? g : 0)];
-        gemm_c1<NT, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr1, NA, lane);
+        gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr1, NA, lane);
         // stage 1 per voxel: isotropic fraction (amico/models.pyx:911)
         #pragma unroll 1
         for (int v = 0; v < nb; ++v) {
@@ -702,10 +711,10 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
         }
         // stage 2 right-hand sides for the whole batch (:914-925)
         if (p.norms_const)
-            gemm_c2<NT, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
+            gemm_c2<NT, TP, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
                                   ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
         else
-            gemm_c2<NT, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
+            gemm_c2<NT, TP, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
                                    ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
         #pragma unroll 1
         for (int v = 0; v < nb; ++v) {
@@ -761,13 +770,13 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
 // solvers (ncu: `no_instruction` was the top stall).  Each stage kernel keeps one solver hot.  Between stages only
 // 16 B (x_iso, x_dot) + 4 NPL B (support mask) per voxel travel through HBM; stage 3 recomputes c1 = A^T y on the
 // tensor pipe instead of storing 1.2 KB per voxel.
-template <int STAGE, int NPL, typename TS>
-__global__ void __launch_bounds__(512, 1) k_noddi_stage(const FitParams p)
+template <int STAGE, int NPL, typename TS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad);
-    constexpr int NT = 4 * NPL;
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad, 1);
+    constexpr int NT = 4 * NPL, TP = (MAXT > 512 && NT % 2 == 0) ? NT / 2 : NT;
     const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
     double *scr = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)BV * NA;
     const int g = lane >> 2;
@@ -791,10 +800,10 @@ __global__ void __launch_bounds__(512, 1) k_noddi_stage(const FitParams p)
             const double *T2 = p.T2 + (size_t)tile.x * p.T2_stride;
             const double xi = p.xiso[2 * mypos], xd = p.xiso[2 * mypos + 1];
             if (p.norms_const)
-                gemm_c2<NT, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms,
+                gemm_c2<NT, TP, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms,
                                       n_wm, scr, NA, ws.bx, lane);
             else
-                gemm_c2<NT, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms,
+                gemm_c2<NT, TP, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms,
                                        n_wm, scr, NA, ws.bx, lane);
             #pragma unroll 1
             for (int v = 0; v < nb; ++v) {
@@ -814,7 +823,7 @@ __global__ void __launch_bounds__(512, 1) k_noddi_stage(const FitParams p)
             }
         } else {
             const double *T1 = p.T1 + (size_t)tile.x * p.T1_stride;
-            gemm_c1<NT, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane);
+            gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane);
             #pragma unroll 1
             for (int v = 0; v < nb; ++v) {
                 const long long pos = tile.y + v;
