@@ -73,10 +73,12 @@ struct amx_plan {
     double *d_norms = nullptr;
     float *d_icvf = nullptr, *d_kappa = nullptr;
     double *d_Rs = nullptr, *d_sandi_norms = nullptr, *d_d_in = nullptr, *d_d_isos = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
-    DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, st_y, st_dirs, st_est, st_rmse, st_nrmse, st_extra, st_sup, st_coef;
+    DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask;
+    struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
     int max_smem = 0, sm_count = 0;
     // last-call records
     double last_ms[8] = {0};
@@ -105,7 +107,14 @@ int plan_common_init(amx_plan *pl, int device)
     CK(cudaDeviceGetAttribute(&pl->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CK(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
     for (auto &ev : pl->ev) CK(cudaEventCreate(&ev));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pl->ev_comp[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
+    }
     return AMX_OK;
 }
 
@@ -198,11 +207,21 @@ int amx_plan_destroy(amx_plan *pl)
     void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
-    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask, &pl->st_y, &pl->st_dirs, &pl->st_est,
-                      &pl->st_rmse, &pl->st_nrmse, &pl->st_extra, &pl->st_sup, &pl->st_coef};
+    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask};
     for (DevBuf *b : bufs) b->release();
+    for (auto &sg : pl->stg) {
+        DevBuf *sb[] = {&sg.y, &sg.dirs, &sg.est, &sg.rmse, &sg.nrmse, &sg.extra, &sg.sup, &sg.coef, &sg.lut};
+        for (DevBuf *b : sb) b->release();
+    }
     for (auto &ev : pl->ev) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
+        if (pl->ev_comp[i]) cudaEventDestroy(pl->ev_comp[i]);
+        if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
+    }
     if (pl->stream) cudaStreamDestroy(pl->stream);
+    if (pl->s_in) cudaStreamDestroy(pl->s_in);
+    if (pl->s_out) cudaStreamDestroy(pl->s_out);
     delete pl;
     return AMX_OK;
 }
@@ -415,28 +434,24 @@ int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, 
     return fail(AMX_E_INVALID, "unsupported atom count (npl=%d)", npl);
 }
 
-// Enqueue LUT index + binning + fused fit for device-resident voxels.  All pointers are device pointers.
-int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launches)
+// Enqueue LUT index + binning + fit kernels for device-resident voxels; fully asynchronous (the tile count stays on the
+// device, the error / overflow words are read by the caller at the end).  All pointers are device pointers.
+int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launches, long long vox_offset)
 {
     const long long n_vox = a->n_vox;
     const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
     const int tile_v = batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
     const bool rotated = pl->model != AMX_MODEL_SANDI;
     const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
-    CK(pl->status.reserve(64));
     CK(pl->tiles.reserve((size_t)max_tiles * sizeof(int4)));
     CK(pl->bins.reserve(((size_t)4 * pl->ndirs + 8) * sizeof(int)));
     int *bins = (int *)pl->bins.p;
     int *hist = bins, *offs = bins + pl->ndirs, *cursor = bins + 2 * pl->ndirs, *tile_offs = bins + 3 * pl->ndirs,
-        *totals = bins + 4 * pl->ndirs;  // totals[0]=n_tiles, [1]=n binned, [2]=tile counter
+        *totals = bins + 4 * pl->ndirs;  // totals[0]=n_tiles, [1]=n binned, [2..4]=tile counters
     long long *status = (long long *)pl->status.p;
     CK(cudaMemsetAsync(pl->bins.p, 0, ((size_t)4 * pl->ndirs + 8) * sizeof(int), st));
-    {
-        long long init[3] = {0, (long long)1 << 62, 0};
-        CK(cudaMemcpyAsync(status, init, sizeof init, cudaMemcpyHostToDevice, st));
-    }
     CK(cudaEventRecord(pl->ev[0], st));
-    int n_tiles = 0;
+    long long n_tiles_bound = max_tiles;
     int *lut = nullptr;
     if (rotated) {
         if (!a->dirs) return fail(AMX_E_INVALID, "dirs is NULL");
@@ -445,26 +460,16 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
         CK(pl->order.reserve((size_t)n_vox * sizeof(int)));
         const int B = 256;
         const unsigned G = (unsigned)((n_vox + B - 1) / B);
-        k_lut<<<G, B, 0, st>>>(a->dirs, n_vox, pl->d_htable, pl->ndirs, lut, hist, status);
+        k_lut<<<G, B, 0, st>>>(a->dirs, n_vox, pl->d_htable, pl->ndirs, lut, hist, status, vox_offset);
         k_scan_bins<<<1, 1024, 0, st>>>(hist, pl->ndirs, tile_v, offs, cursor, tile_offs, totals);
         k_scatter<<<G, B, 0, st>>>(lut, n_vox, cursor, (int *)pl->order.p);
         k_tiles<<<(pl->ndirs + 127) / 128, 128, 0, st>>>(hist, offs, tile_offs, pl->ndirs, tile_v, (int4 *)pl->tiles.p);
         CK(cudaGetLastError());
         *launches += 4;
-        // the tile count and the error flag decide the launch: one small read-back
-        int h_tot[2];
-        long long h_status[2];
-        CK(cudaMemcpyAsync(h_tot, totals, sizeof h_tot, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(h_status, status, sizeof h_status, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        if (h_status[0]) {
-            pl->last_cnt[6] = h_status[1];
-            return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
-        }
-        n_tiles = h_tot[0];
     } else {
-        n_tiles = (int)((n_vox + tile_v - 1) / tile_v);
-        k_tiles_linear<<<(n_tiles + 127) / 128, 128, 0, st>>>(n_vox, tile_v, (int4 *)pl->tiles.p, n_tiles);
+        const int n_tiles = (int)((n_vox + tile_v - 1) / tile_v);
+        n_tiles_bound = n_tiles;
+        k_tiles_linear<<<(n_tiles + 127) / 128, 128, 0, st>>>(n_vox, tile_v, (int4 *)pl->tiles.p, n_tiles, totals);
         CK(cudaGetLastError());
         *launches += 1;
         if (a->lut_out) CK(cudaMemsetAsync(a->lut_out, 0, (size_t)n_vox * sizeof(int), st));
@@ -479,7 +484,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.T1 = pl->d_T1; p.ldT1 = pl->ldT1; p.T1_stride = pl->T1_stride;
     p.T2 = pl->d_T2; p.ldT2 = pl->ldT2; p.T2_stride = pl->T2_stride; p.K2 = pl->K2;
     p.y = a->y; p.y_f64 = a->y_dtype == AMX_F64; p.n_vox = n_vox;
-    p.order = rotated ? (const int *)pl->order.p : nullptr; p.tiles = (const int4 *)pl->tiles.p; p.n_tiles = n_tiles;
+    p.order = rotated ? (const int *)pl->order.p : nullptr; p.tiles = (const int4 *)pl->tiles.p; p.n_tiles_ptr = totals;
     p.tile_counter = totals + 2;
     p.lambda1 = a->lambda1; p.lambda2 = a->lambda2; p.flags = a->flags;
     p.dwi_rows = pl->d_dwi_rows; p.dc = pl->dc; p.norms = pl->d_norms; p.norms_const = pl->norms_const;
@@ -510,7 +515,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     const size_t smem = fixed + ws_bytes * nwarps;
     int ctas_per_sm = std::max(1, (int)std::min<size_t>(budget / smem, (size_t)std::max(1, 16 / nwarps)));
     if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
-    int grid = std::max(1, std::min(n_tiles, pl->sm_count * ctas_per_sm));
+    int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count * ctas_per_sm));
 
     if (p.batched) {
         CK(pl->scratch.reserve((size_t)grid * nwarps * 2 * BV * p.NA * sizeof(double)));
@@ -530,7 +535,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     if (rc) return rc;
     *launches += (p.batched == 2) ? 3 : 1;
     CK(cudaEventRecord(pl->ev[2], st));
-    pl->last_cnt[1] = n_tiles;
+    pl->last_cnt[1] = n_tiles_bound;  // upper bound; the exact count stays on the device
     pl->last_cnt[3] = (int64_t)smem;
     pl->last_cnt[4] = nwarps;
     pl->last_cnt[5] = staged ? 1 : 0;
@@ -553,67 +558,100 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     if (has_extra && !a->extra) return fail(AMX_E_INVALID, "AMX_FLAG_EXTRA without extra buffer");
     if (a->y_dtype != AMX_F32 && a->y_dtype != AMX_F64) return fail(AMX_E_INVALID, "bad y_dtype %d", a->y_dtype);
     if (pl->model != AMX_MODEL_SANDI && !a->dirs) return fail(AMX_E_INVALID, "dirs is NULL");
+    if (a->space != AMX_SPACE_DEVICE && a->space != AMX_SPACE_HOST) return fail(AMX_E_INVALID, "bad space %d", a->space);
     CK(cudaSetDevice(pl->device));
     pl->timing_valid = false;
     memset(pl->last_cnt, 0, sizeof pl->last_cnt);
     if (a->n_vox == 0) return AMX_OK;
     int launches = 0;
-    int rc = AMX_OK;
     amx_fit_args d = *a;
     if (!has_extra) d.flags &= ~AMX_FLAG_EXTRA;
-    const size_t n = (size_t)a->n_vox, m = (size_t)pl->m;
-    const size_t ybytes = n * m * (a->y_dtype == AMX_F64 ? 8 : 4);
-    const size_t extra_elems = has_extra ? (pl->model == AMX_MODEL_NODDI ? 2 * n : n * m) : 0;
+    const size_t n = (size_t)a->n_vox, m = (size_t)pl->m, nm = (size_t)pl->n_maps;
+    const size_t ysz = a->y_dtype == AMX_F64 ? 8 : 4;
+    const size_t extra_w = has_extra ? (pl->model == AMX_MODEL_NODDI ? 2 : m) : 0;
     cudaStream_t st = pl->stream;
+    if (a->space == AMX_SPACE_DEVICE && a->stream) st = (cudaStream_t)a->stream;
+    CK(pl->status.reserve(64));
+    {
+        long long init[3] = {0, (long long)1 << 62, 0};
+        CK(cudaMemcpyAsync(pl->status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
+    cudaStream_t end_stream = st;
     if (a->space == AMX_SPACE_DEVICE) {
-        if (a->stream) st = (cudaStream_t)a->stream;
         CK(cudaEventRecord(pl->ev[3], st));
-        rc = fit_device(pl, &d, st, &launches);
-    } else if (a->space == AMX_SPACE_HOST) {
-        CK(pl->st_y.reserve(ybytes));
-        CK(pl->st_est.reserve(n * pl->n_maps * sizeof(double)));
-        CK(cudaEventRecord(pl->ev[3], st));
-        CK(cudaMemcpyAsync(pl->st_y.p, a->y, ybytes, cudaMemcpyHostToDevice, st));
-        d.y = pl->st_y.p; d.estimates = (double *)pl->st_est.p;
-        if (a->dirs) {
-            CK(pl->st_dirs.reserve(n * 3 * sizeof(double)));
-            CK(cudaMemcpyAsync(pl->st_dirs.p, a->dirs, n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
-            d.dirs = (double *)pl->st_dirs.p;
-        }
-        if (d.flags & AMX_FLAG_RMSE) { CK(pl->st_rmse.reserve(n * sizeof(double))); d.rmse = (double *)pl->st_rmse.p; }
-        if (d.flags & AMX_FLAG_NRMSE) { CK(pl->st_nrmse.reserve(n * sizeof(double))); d.nrmse = (double *)pl->st_nrmse.p; }
-        if (has_extra) { CK(pl->st_extra.reserve(extra_elems * sizeof(double))); d.extra = (double *)pl->st_extra.p; }
-        if (a->support_out) { CK(pl->st_sup.reserve(n * sizeof(int))); d.support_out = (int *)pl->st_sup.p; }
-        if (a->coeff_out) { CK(pl->st_coef.reserve(n * pl->n * sizeof(double))); d.coeff_out = (double *)pl->st_coef.p; }
-        if (a->lut_out) { CK(pl->lut.reserve(n * sizeof(int))); d.lut_out = (int *)pl->lut.p; }
-        rc = fit_device(pl, &d, st, &launches);
-        // the reference flips DIRs in place before it can fail, so hand the flipped directions back either way
-        if (a->dirs && (rc == AMX_OK || rc == AMX_E_LUT_RANGE))
-            CK(cudaMemcpyAsync(a->dirs, d.dirs, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
-        if (a->lut_out && (rc == AMX_OK || rc == AMX_E_LUT_RANGE))
-            CK(cudaMemcpyAsync(a->lut_out, d.lut_out, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-        if (rc == AMX_OK) {
-            CK(cudaMemcpyAsync(a->estimates, d.estimates, n * pl->n_maps * sizeof(double), cudaMemcpyDeviceToHost, st));
-            if (d.flags & AMX_FLAG_RMSE) CK(cudaMemcpyAsync(a->rmse, d.rmse, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-            if (d.flags & AMX_FLAG_NRMSE) CK(cudaMemcpyAsync(a->nrmse, d.nrmse, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-            if (has_extra) CK(cudaMemcpyAsync(a->extra, d.extra, extra_elems * sizeof(double), cudaMemcpyDeviceToHost, st));
-            if (a->support_out) CK(cudaMemcpyAsync(a->support_out, d.support_out, n * sizeof(int), cudaMemcpyDeviceToHost, st));
-            if (a->coeff_out) CK(cudaMemcpyAsync(a->coeff_out, d.coeff_out, n * pl->n * sizeof(double), cudaMemcpyDeviceToHost, st));
-        }
+        int rc = fit_device(pl, &d, st, &launches, 0);
+        if (rc) { cudaStreamSynchronize(st); return rc; }
     } else {
-        return fail(AMX_E_INVALID, "bad space %d", a->space);
+        // Host buffers: voxel chunks flow through a 3-stream pipeline (H2D | LUT+binning+fit | D2H) over two staging sets,
+        // so the copies of neighbouring chunks hide behind the fit.  Pinned host memory makes the copies truly async.
+        long long chunk = std::max(8192, env_int("AMX_HOST_CHUNK", 262144));
+        if ((long long)n <= chunk + chunk / 2) chunk = (long long)n;
+        const long long n_chunks = ((long long)n + chunk - 1) / chunk;
+        const int nset = n_chunks > 1 ? 2 : 1;
+        for (int b = 0; b < nset; ++b) {
+            amx_plan::Stage &sg = pl->stg[b];
+            CK(sg.y.reserve((size_t)chunk * m * ysz));
+            CK(sg.est.reserve((size_t)chunk * nm * sizeof(double)));
+            if (a->dirs) CK(sg.dirs.reserve((size_t)chunk * 3 * sizeof(double)));
+            if (d.flags & AMX_FLAG_RMSE) CK(sg.rmse.reserve((size_t)chunk * sizeof(double)));
+            if (d.flags & AMX_FLAG_NRMSE) CK(sg.nrmse.reserve((size_t)chunk * sizeof(double)));
+            if (has_extra) CK(sg.extra.reserve((size_t)chunk * extra_w * sizeof(double)));
+            if (a->support_out) CK(sg.sup.reserve((size_t)chunk * sizeof(int)));
+            if (a->coeff_out) CK(sg.coef.reserve((size_t)chunk * pl->n * sizeof(double)));
+            if (a->lut_out) CK(sg.lut.reserve((size_t)chunk * sizeof(int)));
+        }
+        cudaStream_t s_in = n_chunks > 1 ? pl->s_in : st, s_out = n_chunks > 1 ? pl->s_out : st;
+        if (n_chunks > 1) {  // order the side streams after the status reset on the compute stream
+            CK(cudaEventRecord(pl->ev_comp[0], st));
+            CK(cudaStreamWaitEvent(s_in, pl->ev_comp[0], 0));
+        }
+        CK(cudaEventRecord(pl->ev[3], s_in));
+        for (long long i = 0; i < n_chunks; ++i) {
+            const int b = (int)(i & 1) % nset;
+            amx_plan::Stage &sg = pl->stg[b];
+            const size_t off = (size_t)(i * chunk), cnt = (size_t)std::min<long long>(chunk, (long long)n - i * chunk);
+            if (i >= 2) CK(cudaStreamWaitEvent(s_in, pl->ev_comp[b], 0));  // inputs of this set consumed by chunk i-2
+            CK(cudaMemcpyAsync(sg.y.p, (const char *)a->y + off * m * ysz, cnt * m * ysz, cudaMemcpyHostToDevice, s_in));
+            if (a->dirs) CK(cudaMemcpyAsync(sg.dirs.p, a->dirs + off * 3, cnt * 3 * sizeof(double), cudaMemcpyHostToDevice, s_in));
+            amx_fit_args c = d;
+            c.n_vox = (int64_t)cnt;
+            c.y = sg.y.p; c.estimates = (double *)sg.est.p;
+            c.dirs = a->dirs ? (double *)sg.dirs.p : nullptr;
+            c.rmse = (d.flags & AMX_FLAG_RMSE) ? (double *)sg.rmse.p : nullptr;
+            c.nrmse = (d.flags & AMX_FLAG_NRMSE) ? (double *)sg.nrmse.p : nullptr;
+            c.extra = has_extra ? (double *)sg.extra.p : nullptr;
+            c.support_out = a->support_out ? (int *)sg.sup.p : nullptr;
+            c.coeff_out = a->coeff_out ? (double *)sg.coef.p : nullptr;
+            c.lut_out = a->lut_out ? (int *)sg.lut.p : nullptr;
+            if (n_chunks > 1) {
+                CK(cudaEventRecord(pl->ev_in[b], s_in));
+                CK(cudaStreamWaitEvent(st, pl->ev_in[b], 0));
+                if (i >= 2) CK(cudaStreamWaitEvent(st, pl->ev_out[b], 0));  // outputs of this set drained by chunk i-2
+            }
+            int rc = fit_device(pl, &c, st, &launches, (long long)off);
+            if (rc) { cudaDeviceSynchronize(); return rc; }
+            if (n_chunks > 1) {
+                CK(cudaEventRecord(pl->ev_comp[b], st));
+                CK(cudaStreamWaitEvent(s_out, pl->ev_comp[b], 0));
+            }
+            // the reference flips DIRs in place (amico/lut.pyx:335-338): hand the flipped directions back
+            if (a->dirs) CK(cudaMemcpyAsync(a->dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            CK(cudaMemcpyAsync(a->estimates + off * nm, c.estimates, cnt * nm * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.rmse) CK(cudaMemcpyAsync(a->rmse + off, c.rmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.nrmse) CK(cudaMemcpyAsync(a->nrmse + off, c.nrmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.extra) CK(cudaMemcpyAsync(a->extra + off * extra_w, c.extra, cnt * extra_w * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.support_out) CK(cudaMemcpyAsync(a->support_out + off, c.support_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+            if (c.coeff_out) CK(cudaMemcpyAsync(a->coeff_out + off * pl->n, c.coeff_out, cnt * pl->n * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.lut_out) CK(cudaMemcpyAsync(a->lut_out + off, c.lut_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s_out));
+            if (n_chunks > 1) CK(cudaEventRecord(pl->ev_out[b], s_out));
+        }
+        end_stream = s_out;
     }
-    if (rc != AMX_OK) {
-        std::string keep = g_err;
-        cudaStreamSynchronize(st);
-        if (err_voxel) *err_voxel = pl->last_cnt[6];
-        g_err = keep;
-        return rc;
-    }
-    CK(cudaEventRecord(pl->ev[4], st));
+    CK(cudaEventRecord(pl->ev[4], end_stream));
     long long h_status[3] = {0, 0, 0};
-    CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, end_stream));
+    CK(cudaStreamSynchronize(end_stream));
+    if (end_stream != st) CK(cudaStreamSynchronize(st));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->last_ms[0] = ms;
     if (cudaEventElapsedTime(&ms, pl->ev[1], pl->ev[2]) == cudaSuccess) pl->last_ms[1] = ms;
@@ -621,6 +659,11 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     pl->timing_valid = true;
     pl->last_cnt[0] = launches;
     pl->last_cnt[2] = h_status[2];
+    if (h_status[0]) {
+        pl->last_cnt[6] = h_status[1];
+        if (err_voxel) *err_voxel = h_status[1];
+        return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
+    }
     if (h_status[2])
         return fail(AMX_E_CAPACITY, "%lld voxel(s) outgrew the %d-atom active-set workspace", h_status[2], LC);
     return AMX_OK;
@@ -636,15 +679,15 @@ int amx_lut_indices(amx_plan *pl, int space, double *dirs, int64_t n, int32_t *i
     double *d_dirs = dirs;
     int *d_idx = idx;
     if (space == AMX_SPACE_HOST) {
-        CK(pl->st_dirs.reserve((size_t)n * 3 * sizeof(double)));
+        CK(pl->stg[0].dirs.reserve((size_t)n * 3 * sizeof(double)));
         CK(pl->lut.reserve((size_t)n * sizeof(int)));
-        d_dirs = (double *)pl->st_dirs.p; d_idx = (int *)pl->lut.p;
+        d_dirs = (double *)pl->stg[0].dirs.p; d_idx = (int *)pl->lut.p;
         CK(cudaMemcpyAsync(d_dirs, dirs, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
     CK(pl->status.reserve(64));
     long long init[3] = {0, (long long)1 << 62, 0};
     CK(cudaMemcpyAsync(pl->status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
-    k_lut<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_dirs, n, pl->d_htable, pl->ndirs, d_idx, nullptr, (long long *)pl->status.p);
+    k_lut<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_dirs, n, pl->d_htable, pl->ndirs, d_idx, nullptr, (long long *)pl->status.p, 0);
     CK(cudaGetLastError());
     if (space == AMX_SPACE_HOST) {
         CK(cudaMemcpyAsync(dirs, d_dirs, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));

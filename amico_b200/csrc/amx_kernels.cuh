@@ -32,7 +32,7 @@ __device__ __forceinline__ int dir_to_lut_idx(double *d, const int16_t *__restri
 
 // status words: [0] error flag, [1] first offending voxel, [2] workspace-overflow voxel count
 __global__ void k_lut(double *dirs, long long n, const int16_t *__restrict__ htable, int ndirs, int *lut, int *hist,
-                      long long *status)
+                      long long *status, long long vox_offset)
 {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -40,7 +40,7 @@ __global__ void k_lut(double *dirs, long long n, const int16_t *__restrict__ hta
     if (idx < 0 || idx >= ndirs) {
         idx = -1;
         atomicExch((unsigned long long *)&status[0], 1ull);
-        atomicMin(&status[1], i);
+        atomicMin(&status[1], i + vox_offset);
     } else if (hist) {
         atomicAdd(&hist[idx], 1);
     }
@@ -100,9 +100,10 @@ __global__ void k_tiles(const int *hist, const int *offs, const int *tile_offs, 
 }
 
 // tiles of consecutive voxels (models without a direction)
-__global__ void k_tiles_linear(long long n, int tile_v, int4 *tiles, int n_tiles)
+__global__ void k_tiles_linear(long long n, int tile_v, int4 *tiles, int n_tiles, int *totals)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t == 0) totals[0] = n_tiles;
     if (t >= n_tiles) return;
     long long s = (long long)t * tile_v;
     tiles[t] = make_int4(0, (int)s, (int)min((long long)tile_v, n - s), 0);
@@ -189,7 +190,7 @@ struct FitParams {
     const double *T2; int ldT2; size_t T2_stride; int K2;  // LARS system
     // voxels
     const void *y; int y_f64; long long n_vox;
-    const int *order; const int4 *tiles; int n_tiles; int *tile_counter;
+    const int *order; const int4 *tiles; const int *n_tiles_ptr; int *tile_counter;
     double lambda1, lambda2; unsigned flags;
     // NODDI
     const int *dwi_rows; int dc; const double *norms; int norms_const; const float *icvf; const float *kappa; int exvivo;
@@ -494,7 +495,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
         if (threadIdx.x == 0) *s_tile = atomicAdd(p.tile_counter, 1);
         __syncthreads();
         const int t = *s_tile;
-        if (t >= p.n_tiles) break;
+        if (t >= *p.n_tiles_ptr) break;
         const int4 tile = p.tiles[t];
         const int dir = tile.x;
         const TS *Sg = (const TS *)p.slab + (size_t)dir * p.slab_stride;
@@ -682,11 +683,12 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
 #pragma unroll
     for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
     long long n_overflow = 0;
+    const int n_tiles = *p.n_tiles_ptr;
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(p.tile_counter, 1);
         b = __shfl_sync(FULL, b, 0);
-        if (b >= p.n_tiles) break;
+        if (b >= n_tiles) break;
         const int4 tile = p.tiles[b];
         const int nb = tile.z;  // <= BV
         const TS *S = (const TS *)p.slab + (size_t)tile.x * p.slab_stride;
@@ -785,11 +787,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
     for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
     long long n_overflow = 0;
     int *counter = p.tile_counter + (STAGE - 1);
+    const int n_tiles = *p.n_tiles_ptr;
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(counter, 1);
         b = __shfl_sync(FULL, b, 0);
-        if (b >= p.n_tiles) break;
+        if (b >= n_tiles) break;
         const int4 tile = p.tiles[b];
         const int nb = tile.z;  // <= BV
         const TS *S = (const TS *)p.slab + (size_t)tile.x * p.slab_stride;

@@ -284,3 +284,47 @@ def test_full_size_properties():
         Q = synth.Problem(P.cfg, P.model, P.scheme, P.lut_dirs, P.htable, P.KERNELS, P.params, P.y[idx], P.DIRs[idx])
         ref = orc().fit_problem(Q, nthreads=os.cpu_count())
         assert pass_fraction(a.cpu().numpy()[idx], ref["estimates"]) >= 0.999
+
+
+# ----------------------------------------------------------------------------------------------- host pipeline / variants
+def test_chunked_host_pipeline_matches_single_shot(monkeypatch):
+    """The host-pointer path streams voxel chunks through H2D | fit | D2H; any chunking must give the same bits."""
+    P = synth.make_problem(2, n_vox=40000, seed=31)
+    l1, l2 = orc().DEFAULT_LAMBDAS["NODDI"]
+    with make_plan(P) as plan:
+        monkeypatch.setenv("AMX_HOST_CHUNK", "100000000")
+        d0 = np.array(P.DIRs)
+        a = plan.fit(P.y, d0, l1, l2, rmse=True, nrmse=True, extra=True, debug=True)
+        monkeypatch.setenv("AMX_HOST_CHUNK", "8192")  # 5 chunks, the last one ragged
+        d1 = np.array(P.DIRs)
+        b = plan.fit(P.y, d1, l1, l2, rmse=True, nrmse=True, extra=True, debug=True)
+    for k in ("estimates", "rmse", "nrmse", "estimates_mod", "lut", "support", "x"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(d0, d1)
+    # an out-of-range direction in a late chunk reports its GLOBAL voxel index
+    P.DIRs[33333] = [np.nan, 0, 0]
+    with make_plan(P) as plan:
+        with pytest.raises(RuntimeError, match=r"\(voxel 33333\)"):
+            plan.fit(P.y, np.array(P.DIRs), l1, l2)
+
+
+@pytest.mark.parametrize("env", [{"AMX_NODDI_SPLIT": "0"}, {"AMX_NODDI_BATCHED": "0"}, {"AMX_NODDI_BATCHED": "0", "AMX_NO_TMA": "1"},
+                                 {"AMX_WARPS": "8"}])
+def test_noddi_kernel_variants_agree(monkeypatch, env):
+    """Fused / per-voxel / non-TMA variants of the NODDI path are kept for A/B measurements: same maps within tolerance."""
+    P = synth.make_problem(2, n_vox=6000, seed=8)
+    base = gpu_fit(P)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = gpu_fit(P)
+    assert pass_fraction(alt["estimates"], base["estimates"]) >= 0.999
+
+
+def test_noddi_whole_brain_protocol_m288():
+    """cfg3 protocol (18 b0 + 2x135 directions, m = 288): same kernels, bigger rows."""
+    P = synth.make_problem(3, n_vox=6000)
+    ref = orc().fit_problem(P, nthreads=os.cpu_count(), return_debug=True)
+    got = gpu_fit(P, debug=True)
+    assert got["_counters"]["overflow_voxels"] == 0
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
+    assert float((got["support"] == ref["support"]).mean()) >= 0.998
