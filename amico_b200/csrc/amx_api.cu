@@ -65,7 +65,8 @@ struct amx_plan {
     size_t slab_stride = 0;   // elements per direction
     unsigned slab_bytes = 0;  // bytes to stage per direction
     void *d_slab = nullptr;
-    double *d_T1 = nullptr, *d_T2 = nullptr;
+    double *d_T1 = nullptr, *d_T2 = nullptr, *d_diag0 = nullptr;
+    double ridge_baked = -1.0;  // ridge currently added to the diagonal of d_T2 (< 0: none)
     int ldT1 = 0, ldT2 = 0, K2 = 0;
     size_t T1_stride = 0, T2_stride = 0;
     int16_t *d_htable = nullptr;
@@ -204,7 +205,7 @@ int amx_plan_destroy(amx_plan *pl)
 {
     if (!pl) return AMX_OK;
     cudaSetDevice(pl->device);
-    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
+    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_diag0, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
     DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask};
@@ -450,6 +451,19 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
         *totals = bins + 4 * pl->ndirs;  // totals[0]=n_tiles, [1]=n binned, [2..4]=tile counters
     long long *status = (long long *)pl->status.p;
     CK(cudaMemsetAsync(pl->bins.p, 0, ((size_t)4 * pl->ndirs + 8) * sizeof(int), st));
+    {
+        const double ridge = a->lambda2 > 1e-10 ? a->lambda2 : 1e-10;
+        if (ridge != pl->ridge_baked) {
+            if (!pl->d_diag0) {
+                CK(cudaMalloc((void **)&pl->d_diag0, (size_t)pl->ndirs * pl->K2 * sizeof(double)));
+                k_save_diag<<<pl->ndirs, 128, 0, st>>>(pl->d_T2, pl->K2, pl->ldT2, pl->T2_stride, pl->d_diag0);
+            }
+            k_set_ridge<<<pl->ndirs, 128, 0, st>>>(pl->d_T2, pl->K2, pl->ldT2, pl->T2_stride, pl->d_diag0, ridge);
+            CK(cudaGetLastError());
+            pl->ridge_baked = ridge;
+            *launches += 1;
+        }
+    }
     CK(cudaEventRecord(pl->ev[0], st));
     long long n_tiles_bound = max_tiles;
     int *lut = nullptr;
@@ -494,6 +508,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
     p.batched = batched ? (env_int("AMX_NODDI_SPLIT", 1) ? 2 : 1) : 0;
+    p.fast_lars = env_int("AMX_FAST_LARS", 1);
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);

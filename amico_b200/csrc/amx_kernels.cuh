@@ -179,6 +179,20 @@ __global__ void k_gram(const TS *__restrict__ slab, size_t slab_stride, int n_pa
     }
 }
 
+// LARS works on G + ridge I: keep the pristine diagonal and write fl(G_kk + ridge) into the table (the same single
+// rounding the CPU path applies to its Gram column), so the solver loops carry no ridge special case.
+__global__ void k_save_diag(const double *G, int K, int ldG, size_t G_stride, double *diag0)
+{
+    int d = blockIdx.x;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) diag0[(size_t)d * K + k] = G[(size_t)d * G_stride + (size_t)k * ldG + k];
+}
+__global__ void k_set_ridge(double *G, int K, int ldG, size_t G_stride, const double *diag0, double ridge)
+{
+    int d = blockIdx.x;
+    for (int k = threadIdx.x; k < K; k += blockDim.x)
+        G[(size_t)d * G_stride + (size_t)k * ldG + k] = __dadd_rn(diag0[(size_t)d * K + k], ridge);
+}
+
 // ------------------------------------------------------------------------------------------------
 struct FitParams {
     int model, m, n, n_pad, ndirs, n_maps, NA;
@@ -203,6 +217,7 @@ struct FitParams {
     // launch geometry
     int nwarps; unsigned ws_doubles; unsigned slab_smem_off, ws_smem_off;
     int m_pad, dc_pad;
+    int fast_lars;    // NODDI stage 2: throughput-oriented LARS (same path, fused arithmetic)
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
     double *xiso;        // split NODDI path: [n_vox][2] (x_iso, x_dot) by sorted position
@@ -813,8 +828,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
-                int ov = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat,
-                                        ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
+                int ov = p.fast_lars
+                             ? warp_lars_fast<NPL>(T2, p.ldT2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat, ws.u,
+                                                   ws.gs, ws.P, ws.x, lane)
+                             : warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat,
+                                              ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) {
                     const int j = lane + 32 * s;

@@ -246,7 +246,7 @@ done:
 }
 
 // ------------------------------------------------------------------------------------------------
-// Non-negative LARS on G = T + ridge*I (ridge = max(lambda2, 1e-10)), correlations DtR (destroyed),
+// Non-negative LARS on T = G + ridge*I (ridge = max(lambda2, 1e-10), baked into the diagonal), correlations DtR (destroyed),
 // following oracle/amico_oracle.c::lars_core step by step.  Ltrue = min(rows, K) of the underlying
 // least-squares system.  x: per-warp shared output (exact zeros off-support).
 // Mi: packed upper inverse of G_SS; u, gs: LC doubles; ind: LC ints.
@@ -257,7 +257,7 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
                          double *DtR, double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane,
                          int *steps_out)
 {
-    const double ridge = ridge_in > 1e-10 ? ridge_in : 1e-10;
+    (void)ridge_in;  // T already holds G + max(lambda2, 1e-10) I (k_set_ridge)
     int L = Ltrue < K ? Ltrue : K;
     int overflow = 0;
 #pragma unroll
@@ -298,7 +298,6 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
             double g = 0.0;
             if (lane <= i) {
                 g = T[(size_t)cur * ldT + ind_l];
-                if (lane == i) g = __dadd_rn(g, ridge);
                 gs[lane] = g;
             }
             __syncwarp();
@@ -370,9 +369,7 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
                     const double uj = u[j0 + q];
 #pragma unroll
                     for (int s = 0; s < NPL; ++s) {
-                        double gv = gq[q][s];
-                        if (lane + 32 * s == aq[q]) gv = __dadd_rn(gv, ridge);
-                        if (lane + 32 * s < K) sl[s] = madd(sl[s], gv, uj);
+                        if (lane + 32 * s < K) sl[s] = madd(sl[s], gq[q][s], uj);
                     }
                 }
             }
@@ -464,6 +461,209 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
     if (lane < na && ind_l >= 0) x[ind_l] = coef_l;
     __syncwarp();
     if (steps_out) *steps_out = iter;
+    return overflow;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp_lars_fast: the same homotopy path as warp_lars (same entering / leaving rules, same stopping rules) written for
+// throughput instead of bit-for-bit equality with the CPU arithmetic: fused multiply-adds, warp-shuffle reductions for
+// the small sums, reciprocal instead of division for the candidate steps.  Used by NODDI stage 2, where only the SUPPORT
+// of the (unique) elastic-net minimiser is consumed (amico/models.pyx:929-936) and its input already differs from the
+// CPU's at the 1e-12 level through stage 1.
+template <int NPL>
+__device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT, int K, int Ltrue, double lambda1, double *DtR,
+                                           double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane)
+{
+    int L = Ltrue < K ? Ltrue : K;
+    int overflow = 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) x[lane + 32 * s] = 0.0;
+    __syncwarp();
+    if (L <= 0) return 0;
+    int cur;
+    {
+        double bv = 0.0;
+        int bi = -1;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            if (k < K) {
+                double v = DtR[k];
+                if (bi < 0 || v > bv) { bv = v; bi = k; }
+            }
+        }
+        warp_argmax(bv, bi);
+        if (fabs(bv) < lambda1) return 0;
+        cur = bi;
+    }
+    int newAtom = 1, iter = 0, na = 0;
+    double coef_l = 0.0;
+    int ind_l = -1;
+    unsigned act = 0;
+    const int length_path = 4 * L;
+#pragma unroll 1
+    for (int i = 0; i < L; ++i) {
+        if (i < 0) break;
+        ++iter;
+        if (newAtom) {
+            if (i >= LC) { overflow = 1; na = i; break; }
+            if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
+            if ((cur & 31) == lane) act |= 1u << (cur >> 5);
+            __syncwarp();
+            double g = 0.0;
+            if (lane <= i) {
+                g = T[(size_t)cur * ldT + ind_l];
+                gs[lane] = g;
+            }
+            __syncwarp();
+            if (i == 0) {
+                if (lane == 0) Mi[0] = 1.0 / g;
+            } else {
+                double ur = 0.0;
+                if (lane < i) {
+#pragma unroll 1
+                    for (int c = 0; c < i; ++c) ur = fma(sym_at(Mi, lane, c), gs[c], ur);
+                    u[lane] = ur;
+                }
+                const double dot = warp_sum(lane < i ? ur * g : 0.0);
+                const double schur = 1.0 / (shfl(g, i) - dot);
+                __syncwarp();
+                if (lane < i) {
+                    const double su = schur * ur;
+#pragma unroll 1
+                    for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = fma(su, u[k], Mi[tri(k, lane)]);
+                    Mi[tri(i, lane)] = -su;
+                }
+                if (lane == i) Mi[tri(i, i)] = schur;
+            }
+            __syncwarp();
+        }
+        na = i + 1;
+        // path direction u = invGs * sign(DtR_S)
+        double dl = 0.0, sg = 0.0;
+        if (lane <= i) {
+            dl = DtR[ind_l];
+            sg = dl > 0.0 ? 1.0 : -1.0;
+            gs[lane] = sg;
+        }
+        __syncwarp();
+        double ul = 0.0;
+        if (lane <= i) {
+#pragma unroll 1
+            for (int c = 0; c <= i; ++c) ul = fma(sym_at(Mi, lane, c), gs[c], ul);
+            u[lane] = ul;
+        }
+        __syncwarp();
+        // largest step before an active coefficient crosses zero (last index wins ties)
+        double step_max = INFINITY;
+        int fz = -1;
+        if (lane <= i) {
+            double r = -coef_l / ul;
+            if (r > 0.0) { step_max = r; fz = lane; }
+        }
+        warp_argmin<false>(step_max, fz);
+        if (fz < 0) step_max = INFINITY;
+        const double cc = fabs(shfl(dl, 0));
+        // correlation slopes T[:, S] u; rows are L2-resident: fetch GD rows at a time
+        double sl[NPL];
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
+        constexpr int GD = (NPL <= 2) ? 4 : 3;
+#pragma unroll 1
+        for (int j0 = 0; j0 <= i; j0 += GD) {
+            double gq[GD][NPL];
+#pragma unroll
+            for (int q = 0; q < GD; ++q) {
+                const double *row = T + (size_t)ind[min(j0 + q, i)] * ldT + lane;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) gq[q][s] = (lane + 32 * s < K) ? row[32 * s] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < GD; ++q) {
+                const double uj = (j0 + q <= i) ? u[j0 + q] : 0.0;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) sl[s] = fma(gq[q][s], uj, sl[s]);
+            }
+        }
+        // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index
+        double tl[NPL];
+        double bt = INFINITY;
+        int bk = -1;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            tl[s] = INFINITY;
+            if (k < K) {
+                if (!((act >> s) & 1u) && sl[s] < 1.0) tl[s] = (cc - DtR[k]) * __drcp_rn(1.0 - sl[s]);
+                double at = fabs(tl[s]);
+                if (bk < 0 || at < bt) { bt = at; bk = k; }
+            }
+        }
+        warp_argmin<true>(bt, bk);
+        double step;
+        {
+            double mine = 0.0;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s)
+                if (s == (bk >> 5)) mine = tl[s];
+            step = shfl(mine, bk & 31);
+        }
+        cur = bk;
+        const double coeff1 = warp_sum(lane <= i ? sg * ul : 0.0);
+        const double coeff2 = warp_sum(lane <= i ? dl * ul : 0.0);
+        const double step_max2 = cc - lambda1;
+        step = fmin(fmin(step, step_max2), step_max);
+        if (step == INFINITY) break;
+        if (lane <= i) {
+            coef_l = fma(step, ul, coef_l);
+            if (coef_l < 0.0) coef_l = 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            if (k < K) DtR[k] = fma(-step, sl[s], DtR[k]);
+        }
+        normX += coeff1 * step * step - 2.0 * coeff2 * step;
+        __syncwarp();
+        if (step == step_max) {
+            const int z = fz;
+            const int az = ind[z];
+            const double schur_r = Mi[tri(z, z)];
+            double uk = 0.0;
+            if (lane < i) uk = (lane < z) ? Mi[tri(z, lane)] : Mi[tri(lane + 1, z)];
+            __syncwarp();
+            if (lane < i) u[lane] = uk;
+            double cn = __shfl_down_sync(FULL, coef_l, 1);
+            int in_ = __shfl_down_sync(FULL, ind_l, 1);
+            if (lane >= z && lane < i) { coef_l = cn; ind_l = in_; }
+            if (lane == i) { coef_l = 0.0; ind_l = -1; }
+            if ((az & 31) == lane) act &= ~(1u << (az >> 5));
+#pragma unroll 1
+            for (int j = z; j < i; ++j) {
+                double mv = 0.0;
+                if (lane <= j) mv = Mi[tri(j + 1, lane < z ? lane : lane + 1)];
+                __syncwarp();
+                if (lane <= j) Mi[tri(j, lane)] = mv;
+                __syncwarp();
+            }
+            if (lane <= i) ind[lane] = ind_l;
+            __syncwarp();
+            if (lane < i) {
+                const double ir = uk / schur_r;
+#pragma unroll 1
+                for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = fma(-ir, u[k], Mi[tri(k, lane)]);
+            }
+            __syncwarp();
+            newAtom = 0;
+            na = i;
+            i -= 2;
+        } else {
+            newAtom = 1;
+        }
+        if (iter >= length_path - 1 || fabs(step) < 1e-15 || step == step_max2 || normX < 1e-15 || i == L - 1) break;
+    }
+    if (lane < na && ind_l >= 0) x[ind_l] = coef_l;
+    __syncwarp();
     return overflow;
 }
 
