@@ -50,6 +50,21 @@ def workload(cfg, n_vox):
     }
 
 
+def ncu_traffic(n_vox):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fit kernels for one launch, from the committed ncu --set full
+    capture of this same command (profiles/); None when the capture is for another problem size."""
+    p = os.path.join(ROOT, "profiles", "ncu_full_r01_noddi_stage_kernels.json")
+    try:
+        with open(p) as f:
+            ks = json.load(f)
+        if ks and int(ks[0].get("n_vox", 1048576)) == int(n_vox):
+            scale = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+            return float(sum(float(k[m]) * scale[k["unit"][m]] for k in ks for m in ("dram__bytes_read.sum", "dram__bytes_write.sum")))
+    except Exception:
+        pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -286,6 +301,8 @@ def main():
     maps = parallel.gather_maps(est_dev, rank, world)
     checksum = float(maps.sum().item()) if maps is not None else None
 
+    fit_kernel_name = ("amx::k_noddi_stage<1|2|3> (NNLS / LARS / NNLS+maps stage kernels, timed as one span)"
+                       if mid == "NODDI" else "amx::k_fit (fused per-voxel fit)")
     if rank == 0:
         m, n_maps = plan.m, plan.n_maps
         n_rot = plan.n_atoms - 1
@@ -300,7 +317,7 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": dict(workload(args.cfg, n_vox), parallelism=f"voxel shards x{world}"),
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "amx::k_fit (fused per-voxel fit)", "kernel_ms_per_launch": 1e3 * k_s,
+                         "traffic": ncu_traffic(n_vox), "kernel": fit_kernel_name, "kernel_ms_per_launch": 1e3 * k_s,
                          "bytes_per_voxel": B, "compulsory_bytes_per_voxel": B0,
                          "achieved_compulsory_GBs": B0 * n_vox / k_s / 1e9, "peak_source": peak_src},
             "fit": {"tiles": counters["tiles"], "warps_per_cta": counters["warps_per_cta"], "smem_bytes": counters["smem_bytes"],
