@@ -1,6 +1,7 @@
 // C ABI of the B200-native per-voxel fit (see include/amico_b200.h).
 #include "../../include/amico_b200.h"
 #include "amx_kernels.cuh"
+#include "amx_slow.cuh"
 
 #include <algorithm>
 #include <cstdarg>
@@ -78,7 +79,8 @@ struct amx_plan {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
-    DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask;
+    DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws;
+    int lc_cap_set = LC;
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
     int max_smem = 0, sm_count = 0;
     // last-call records
@@ -208,7 +210,7 @@ int amx_plan_destroy(amx_plan *pl)
     void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_diag0, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
-    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask};
+    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask, &pl->ovf_list, &pl->slow_ws};
     for (DevBuf *b : bufs) b->release();
     for (auto &sg : pl->stg) {
         DevBuf *sb[] = {&sg.y, &sg.dirs, &sg.est, &sg.rmse, &sg.nrmse, &sg.extra, &sg.sup, &sg.coef, &sg.lut};
@@ -505,6 +507,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.icvf = pl->d_icvf; p.kappa = pl->d_kappa; p.exvivo = pl->exvivo; p.n_wm = pl->n_wm;
     p.mouse = pl->mouse; p.n_perp = pl->n_perp; p.n_iso = pl->n_iso; p.n_rs = pl->n_rs; p.n_in = pl->n_in;
     p.Rs = pl->d_Rs; p.sandi_norms = pl->d_sandi_norms; p.d_in = pl->d_d_in; p.d_isos = pl->d_d_isos;
+    p.lut = lut;
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
     p.batched = batched ? (env_int("AMX_NODDI_SPLIT", 1) ? 2 : 1) : 0;
@@ -539,6 +542,16 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
         CK(pl->supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
         p.xiso = (double *)pl->xiso.p;
         p.supmask = (unsigned *)pl->supmask.p;
+        p.ovf_cap = 3 * n_vox;
+        CK(pl->ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
+        p.ovf_list = (int *)pl->ovf_list.p;
+    }
+    {
+        const int want = std::max(1, std::min(LC, env_int("AMX_LC_CAP", LC)));
+        if (want != pl->lc_cap_set) {
+            CK(cudaMemcpyToSymbolAsync(c_lc_cap, &want, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            pl->lc_cap_set = want;
+        }
     }
     int rc;
     switch (pl->model) {
@@ -549,6 +562,17 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     }
     if (rc) return rc;
     *launches += (p.batched == 2) ? 3 : 1;
+    if (p.batched == 2) {
+        // voxels whose active set outgrew a warp (possible with a small lambda1) are re-fitted by the scalar slow path;
+        // the launch is unconditional and returns at once when the queue is empty
+        const int cap = std::min(pl->m, pl->n) + 2;
+        const size_t wsb = slow_ws_bytes(cap, p.NA);
+        const int slow_threads = pl->sm_count * 16;
+        CK(pl->slow_ws.reserve(wsb * slow_threads));
+        k_slow_noddi<float><<<slow_threads / 32, 32, 0, st>>>(p, p.ovf_list, status, (unsigned char *)pl->slow_ws.p, wsb, cap);
+        CK(cudaGetLastError());
+        *launches += 1;
+    }
     CK(cudaEventRecord(pl->ev[2], st));
     pl->last_cnt[1] = n_tiles_bound;  // upper bound; the exact count stays on the device
     pl->last_cnt[3] = (int64_t)smem;
@@ -588,7 +612,7 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     if (a->space == AMX_SPACE_DEVICE && a->stream) st = (cudaStream_t)a->stream;
     CK(pl->status.reserve(64));
     {
-        long long init[3] = {0, (long long)1 << 62, 0};
+        long long init[4] = {0, (long long)1 << 62, 0, 0};
         CK(cudaMemcpyAsync(pl->status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
     }
     cudaStream_t end_stream = st;
@@ -663,7 +687,7 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
         end_stream = s_out;
     }
     CK(cudaEventRecord(pl->ev[4], end_stream));
-    long long h_status[3] = {0, 0, 0};
+    long long h_status[4] = {0, 0, 0, 0};
     CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, end_stream));
     CK(cudaStreamSynchronize(end_stream));
     if (end_stream != st) CK(cudaStreamSynchronize(st));
@@ -673,14 +697,15 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     if (cudaEventElapsedTime(&ms, pl->ev[3], pl->ev[4]) == cudaSuccess) pl->last_ms[2] = ms;
     pl->timing_valid = true;
     pl->last_cnt[0] = launches;
-    pl->last_cnt[2] = h_status[2];
+    pl->last_cnt[2] = h_status[3];
+    pl->last_cnt[6] = h_status[2];
     if (h_status[0]) {
         pl->last_cnt[6] = h_status[1];
         if (err_voxel) *err_voxel = h_status[1];
         return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
     }
-    if (h_status[2])
-        return fail(AMX_E_CAPACITY, "%lld voxel(s) outgrew the %d-atom active-set workspace", h_status[2], LC);
+    if (h_status[3])
+        return fail(AMX_E_CAPACITY, "%lld voxel(s) outgrew the %d-atom active-set workspace of a kernel without slow path", h_status[3], LC);
     return AMX_OK;
 }
 

@@ -30,7 +30,8 @@ __device__ __forceinline__ int dir_to_lut_idx(double *d, const int16_t *__restri
     return (int)htable[(int)r1 * 181 + (int)r2];
 }
 
-// status words: [0] error flag, [1] first offending voxel, [2] workspace-overflow voxel count
+// status words: [0] error flag, [1] first offending voxel, [2] voxels queued for the scalar slow path,
+// [3] voxels a kernel WITHOUT slow path could not finish (-> AMX_E_CAPACITY)
 __global__ void k_lut(double *dirs, long long n, const int16_t *__restrict__ htable, int ndirs, int *lut, int *hist,
                       long long *status, long long vox_offset)
 {
@@ -221,6 +222,9 @@ struct FitParams {
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
     double *xiso;        // split NODDI path: [n_vox][2] (x_iso, x_dot) by sorted position
+    const int *lut;      // LUT index per voxel (k_lut)
+    int *ovf_list;       // voxels whose active set outgrew a warp: re-fitted by the scalar slow path (amx_slow.cuh)
+    long long ovf_cap;
     unsigned *supmask;   // split NODDI path: [n_vox][NPL] stage-2 support, word s bit l <-> atom l + 32 s
 };
 
@@ -255,10 +259,12 @@ __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_
 //   FUSED : products are exact in fp64 (fp32-valued dictionary times fp32-valued signal), so fma == mul + add bit for bit;
 //   SCALED: NODDI stage 2, column-normalised DWI rows: a = fl(S * norm) first, exactly like the reference's A2.
 template <int NPL, typename TS, bool FUSED, bool SCALED>
-__device__ __noinline__ void at_y(const TS *S, int n_pad, int n, int nrows, const int *__restrict__ rows, const double *yv,
-                                  const double *__restrict__ norms, int ldn, int norms_const, double *out, int lane)
+__device__ __noinline__ double at_y(const TS *S, int n_pad, int n, int nrows, const int *__restrict__ rows, const double *yv,
+                                    const double *__restrict__ norms, int ldn, int norms_const, double *out, int lane)
 {
     double acc[NPL], nk[NPL];
+    double ysq = 0.0;  // sum_r yv[r]^2 in index order, un-fused: the ||y||^2 the LARS stopping rule starts from (rides along for free:
+                       // an independent dependency chain next to the accumulators)
 #pragma unroll
     for (int s = 0; s < NPL; ++s) {
         acc[s] = 0.0;
@@ -269,6 +275,7 @@ __device__ __noinline__ void at_y(const TS *S, int n_pad, int n, int nrows, cons
     for (int rr = 0; rr < nrows; ++rr) {
         const int r = SCALED ? rows[rr] : rr;
         const double yr = yv[rr];
+        ysq = madd(ysq, yr, yr);
         const TS *row = S + (size_t)r * n_pad + lane;
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
@@ -284,6 +291,7 @@ __device__ __noinline__ void at_y(const TS *S, int n_pad, int n, int nrows, cons
 #pragma unroll
     for (int s = 0; s < NPL; ++s) out[lane + 32 * s] = acc[s];
     __syncwarp();
+    return ysq;
 }
 
 // sum_i v[i]^2 in index order (all lanes compute the same value)
@@ -568,8 +576,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
                     ws.y2[jj] = v2 < 0.0 ? 0.0 : v2;
                 }
                 __syncwarp();
-                const double normX = seq_sumsq(ws.y2, p.dc);
-                at_y<NPL, TS, false, true>(S, n_pad, n_wm, p.dc, p.dwi_rows, ws.y2, p.norms, n_wm, p.norms_const, ws.dtr, lane);
+                const double normX = at_y<NPL, TS, false, true>(S, n_pad, n_wm, p.dc, p.dwi_rows, ws.y2, p.norms, n_wm, p.norms_const, ws.dtr, lane);
                 overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, normX,
                                            ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
                 // stage 3: debias on the support (:929-942)
@@ -587,9 +594,9 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
                                 (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
             } else if (MODEL != MODEL_NODDI) {
                 // single elastic-net fit on the full dictionary (:615, :1238, :1569)
-                const double normX = seq_sumsq(ws.y, m);
-                if (p.y_f64 || sizeof(TS) == 8) at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
-                else at_y<NPL, TS, true, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
+                const double normX = (p.y_f64 || sizeof(TS) == 8)
+                                         ? at_y<NPL, TS, false, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane)
+                                         : at_y<NPL, TS, true, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
                 overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n, m < n ? m : n, p.lambda1, ws.dtr, normX, ws.mat, ws.u,
                                            ws.gs, ws.P, ws.x, lane, nullptr);
                 for_each_positive<NPL>(ws.x, n, lane, [&](int, double) { ++support; });
@@ -674,7 +681,7 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
         }
         __syncthreads();
     }
-    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
+    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[3], (unsigned long long)n_overflow);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -777,7 +784,16 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
             __syncwarp();
         }
     }
-    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
+    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[3], (unsigned long long)n_overflow);
+}
+
+// queue a voxel for the scalar slow path (status[2] counts the entries)
+__device__ __forceinline__ void queue_slow(const FitParams &p, long long vox, int lane)
+{
+    if (lane == 0) {
+        unsigned long long idx = atomicAdd((unsigned long long *)&p.status[2], 1ull);
+        if ((long long)idx < p.ovf_cap) p.ovf_list[idx] = (int)vox;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -800,7 +816,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
     unsigned all = 0;
 #pragma unroll
     for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
-    long long n_overflow = 0;
     int *counter = p.tile_counter + (STAGE - 1);
     const int n_tiles = *p.n_tiles_ptr;
     for (;;) {
@@ -839,7 +854,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                     const unsigned w = __ballot_sync(FULL, (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n));
                     if (lane == s) p.supmask[(size_t)(tile.y + v) * NPL + s] = w;
                 }
-                if (ov) ++n_overflow;
+                if (ov) queue_slow(p, (long long)p.order[tile.y + v], lane);
                 __syncwarp();
             }
         } else {
@@ -857,7 +872,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                         p.xiso[2 * pos] = ws.x[n - 1];
                         p.xiso[2 * pos + 1] = p.exvivo ? ws.x[n - 2] : 0.0;
                     }
-                    if (ov) ++n_overflow;
+                    if (ov) queue_slow(p, (long long)p.order[pos], lane);
                 } else {  // debias on the support (:929-942), maps
                     const long long vox = (long long)p.order[pos];
                     unsigned allowed = 0;
@@ -888,13 +903,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                         fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
                                             p.nrmse ? p.nrmse + vox : nullptr, lane);
                     }
-                    if (ov) ++n_overflow;
+                    if (ov) queue_slow(p, vox, lane);
                 }
                 __syncwarp();
             }
         }
     }
-    if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[2], (unsigned long long)n_overflow);
 }
 
 }  // namespace amx

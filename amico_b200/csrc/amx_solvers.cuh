@@ -61,7 +61,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
     __syncwarp();
     for (;;) {
         if (np >= mcap) break;
-        if (np >= LC) { overflow = 1; break; }
+        if (np >= c_lc_cap) { overflow = 1; break; }
         // dual w = c - T[:,P] x_P on the zero set
         double wl[NPL];
         unsigned valid = 0;
@@ -291,7 +291,7 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
         if (i < 0) break;  // the CPU path would read ind[-1] here; cannot happen with pos=true
         ++iter;
         if (newAtom) {
-            if (i >= LC) { overflow = 1; na = i; break; }
+            if (i >= c_lc_cap) { overflow = 1; na = i; break; }
             if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
             if ((cur & 31) == lane) act |= 1u << (cur >> 5);
             __syncwarp();
@@ -506,7 +506,7 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         if (i < 0) break;
         ++iter;
         if (newAtom) {
-            if (i >= LC) { overflow = 1; na = i; break; }
+            if (i >= c_lc_cap) { overflow = 1; na = i; break; }
             if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
             if ((cur & 31) == lane) act |= 1u << (cur >> 5);
             __syncwarp();

@@ -8,6 +8,9 @@ namespace amx {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int LC = 32;                    // active-set capacity of the warp solvers (one lane per active atom)
 constexpr int TRI = LC * (LC + 1) / 2;    // packed triangular storage
+// Active sets that would outgrow the warp solvers are finished by the scalar slow path (k_slow_*).  The limit is a
+// constant-bank word so that tests can lower it and exercise that path (AMX_LC_CAP).
+__constant__ int c_lc_cap = LC;
 
 __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }  // r >= c
 

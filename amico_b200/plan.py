@@ -215,4 +215,4 @@ class Plan:
         out = (C.c_int64 * 8)()
         L.check(L.load().amx_plan_last_counters(self._h, out, 8))
         return {"launches": out[0], "tiles": out[1], "overflow_voxels": out[2], "smem_bytes": out[3], "warps_per_cta": out[4],
-                "tma_staged": bool(out[5]), "grid": out[7]}
+                "tma_staged": bool(out[5]), "slow_path_voxels": out[6], "grid": out[7]}

@@ -138,9 +138,11 @@ int amx_lut_indices(amx_plan *plan, int space, double *dirs, int64_t n, int32_t 
  * out[2] = whole enqueue-to-done span including any staging copies.  n <= 8 values are written. */
 int amx_plan_last_timing(amx_plan *plan, double *out_ms, int n);
 
-/* Counters of the last amx_fit: out[0] = kernels launched, out[1] = voxel tiles, out[2] = voxels
- * whose active set hit the workspace cap (0 in a healthy run), out[3] = bytes of dynamic shared
- * memory per CTA, out[4] = warps per CTA, out[5] = 1 if the slab was staged through TMA. */
+/* Counters of the last amx_fit: out[0] = kernels launched, out[1] = voxel tiles (upper bound),
+ * out[2] = voxels a kernel without slow path could not finish (-> AMX_E_CAPACITY; 0 in a healthy
+ * run), out[3] = bytes of dynamic shared memory per CTA, out[4] = warps per CTA, out[5] = 1 if the
+ * slab was staged through TMA, out[6] = voxel fits redone by the scalar slow path (active sets
+ * larger than a warp), out[7] = grid size. */
 int amx_plan_last_counters(amx_plan *plan, int64_t *out, int n);
 
 #ifdef __cplusplus

@@ -328,3 +328,20 @@ def test_noddi_whole_brain_protocol_m288():
     assert got["_counters"]["overflow_voxels"] == 0
     assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
     assert float((got["support"] == ref["support"]).mean()) >= 0.998
+
+
+def test_large_active_sets_take_the_slow_path(monkeypatch):
+    """Supports larger than a warp (small lambda1) are finished by the scalar slow path, not truncated or refused."""
+    P = synth.make_problem(2, n_vox=3000, seed=12)
+    ref = orc().fit_problem(P, lambda1=0.05, return_debug=True, nthreads=os.cpu_count())
+    assert (ref["support"] > 34).mean() > 0.05           # the case is real: many supports exceed 32 atoms
+    got = gpu_fit(P, lambda1=0.05, debug=True, rmse=True)
+    assert got["_counters"]["slow_path_voxels"] > 0 and got["_counters"]["overflow_voxels"] == 0
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.995
+    # and with an artificially tiny warp capacity every stage of nearly every voxel goes through it
+    monkeypatch.setenv("AMX_LC_CAP", "5")
+    ref = orc().fit_problem(P, rmse=True, return_debug=True, nthreads=os.cpu_count())
+    got = gpu_fit(P, debug=True, rmse=True)
+    assert got["_counters"]["slow_path_voxels"] > 2000
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
+    assert float((got["support"] == ref["support"]).mean()) >= 0.998

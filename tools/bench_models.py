@@ -13,8 +13,11 @@ from amico_b200 import models as amx_models, synth  # noqa: E402
 from amico_b200.plan import Plan  # noqa: E402
 
 n_vox = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
+only = sys.argv[2].split(",") if len(sys.argv) > 2 else None
 out = {}
 for cfg, model in ((1, "FreeWater"), (4, "SANDI"), (5, "CylinderZeppelinBall"), (3, "NODDI"), (2, "NODDI")):
+    if only and f"{model}{cfg}" not in only:
+        continue
     t0 = time.time()
     P = synth.make_problem(cfg, n_vox=n_vox, model=model)
     mdl = getattr(amx_models, model)()
