@@ -79,8 +79,10 @@ struct amx_plan {
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
-    DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws;
-    int lc_cap_set = LC;
+    // per-launch workspace; two sets so that consecutive voxel chunks can be in flight on two compute streams
+    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws; } work[2];
+    cudaStream_t cs[2] = {nullptr, nullptr};          // [0] == stream
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
     int max_smem = 0, sm_count = 0;
     // last-call records
@@ -110,6 +112,10 @@ int plan_common_init(amx_plan *pl, int device)
     CK(cudaDeviceGetAttribute(&pl->max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     CK(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&pl->stream, cudaStreamNonBlocking));
+    pl->cs[0] = pl->stream;
+    CK(cudaStreamCreateWithFlags(&pl->cs[1], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&pl->ev_fork, cudaEventDisableTiming));
+    for (auto &e : pl->ev_join) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     CK(cudaStreamCreateWithFlags(&pl->s_in, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&pl->s_out, cudaStreamNonBlocking));
     for (auto &ev : pl->ev) CK(cudaEventCreate(&ev));
@@ -210,8 +216,13 @@ int amx_plan_destroy(amx_plan *pl)
     void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_diag0, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
-    DevBuf *bufs[] = {&pl->lut, &pl->order, &pl->bins, &pl->tiles, &pl->status, &pl->scratch, &pl->xiso, &pl->supmask, &pl->ovf_list, &pl->slow_ws};
-    for (DevBuf *b : bufs) b->release();
+    for (auto &wk : pl->work) {
+        DevBuf *bufs[] = {&wk.lut, &wk.order, &wk.bins, &wk.tiles, &wk.status, &wk.scratch, &wk.xiso, &wk.supmask, &wk.ovf_list, &wk.slow_ws};
+        for (DevBuf *b : bufs) b->release();
+    }
+    if (pl->cs[1]) cudaStreamDestroy(pl->cs[1]);
+    if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
+    for (auto &e : pl->ev_join) if (e) cudaEventDestroy(e);
     for (auto &sg : pl->stg) {
         DevBuf *sb[] = {&sg.y, &sg.dirs, &sg.est, &sg.rmse, &sg.nrmse, &sg.extra, &sg.sup, &sg.coef, &sg.lut};
         for (DevBuf *b : sb) b->release();
@@ -437,22 +448,10 @@ int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, 
     return fail(AMX_E_INVALID, "unsupported atom count (npl=%d)", npl);
 }
 
-// Enqueue LUT index + binning + fit kernels for device-resident voxels; fully asynchronous (the tile count stays on the
-// device, the error / overflow words are read by the caller at the end).  All pointers are device pointers.
-int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launches, long long vox_offset)
+// Per-call table state that every chunk shares: ridge baked into the LARS Gram diagonal, active-set cap constant.
+// Runs on the caller's stream BEFORE the chunk streams fork.
+int prepare_tables(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launches)
 {
-    const long long n_vox = a->n_vox;
-    const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
-    const int tile_v = batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
-    const bool rotated = pl->model != AMX_MODEL_SANDI;
-    const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
-    CK(pl->tiles.reserve((size_t)max_tiles * sizeof(int4)));
-    CK(pl->bins.reserve(((size_t)4 * pl->ndirs + 8) * sizeof(int)));
-    int *bins = (int *)pl->bins.p;
-    int *hist = bins, *offs = bins + pl->ndirs, *cursor = bins + 2 * pl->ndirs, *tile_offs = bins + 3 * pl->ndirs,
-        *totals = bins + 4 * pl->ndirs;  // totals[0]=n_tiles, [1]=n binned, [2..4]=tile counters
-    long long *status = (long long *)pl->status.p;
-    CK(cudaMemsetAsync(pl->bins.p, 0, ((size_t)4 * pl->ndirs + 8) * sizeof(int), st));
     {
         const double ridge = a->lambda2 > 1e-10 ? a->lambda2 : 1e-10;
         if (ridge != pl->ridge_baked) {
@@ -466,31 +465,60 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
             *launches += 1;
         }
     }
-    CK(cudaEventRecord(pl->ev[0], st));
+    {
+        const int want = std::max(1, std::min(LC, env_int("AMX_LC_CAP", LC)));
+        static int cap_on_device[64];  // value of the constant on each device (0 = the compiled default LC)
+        int &cur = cap_on_device[pl->device & 63];
+        if (want != (cur ? cur : LC)) {
+            CK(cudaMemcpyToSymbolAsync(c_lc_cap, &want, sizeof(int), 0, cudaMemcpyHostToDevice, st));
+            cur = want;
+        }
+    }
+    return AMX_OK;
+}
+
+// Enqueue LUT index + binning + fit kernels for device-resident voxels; fully asynchronous (the tile count stays on the
+// device, the error / overflow words are read by the caller at the end).  All pointers are device pointers.
+int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStream_t st, int *launches, long long vox_offset,
+               bool record_events)
+{
+    const long long n_vox = a->n_vox;
+    const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
+    const int tile_v = batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
+    const bool rotated = pl->model != AMX_MODEL_SANDI;
+    const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
+    CK(wk.tiles.reserve((size_t)max_tiles * sizeof(int4)));
+    CK(wk.bins.reserve(((size_t)4 * pl->ndirs + 8) * sizeof(int)));
+    int *bins = (int *)wk.bins.p;
+    int *hist = bins, *offs = bins + pl->ndirs, *cursor = bins + 2 * pl->ndirs, *tile_offs = bins + 3 * pl->ndirs,
+        *totals = bins + 4 * pl->ndirs;  // totals[0]=n_tiles, [1]=n binned, [2..4]=tile counters
+    long long *status = (long long *)wk.status.p;
+    CK(cudaMemsetAsync(wk.bins.p, 0, ((size_t)4 * pl->ndirs + 8) * sizeof(int), st));
+    if (record_events) CK(cudaEventRecord(pl->ev[0], st));
     long long n_tiles_bound = max_tiles;
     int *lut = nullptr;
     if (rotated) {
         if (!a->dirs) return fail(AMX_E_INVALID, "dirs is NULL");
         if (a->lut_out) lut = a->lut_out;
-        else { CK(pl->lut.reserve((size_t)n_vox * sizeof(int))); lut = (int *)pl->lut.p; }
-        CK(pl->order.reserve((size_t)n_vox * sizeof(int)));
+        else { CK(wk.lut.reserve((size_t)n_vox * sizeof(int))); lut = (int *)wk.lut.p; }
+        CK(wk.order.reserve((size_t)n_vox * sizeof(int)));
         const int B = 256;
         const unsigned G = (unsigned)((n_vox + B - 1) / B);
         k_lut<<<G, B, 0, st>>>(a->dirs, n_vox, pl->d_htable, pl->ndirs, lut, hist, status, vox_offset);
         k_scan_bins<<<1, 1024, 0, st>>>(hist, pl->ndirs, tile_v, offs, cursor, tile_offs, totals);
-        k_scatter<<<G, B, 0, st>>>(lut, n_vox, cursor, (int *)pl->order.p);
-        k_tiles<<<(pl->ndirs + 127) / 128, 128, 0, st>>>(hist, offs, tile_offs, pl->ndirs, tile_v, (int4 *)pl->tiles.p);
+        k_scatter<<<G, B, 0, st>>>(lut, n_vox, cursor, (int *)wk.order.p);
+        k_tiles<<<(pl->ndirs + 127) / 128, 128, 0, st>>>(hist, offs, tile_offs, pl->ndirs, tile_v, (int4 *)wk.tiles.p);
         CK(cudaGetLastError());
         *launches += 4;
     } else {
         const int n_tiles = (int)((n_vox + tile_v - 1) / tile_v);
         n_tiles_bound = n_tiles;
-        k_tiles_linear<<<(n_tiles + 127) / 128, 128, 0, st>>>(n_vox, tile_v, (int4 *)pl->tiles.p, n_tiles, totals);
+        k_tiles_linear<<<(n_tiles + 127) / 128, 128, 0, st>>>(n_vox, tile_v, (int4 *)wk.tiles.p, n_tiles, totals);
         CK(cudaGetLastError());
         *launches += 1;
         if (a->lut_out) CK(cudaMemsetAsync(a->lut_out, 0, (size_t)n_vox * sizeof(int), st));
     }
-    CK(cudaEventRecord(pl->ev[1], st));
+    if (record_events) CK(cudaEventRecord(pl->ev[1], st));
 
     FitParams p;
     memset(&p, 0, sizeof p);
@@ -500,7 +528,7 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     p.T1 = pl->d_T1; p.ldT1 = pl->ldT1; p.T1_stride = pl->T1_stride;
     p.T2 = pl->d_T2; p.ldT2 = pl->ldT2; p.T2_stride = pl->T2_stride; p.K2 = pl->K2;
     p.y = a->y; p.y_f64 = a->y_dtype == AMX_F64; p.n_vox = n_vox;
-    p.order = rotated ? (const int *)pl->order.p : nullptr; p.tiles = (const int4 *)pl->tiles.p; p.n_tiles_ptr = totals;
+    p.order = rotated ? (const int *)wk.order.p : nullptr; p.tiles = (const int4 *)wk.tiles.p; p.n_tiles_ptr = totals;
     p.tile_counter = totals + 2;
     p.lambda1 = a->lambda1; p.lambda2 = a->lambda2; p.flags = a->flags;
     p.dwi_rows = pl->d_dwi_rows; p.dc = pl->dc; p.norms = pl->d_norms; p.norms_const = pl->norms_const;
@@ -536,22 +564,15 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
     int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count * ctas_per_sm));
 
     if (p.batched) {
-        CK(pl->scratch.reserve((size_t)grid * nwarps * 2 * BV * p.NA * sizeof(double)));
-        p.scratch = (double *)pl->scratch.p;
-        CK(pl->xiso.reserve((size_t)n_vox * 2 * sizeof(double)));
-        CK(pl->supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
-        p.xiso = (double *)pl->xiso.p;
-        p.supmask = (unsigned *)pl->supmask.p;
+        CK(wk.scratch.reserve((size_t)grid * nwarps * 2 * BV * p.NA * sizeof(double)));
+        p.scratch = (double *)wk.scratch.p;
+        CK(wk.xiso.reserve((size_t)n_vox * 2 * sizeof(double)));
+        CK(wk.supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
+        p.xiso = (double *)wk.xiso.p;
+        p.supmask = (unsigned *)wk.supmask.p;
         p.ovf_cap = 3 * n_vox;
-        CK(pl->ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
-        p.ovf_list = (int *)pl->ovf_list.p;
-    }
-    {
-        const int want = std::max(1, std::min(LC, env_int("AMX_LC_CAP", LC)));
-        if (want != pl->lc_cap_set) {
-            CK(cudaMemcpyToSymbolAsync(c_lc_cap, &want, sizeof(int), 0, cudaMemcpyHostToDevice, st));
-            pl->lc_cap_set = want;
-        }
+        CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
+        p.ovf_list = (int *)wk.ovf_list.p;
     }
     int rc;
     switch (pl->model) {
@@ -568,12 +589,12 @@ int fit_device(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *launch
         const int cap = std::min(pl->m, pl->n) + 2;
         const size_t wsb = slow_ws_bytes(cap, p.NA);
         const int slow_threads = pl->sm_count * 16;
-        CK(pl->slow_ws.reserve(wsb * slow_threads));
-        k_slow_noddi<float><<<slow_threads / 32, 32, 0, st>>>(p, p.ovf_list, status, (unsigned char *)pl->slow_ws.p, wsb, cap);
+        CK(wk.slow_ws.reserve(wsb * slow_threads));
+        k_slow_noddi<float><<<slow_threads / 32, 32, 0, st>>>(p, p.ovf_list, status, (unsigned char *)wk.slow_ws.p, wsb, cap);
         CK(cudaGetLastError());
         *launches += 1;
     }
-    CK(cudaEventRecord(pl->ev[2], st));
+    if (record_events) CK(cudaEventRecord(pl->ev[2], st));
     pl->last_cnt[1] = n_tiles_bound;  // upper bound; the exact count stays on the device
     pl->last_cnt[3] = (int64_t)smem;
     pl->last_cnt[4] = nwarps;
@@ -605,28 +626,26 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     int launches = 0;
     amx_fit_args d = *a;
     if (!has_extra) d.flags &= ~AMX_FLAG_EXTRA;
+    const bool host = a->space == AMX_SPACE_HOST;
     const size_t n = (size_t)a->n_vox, m = (size_t)pl->m, nm = (size_t)pl->n_maps;
     const size_t ysz = a->y_dtype == AMX_F64 ? 8 : 4;
     const size_t extra_w = has_extra ? (pl->model == AMX_MODEL_NODDI ? 2 : m) : 0;
-    cudaStream_t st = pl->stream;
-    if (a->space == AMX_SPACE_DEVICE && a->stream) st = (cudaStream_t)a->stream;
-    CK(pl->status.reserve(64));
-    {
-        long long init[4] = {0, (long long)1 << 62, 0, 0};
-        CK(cudaMemcpyAsync(pl->status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
-    }
-    cudaStream_t end_stream = st;
-    if (a->space == AMX_SPACE_DEVICE) {
-        CK(cudaEventRecord(pl->ev[3], st));
-        int rc = fit_device(pl, &d, st, &launches, 0);
-        if (rc) { cudaStreamSynchronize(st); return rc; }
-    } else {
-        // Host buffers: voxel chunks flow through a 3-stream pipeline (H2D | LUT+binning+fit | D2H) over two staging sets,
-        // so the copies of neighbouring chunks hide behind the fit.  Pinned host memory makes the copies truly async.
-        long long chunk = std::max(8192, env_int("AMX_HOST_CHUNK", 262144));
-        if ((long long)n <= chunk + chunk / 2) chunk = (long long)n;
-        const long long n_chunks = ((long long)n + chunk - 1) / chunk;
-        const int nset = n_chunks > 1 ? 2 : 1;
+    cudaStream_t st = pl->stream;  // the caller's stream: everything is ordered after / joined back into it
+    if (!host && a->stream) st = (cudaStream_t)a->stream;
+
+    // The volume is cut into voxel chunks that alternate between two compute streams (each with its own workspace):
+    // the ragged end of one chunk's stage kernels is filled by the next chunk's kernels, and for host buffers the
+    // H2D / D2H copies of neighbouring chunks hide behind the fit (3-stream pipeline over two staging sets).
+    // (measured: for device-resident data one chunk on one stream is fastest -- per-chunk binning and smaller direction
+    //  bins cost more than the ragged kernel ends -- so chunking defaults on for host buffers only, and the second
+    //  compute stream stays an option, AMX_COMPUTE_STREAMS=2)
+    long long chunk = std::max(8192, env_int(host ? "AMX_HOST_CHUNK" : "AMX_DEVICE_CHUNK", host ? 262144 : 0x7fffffff));
+    if ((long long)n <= chunk + chunk / 2) chunk = (long long)n;
+    const long long n_chunks = ((long long)n + chunk - 1) / chunk;
+    const int nset = n_chunks > 1 ? 2 : 1;
+    const int ncs = (nset > 1 && env_int("AMX_COMPUTE_STREAMS", 1) > 1) ? 2 : 1;
+    for (int b = 0; b < ncs; ++b) CK(pl->work[b].status.reserve(64));
+    if (host) {
         for (int b = 0; b < nset; ++b) {
             amx_plan::Stage &sg = pl->stg[b];
             CK(sg.y.reserve((size_t)chunk * m * ysz));
@@ -639,21 +658,33 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             if (a->coeff_out) CK(sg.coef.reserve((size_t)chunk * pl->n * sizeof(double)));
             if (a->lut_out) CK(sg.lut.reserve((size_t)chunk * sizeof(int)));
         }
-        cudaStream_t s_in = n_chunks > 1 ? pl->s_in : st, s_out = n_chunks > 1 ? pl->s_out : st;
-        if (n_chunks > 1) {  // order the side streams after the status reset on the compute stream
-            CK(cudaEventRecord(pl->ev_comp[0], st));
-            CK(cudaStreamWaitEvent(s_in, pl->ev_comp[0], 0));
-        }
-        CK(cudaEventRecord(pl->ev[3], s_in));
-        for (long long i = 0; i < n_chunks; ++i) {
-            const int b = (int)(i & 1) % nset;
+    }
+    cudaStream_t cs[2] = {st, ncs > 1 ? pl->cs[1] : st};
+    cudaStream_t s_in = (host && nset > 1) ? pl->s_in : st, s_out = (host && nset > 1) ? pl->s_out : st;
+    CK(cudaEventRecord(pl->ev[3], st));
+    {
+        long long init[4] = {0, (long long)1 << 62, 0, 0};
+        for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(pl->work[b].status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    }
+    {
+        int rc = prepare_tables(pl, &d, st, &launches);
+        if (rc) return rc;
+    }
+    if (nset > 1) {  // fork
+        CK(cudaEventRecord(pl->ev_fork, st));
+        if (ncs > 1) CK(cudaStreamWaitEvent(cs[1], pl->ev_fork, 0));
+        if (host) { CK(cudaStreamWaitEvent(s_in, pl->ev_fork, 0)); CK(cudaStreamWaitEvent(s_out, pl->ev_fork, 0)); }
+    }
+    for (long long i = 0; i < n_chunks; ++i) {
+        const int b = (int)(i % nset), wb = (int)(i % ncs);
+        const size_t off = (size_t)(i * chunk), cnt = (size_t)std::min<long long>(chunk, (long long)n - i * chunk);
+        amx_fit_args c = d;
+        c.n_vox = (int64_t)cnt;
+        if (host) {
             amx_plan::Stage &sg = pl->stg[b];
-            const size_t off = (size_t)(i * chunk), cnt = (size_t)std::min<long long>(chunk, (long long)n - i * chunk);
             if (i >= 2) CK(cudaStreamWaitEvent(s_in, pl->ev_comp[b], 0));  // inputs of this set consumed by chunk i-2
             CK(cudaMemcpyAsync(sg.y.p, (const char *)a->y + off * m * ysz, cnt * m * ysz, cudaMemcpyHostToDevice, s_in));
             if (a->dirs) CK(cudaMemcpyAsync(sg.dirs.p, a->dirs + off * 3, cnt * 3 * sizeof(double), cudaMemcpyHostToDevice, s_in));
-            amx_fit_args c = d;
-            c.n_vox = (int64_t)cnt;
             c.y = sg.y.p; c.estimates = (double *)sg.est.p;
             c.dirs = a->dirs ? (double *)sg.dirs.p : nullptr;
             c.rmse = (d.flags & AMX_FLAG_RMSE) ? (double *)sg.rmse.p : nullptr;
@@ -662,15 +693,27 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             c.support_out = a->support_out ? (int *)sg.sup.p : nullptr;
             c.coeff_out = a->coeff_out ? (double *)sg.coef.p : nullptr;
             c.lut_out = a->lut_out ? (int *)sg.lut.p : nullptr;
-            if (n_chunks > 1) {
+            if (nset > 1) {
                 CK(cudaEventRecord(pl->ev_in[b], s_in));
-                CK(cudaStreamWaitEvent(st, pl->ev_in[b], 0));
-                if (i >= 2) CK(cudaStreamWaitEvent(st, pl->ev_out[b], 0));  // outputs of this set drained by chunk i-2
+                CK(cudaStreamWaitEvent(cs[wb], pl->ev_in[b], 0));
+                if (i >= 2) CK(cudaStreamWaitEvent(cs[wb], pl->ev_out[b], 0));  // outputs of this set drained by chunk i-2
             }
-            int rc = fit_device(pl, &c, st, &launches, (long long)off);
-            if (rc) { cudaDeviceSynchronize(); return rc; }
-            if (n_chunks > 1) {
-                CK(cudaEventRecord(pl->ev_comp[b], st));
+        } else {
+            c.y = (const char *)a->y + off * m * ysz;
+            c.estimates = a->estimates + off * nm;
+            c.dirs = a->dirs ? a->dirs + off * 3 : nullptr;
+            c.rmse = a->rmse ? a->rmse + off : nullptr;
+            c.nrmse = a->nrmse ? a->nrmse + off : nullptr;
+            c.extra = (has_extra && a->extra) ? a->extra + off * extra_w : nullptr;
+            c.support_out = a->support_out ? a->support_out + off : nullptr;
+            c.coeff_out = a->coeff_out ? a->coeff_out + off * pl->n : nullptr;
+            c.lut_out = a->lut_out ? a->lut_out + off : nullptr;
+        }
+        int rc = fit_device(pl, pl->work[wb], &c, cs[wb], &launches, (long long)off, i == 0);
+        if (rc) { cudaDeviceSynchronize(); return rc; }
+        if (host) {
+            if (nset > 1) {
+                CK(cudaEventRecord(pl->ev_comp[b], cs[wb]));
                 CK(cudaStreamWaitEvent(s_out, pl->ev_comp[b], 0));
             }
             // the reference flips DIRs in place (amico/lut.pyx:335-338): hand the flipped directions back
@@ -682,30 +725,42 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             if (c.support_out) CK(cudaMemcpyAsync(a->support_out + off, c.support_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s_out));
             if (c.coeff_out) CK(cudaMemcpyAsync(a->coeff_out + off * pl->n, c.coeff_out, cnt * pl->n * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             if (c.lut_out) CK(cudaMemcpyAsync(a->lut_out + off, c.lut_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s_out));
-            if (n_chunks > 1) CK(cudaEventRecord(pl->ev_out[b], s_out));
+            if (nset > 1) CK(cudaEventRecord(pl->ev_out[b], s_out));
         }
-        end_stream = s_out;
     }
-    CK(cudaEventRecord(pl->ev[4], end_stream));
-    long long h_status[4] = {0, 0, 0, 0};
-    CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, end_stream));
-    CK(cudaStreamSynchronize(end_stream));
-    if (end_stream != st) CK(cudaStreamSynchronize(st));
+    if (nset > 1) {  // join everything back into the caller's stream
+        if (ncs > 1) {
+            CK(cudaEventRecord(pl->ev_join[1], cs[1]));
+            CK(cudaStreamWaitEvent(st, pl->ev_join[1], 0));
+        }
+        if (host) {
+            CK(cudaEventRecord(pl->ev_join[0], s_out));
+            CK(cudaStreamWaitEvent(st, pl->ev_join[0], 0));
+        }
+    }
+    CK(cudaEventRecord(pl->ev[4], st));
+    long long h_status[2][4] = {{0, (long long)1 << 62, 0, 0}, {0, (long long)1 << 62, 0, 0}};
+    for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(h_status[b], pl->work[b].status.p, sizeof h_status[b], cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->last_ms[0] = ms;
-    if (cudaEventElapsedTime(&ms, pl->ev[1], pl->ev[2]) == cudaSuccess) pl->last_ms[1] = ms;
     if (cudaEventElapsedTime(&ms, pl->ev[3], pl->ev[4]) == cudaSuccess) pl->last_ms[2] = ms;
+    // chunks overlap on two streams, so the fit kernels are timed as one span: whole call minus the first chunk's binning
+    // (single chunk: exactly the event pair around the fit kernels)
+    if (nset == 1) { if (cudaEventElapsedTime(&ms, pl->ev[1], pl->ev[2]) == cudaSuccess) pl->last_ms[1] = ms; }
+    else pl->last_ms[1] = pl->last_ms[2] - pl->last_ms[0];
     pl->timing_valid = true;
     pl->last_cnt[0] = launches;
-    pl->last_cnt[2] = h_status[3];
-    pl->last_cnt[6] = h_status[2];
-    if (h_status[0]) {
-        pl->last_cnt[6] = h_status[1];
-        if (err_voxel) *err_voxel = h_status[1];
-        return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
+    const long long bad = h_status[0][0] | h_status[1][0], bad_vox = std::min(h_status[0][1], h_status[1][1]);
+    pl->last_cnt[2] = h_status[0][3] + h_status[1][3];
+    pl->last_cnt[6] = h_status[0][2] + h_status[1][2];
+    if (bad) {
+        if (err_voxel) *err_voxel = bad_vox;
+        return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", bad_vox);
     }
-    if (h_status[3])
-        return fail(AMX_E_CAPACITY, "%lld voxel(s) outgrew the %d-atom active-set workspace of a kernel without slow path", h_status[3], LC);
+    if (pl->last_cnt[2])
+        return fail(AMX_E_CAPACITY, "%lld voxel(s) outgrew the %d-atom active-set workspace of a kernel without slow path",
+                    (long long)pl->last_cnt[2], LC);
     return AMX_OK;
 }
 
@@ -720,21 +775,21 @@ int amx_lut_indices(amx_plan *pl, int space, double *dirs, int64_t n, int32_t *i
     int *d_idx = idx;
     if (space == AMX_SPACE_HOST) {
         CK(pl->stg[0].dirs.reserve((size_t)n * 3 * sizeof(double)));
-        CK(pl->lut.reserve((size_t)n * sizeof(int)));
-        d_dirs = (double *)pl->stg[0].dirs.p; d_idx = (int *)pl->lut.p;
+        CK(pl->work[0].lut.reserve((size_t)n * sizeof(int)));
+        d_dirs = (double *)pl->stg[0].dirs.p; d_idx = (int *)pl->work[0].lut.p;
         CK(cudaMemcpyAsync(d_dirs, dirs, (size_t)n * 3 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
-    CK(pl->status.reserve(64));
+    CK(pl->work[0].status.reserve(64));
     long long init[3] = {0, (long long)1 << 62, 0};
-    CK(cudaMemcpyAsync(pl->status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
-    k_lut<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_dirs, n, pl->d_htable, pl->ndirs, d_idx, nullptr, (long long *)pl->status.p, 0);
+    CK(cudaMemcpyAsync(pl->work[0].status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
+    k_lut<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_dirs, n, pl->d_htable, pl->ndirs, d_idx, nullptr, (long long *)pl->work[0].status.p, 0);
     CK(cudaGetLastError());
     if (space == AMX_SPACE_HOST) {
         CK(cudaMemcpyAsync(dirs, d_dirs, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(idx, d_idx, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, st));
     }
     long long h_status[2];
-    CK(cudaMemcpyAsync(h_status, pl->status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_status, pl->work[0].status.p, sizeof h_status, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     if (h_status[0]) return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", h_status[1]);
     return AMX_OK;
