@@ -392,12 +392,18 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     auto k1 = k_noddi_stage<1, NPL, float, MAXT>;
     auto k2 = k_noddi_stage<2, NPL, float, MAXT>;
     auto k3 = k_noddi_stage<3, NPL, float, MAXT>;
-    CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k1<<<grid, block, smem, st>>>(p);
-    k2<<<grid, block, smem, st>>>(p);
-    k3<<<grid, block, smem, st>>>(p);
+    const size_t fixed = p.ws_smem_off;
+    const size_t s1 = fixed + (size_t)p.ws_doubles_stage[0] * 8 * p.nwarps, s2 = fixed + (size_t)p.ws_doubles_stage[1] * 8 * p.nwarps,
+                 s3 = fixed + (size_t)p.ws_doubles_stage[2] * 8 * p.nwarps;
+    (void)smem;
+    CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1));
+    CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2));
+    CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
+    // carve-out hint: what is not shared memory is L1 (Gram rows)
+    CK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1 * 100 + 233471) / 233472 + 1)));
+    k1<<<grid, block, s1, st>>>(p);
+    k2<<<grid, block, s2, st>>>(p);
+    k3<<<grid, block, s3, st>>>(p);
     CK(cudaGetLastError());
     return AMX_OK;
 }
@@ -545,6 +551,13 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);
 
     // shared-memory budget: [header 128][slab (optional)][nwarps x workspace]
+    if (p.batched == 2) {
+        // stage 1 (NNLS on the full dictionary) never holds more than ~8 passive atoms on NODDI dictionaries (rank ~11):
+        // a 16-atom workspace leaves ~85 KB more L1 for its Gram rows; rarer larger sets go to the slow path
+        p.cap_stage[0] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE1", 16)));
+        p.cap_stage[1] = p.cap_stage[2] = LC;
+        for (int k = 0; k < 3; ++k) p.ws_doubles_stage[k] = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, 1, p.cap_stage[k]);
+    }
     const size_t ws_bytes = (size_t)p.ws_doubles * sizeof(double);
     const size_t budget = (size_t)pl->max_smem;
     const int max_warps = (batched && env_int("AMX_NODDI_SPLIT", 1)) ? 24 : 16;

@@ -217,6 +217,7 @@ struct FitParams {
     double *est, *rmse, *nrmse, *extra, *coeff_out; int *support_out; long long *status;
     // launch geometry
     int nwarps; unsigned ws_doubles; unsigned slab_smem_off, ws_smem_off;
+    int cap_stage[3]; unsigned ws_doubles_stage[3];  // stage kernels: per-stage active-set capacity and workspace size
     int m_pad, dc_pad;
     int fast_lars;    // NODDI stage 2: throughput-oriented LARS (same path, fused arithmetic)
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
@@ -235,19 +236,24 @@ struct WarpWS {
 
 constexpr int BV = 8;  // voxels per DMMA micro-batch (the M of m8n8k4)
 // alias: the stage kernels never need c1 and dtr at the same time -> one array
-__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad, int alias = 0) { return (alias ? 2u : 3u) * NA + TRI + 3 * LC + LC / 2 + 3 * BV + m_pad + dc_pad; }
+// cap: active-set capacity the workspace is laid out for (<= LC); the stage kernels size it per stage -- NODDI stage 1 never
+// holds more than ~8 passive atoms -- because every KB of shared memory given back is L1 for the Gram rows
+__host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad, int alias = 0, int cap = LC)
+{
+    return (alias ? 2u : 3u) * NA + (unsigned)(cap * (cap + 1) / 2) + 3u * cap + (unsigned)((cap + 1) / 2) + 3 * BV + m_pad + dc_pad;
+}
 
-__device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad, int alias = 0)
+__device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad, int alias = 0, int cap = LC)
 {
     WarpWS w;
     w.c1 = base; base += NA;
     w.dtr = alias ? w.c1 : base; base += alias ? 0 : NA;
     w.x = base; base += NA;
-    w.mat = base; base += TRI;
-    w.rd = base; base += LC;
-    w.u = base; base += LC;
-    w.gs = base; base += LC;
-    w.P = (int *)base; base += LC / 2;
+    w.mat = base; base += cap * (cap + 1) / 2;
+    w.rd = base; base += cap;
+    w.u = base; base += cap;
+    w.gs = base; base += cap;
+    w.P = (int *)base; base += (cap + 1) / 2;
     w.bx = base; base += 3 * BV;  // per-batch x_iso, x_dot, ||y2||^2
     w.y = base; base += m_pad;
     w.y2 = base;
@@ -349,10 +355,10 @@ __device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *
             const int r = r0 + kk;
             const bool rv = r < m;
             double a = 0.0;
-            if (rv && vvalid) a = y_f64 ? yd[r] : (double)yf[r];
+            if (rv && vvalid) a = y_f64 ? ld_stream(yd + r) : (double)ld_stream(yf + r);
             const TS *row = S + (size_t)(rv ? r : m - 1) * n_pad + g + 8 * t0;
 #pragma unroll
-            for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
+            for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)ld_stream(row + 8 * t));
         }
         double *o = out + (size_t)g * NA + 2 * kk + 8 * t0;
         if (vvalid) {
@@ -387,7 +393,7 @@ __device__ __noinline__ void gemm_c2(const TS *S, int n_pad, int n, int n_wm, in
             const TS *row = S + (size_t)r * n_pad;
             double a = 0.0;
             if (jv && vvalid) {
-                a = (y_f64 ? yd[r] : (double)yf[r]) - xiso * (double)row[n - 1];
+                a = (y_f64 ? ld_stream(yd + r) : (double)ld_stream(yf + r)) - xiso * (double)row[n - 1];
                 if (exvivo) a = a - xdot * 1.0;
                 a = a < 0.0 ? 0.0 : a;
             }
@@ -395,13 +401,13 @@ __device__ __noinline__ void gemm_c2(const TS *S, int n_pad, int n, int n_wm, in
             row += g + 8 * t0;
             if (NC) {
 #pragma unroll
-                for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)row[8 * t]);
+                for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)ld_stream(row + 8 * t));
             } else {
                 const double *nr = norms + (size_t)(jv ? jj : dc - 1) * ldn + g + 8 * t0;
 #pragma unroll
                 for (int t = 0; t < TP; ++t) {
                     const double sc = (g + 8 * (t0 + t) < n_wm) ? nr[8 * t] : 0.0;
-                    dmma(acc[t][0], acc[t][1], a, __dmul_rn((double)row[8 * t], sc));
+                    dmma(acc[t][0], acc[t][1], a, __dmul_rn((double)ld_stream(row + 8 * t), sc));
                 }
             }
         }
@@ -808,7 +814,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad, 1);
+    const int cap = p.cap_stage[STAGE - 1];
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles_stage[STAGE - 1], p.NA, p.m_pad, p.dc_pad, 1, cap);
     constexpr int NT = 4 * NPL, TP = (MAXT > 512 && NT % 2 == 0) ? NT / 2 : NT;
     const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
     double *scr = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)BV * NA;
@@ -845,9 +852,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                 __syncwarp();
                 int ov = p.fast_lars
                              ? warp_lars_fast<NPL>(T2, p.ldT2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat, ws.u,
-                                                   ws.gs, ws.P, ws.x, lane)
+                                                   ws.gs, ws.P, ws.x, lane, cap)
                              : warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat,
-                                              ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
+                                              ws.u, ws.gs, ws.P, ws.x, lane, nullptr, cap);
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) {
                     const int j = lane + 32 * s;
@@ -867,7 +874,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                 for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
                 if (STAGE == 1) {  // isotropic fraction (amico/models.pyx:911)
-                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr, cap);
                     if (lane == 0) {
                         p.xiso[2 * pos] = ws.x[n - 1];
                         p.xiso[2 * pos + 1] = p.exvivo ? ws.x[n - 2] : 0.0;
@@ -883,7 +890,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                         allowed |= ((w >> lane) & 1u) << s;
                         support += __popc(w);
                     }
-                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr, cap);
                     noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
                                     (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
                     if (p.support_out && lane == 0) p.support_out[vox] = support;

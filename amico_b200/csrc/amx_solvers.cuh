@@ -51,9 +51,10 @@ struct NnlsStat {
 // least-squares system (the reference stops growing the passive set at m).  Returns overflow flag.
 template <int NPL>
 __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
-                         unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st)
+                         unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st, int cap = LC)
 {
     int np = 0, iter = 0, overflow = 0;
+    cap = min(cap, c_lc_cap);
     unsigned inP = 0;
     double xp = 0.0, zl = 0.0;
 #pragma unroll
@@ -61,7 +62,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
     __syncwarp();
     for (;;) {
         if (np >= mcap) break;
-        if (np >= c_lc_cap) { overflow = 1; break; }
+        if (np >= cap) { overflow = 1; break; }
         // dual w = c - T[:,P] x_P on the zero set
         double wl[NPL];
         unsigned valid = 0;
@@ -255,8 +256,9 @@ __device__ __forceinline__ double sym_at(const double *Mi, int r, int c) { retur
 template <int NPL>
 __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, double ridge_in, int K, int Ltrue, double lambda1,
                          double *DtR, double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane,
-                         int *steps_out)
+                         int *steps_out, int cap = LC)
 {
+    cap = min(cap, c_lc_cap);
     (void)ridge_in;  // T already holds G + max(lambda2, 1e-10) I (k_set_ridge)
     int L = Ltrue < K ? Ltrue : K;
     int overflow = 0;
@@ -291,7 +293,7 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
         if (i < 0) break;  // the CPU path would read ind[-1] here; cannot happen with pos=true
         ++iter;
         if (newAtom) {
-            if (i >= c_lc_cap) { overflow = 1; na = i; break; }
+            if (i >= cap) { overflow = 1; na = i; break; }
             if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
             if ((cur & 31) == lane) act |= 1u << (cur >> 5);
             __syncwarp();
@@ -472,8 +474,9 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
 // CPU's at the 1e-12 level through stage 1.
 template <int NPL>
 __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT, int K, int Ltrue, double lambda1, double *DtR,
-                                           double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane)
+                                           double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane, int cap = LC)
 {
+    cap = min(cap, c_lc_cap);
     int L = Ltrue < K ? Ltrue : K;
     int overflow = 0;
 #pragma unroll
@@ -506,7 +509,7 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         if (i < 0) break;
         ++iter;
         if (newAtom) {
-            if (i >= c_lc_cap) { overflow = 1; na = i; break; }
+            if (i >= cap) { overflow = 1; na = i; break; }
             if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
             if ((cur & 31) == lane) act |= 1u << (cur >> 5);
             __syncwarp();

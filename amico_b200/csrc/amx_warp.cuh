@@ -58,6 +58,21 @@ __device__ __forceinline__ void warp_argmax(double &v, int &idx) { warp_argext<t
 template <bool LOWEST>
 __device__ __forceinline__ void warp_argmin(double &v, int &idx) { warp_argext<false, LOWEST>(v, idx); }
 
+// streaming loads that do not allocate in L1 (the dictionary slab and the signal pass through once per batch;
+// L1 is kept for the Gram rows the solvers re-read)
+__device__ __forceinline__ float ld_stream(const float *p)
+{
+    float v;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ double ld_stream(const double *p)
+{
+    double v;
+    asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
 // un-fused multiply-add: the reference CPU arithmetic (x86-64, no FMA contraction) rounds the product first
 __device__ __forceinline__ double madd(double s, double a, double b) { return __dadd_rn(s, __dmul_rn(a, b)); }
 

@@ -73,6 +73,7 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
         for (a = 0; a < np_; ++a) L[np_][a] = v[a];
         L[np_][np_] = sqrt(d2); z[np_] = znew;
         P[np_++] = j; inP[j] = 1; ++outer;
+        if (stats && np_ > stats[8]) stats[8] = np_;
         for (;;) {
             if (++iter > itmax) goto done;
             back_subst(L, np_, z, s);
