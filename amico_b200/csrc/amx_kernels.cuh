@@ -91,11 +91,16 @@ __global__ void k_scatter(const int *lut, long long n, int *cursor, int *order)
     order[pos] = (int)i;
 }
 
-__global__ void k_tiles(const int *hist, const int *offs, const int *tile_offs, int ndirs, int tile_v, int4 *tiles)
+// balanced: the ceil(c / tile_v) tiles of a bin get (nearly) equal sizes instead of one short tail tile
+__global__ void k_tiles(const int *hist, const int *offs, const int *tile_offs, int ndirs, int tile_v, int4 *tiles, int balanced)
 {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= ndirs) return;
     int c = hist[d], o = offs[d], t = tile_offs[d];
+    if (balanced && c > 0) {
+        const int nt = (c + tile_v - 1) / tile_v;
+        tile_v = (c + nt - 1) / nt;
+    }
     #pragma unroll 1
     for (int s = 0; s < c; s += tile_v, ++t) tiles[t] = make_int4(d, o + s, min(tile_v, c - s), 0);
 }
@@ -227,6 +232,8 @@ struct FitParams {
     int *ovf_list;       // voxels whose active set outgrew a warp: re-fitted by the scalar slow path (amx_slow.cuh)
     long long ovf_cap;
     unsigned *supmask;   // split NODDI path: [n_vox][NPL] stage-2 support, word s bit l <-> atom l + 32 s
+    unsigned w32_T_bytes[3], w32_state[3];
+    const double *T1p, *T2p; size_t T1p_stride, T2p_stride;  // packed symmetric copies of T1 / T2 (k_pack_sym)  // group kernels (amx_w32.cuh): bytes of the staged Gram table / per-warp state, per stage
 };
 
 struct WarpWS {

@@ -309,15 +309,18 @@ def test_chunked_host_pipeline_matches_single_shot(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"AMX_NODDI_SPLIT": "0"}, {"AMX_NODDI_BATCHED": "0"}, {"AMX_NODDI_BATCHED": "0", "AMX_NO_TMA": "1"},
-                                 {"AMX_WARPS": "8"}])
+                                 {"AMX_WARPS": "8"}, {"AMX_NODDI_W32": "1"}, {"AMX_NODDI_W32": "1", "AMX_W32_TILE": "64"}])
 def test_noddi_kernel_variants_agree(monkeypatch, env):
-    """Fused / per-voxel / non-TMA variants of the NODDI path are kept for A/B measurements: same maps within tolerance."""
+    """Fused / per-voxel / non-TMA / voxel-group variants of the NODDI path are kept for A/B measurements: same maps within
+    tolerance (the group kernels of amx_w32.cuh also return the modulated maps)."""
     P = synth.make_problem(2, n_vox=6000, seed=8)
-    base = gpu_fit(P)
+    base = gpu_fit(P, extra=True)
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    alt = gpu_fit(P)
+    alt = gpu_fit(P, extra=True)
+    assert alt["_counters"]["overflow_voxels"] == 0
     assert pass_fraction(alt["estimates"], base["estimates"]) >= 0.999
+    assert pass_fraction(alt["estimates_mod"], base["estimates_mod"]) >= 0.999
 
 
 def test_noddi_whole_brain_protocol_m288():
