@@ -11,7 +11,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libamico_b200.so")
 
-AMX_OK, AMX_E_INVALID, AMX_E_CUDA, AMX_E_LUT_RANGE, AMX_E_CAPACITY = 0, -1, -2, -3, -4
+AMX_OK, AMX_E_INVALID, AMX_E_CUDA, AMX_E_LUT_RANGE, AMX_E_CAPACITY, AMX_E_NONFINITE = 0, -1, -2, -3, -4, -5
+PRE_NORMALIZE, PRE_MERGE_B0, PRE_DIR_AVG, PRE_REPLACE_BAD = 1, 2, 4, 8
 MODEL_NODDI, MODEL_FREEWATER, MODEL_CZB, MODEL_SANDI = 0, 1, 2, 3
 FLAG_RMSE, FLAG_NRMSE, FLAG_EXTRA = 1, 2, 4
 F32, F64 = 0, 1
@@ -23,6 +24,7 @@ EXPORTS = [
     "amx_plan_create_noddi", "amx_plan_create_freewater", "amx_plan_create_czb", "amx_plan_create_sandi",
     "amx_plan_destroy", "amx_plan_info", "amx_fit", "amx_lut_indices", "amx_plan_last_timing",
     "amx_plan_last_counters",
+    "amx_preprocess", "amx_mean_b0", "amx_dti_directions", "amx_scatter_maps",
 ]
 
 
@@ -33,6 +35,17 @@ class FitArgs(C.Structure):
         ("lambda1", C.c_double), ("lambda2", C.c_double), ("flags", C.c_uint32), ("estimates", C.c_void_p),
         ("rmse", C.c_void_p), ("nrmse", C.c_void_p), ("extra", C.c_void_p), ("lut_out", C.c_void_p),
         ("support_out", C.c_void_p), ("coeff_out", C.c_void_p), ("stream", C.c_void_p),
+    ]
+
+
+class PreArgs(C.Structure):
+    """``amx_pre_args`` of include/amico_b200.h."""
+    _fields_ = [
+        ("space", C.c_int), ("device", C.c_int), ("dwi", C.c_void_p), ("n_total", C.c_int64), ("nS", C.c_int),
+        ("mask", C.c_void_p), ("b0_idx", C.c_void_p), ("b0_count", C.c_int), ("dwi_idx", C.c_void_p),
+        ("dwi_count", C.c_int), ("shell_idx", C.c_void_p), ("shell_off", C.c_void_p), ("n_shells", C.c_int),
+        ("flags", C.c_uint32), ("b0_threshold", C.c_float), ("replace_bad", C.c_float), ("y", C.c_void_p),
+        ("y_capacity", C.c_int64), ("vox_idx", C.c_void_p), ("mean_b0s", C.c_void_p), ("stream", C.c_void_p),
     ]
 
 
@@ -70,6 +83,10 @@ def load():
     lib.amx_lut_indices.argtypes = [vp, i32, vp, i64, vp]
     lib.amx_plan_last_timing.argtypes = [vp, C.POINTER(dbl), i32]
     lib.amx_plan_last_counters.argtypes = [vp, C.POINTER(i64), i32]
+    lib.amx_preprocess.argtypes = [C.POINTER(PreArgs), C.POINTER(i64), C.POINTER(i32)]
+    lib.amx_mean_b0.argtypes = [i32, i32, vp, i64, i32, vp, i32, vp, vp]
+    lib.amx_dti_directions.argtypes = [i32, i32, vp, i32, i64, i32, vp, dbl, vp, vp]
+    lib.amx_scatter_maps.argtypes = [i32, i32, vp, i64, i32, vp, vp, i64, vp]
     for name in EXPORTS:
         if name not in ("amx_last_error",):
             getattr(lib, name).restype = i32

@@ -3,6 +3,7 @@
 #include "amx_kernels.cuh"
 #include "amx_slow.cuh"
 #include "amx_w32.cuh"
+#include "amx_err.h"
 
 #include <algorithm>
 #include <cstdarg>
@@ -51,6 +52,21 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+
+}  // namespace
+
+int amx::set_error(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+namespace {
 
 int env_int(const char *name, int dflt)
 {

@@ -1,0 +1,685 @@
+// The callers either side of the per-voxel fit, on the GPU (include/amico_b200.h, second part):
+//   amx_preprocess      amico/core.py:151-156, 209-278 (load_data: NaN policy, b0 normalisation, b0 merge, directional
+//                       average) + :451-452 (mask compaction, y < 0 -> 0)
+//   amx_mean_b0         amico/core.py:212
+//   amx_dti_directions  amico/core.py:430-436, 456-458 (dipy TensorModel OLS -> principal eigenvector)
+//   amx_scatter_maps    amico/core.py:472-498
+//
+// All three are streaming, HBM-bound passes (a few flops per byte).  Shape of every kernel: a warp takes a CHUNK of 32
+// consecutive voxels -- one contiguous block of 32 * nS floats in the voxel-major volume -- pulls it into shared memory
+// with 128-bit coalesced loads (row stride padded to an odd word count), lets lane v do voxel v's short sequential
+// arithmetic conflict-free, and writes the result rows back fully coalesced.  Grids are sized to the SM count and
+// walk the chunks with a stride (persistent warps).
+#include "../../include/amico_b200.h"
+#include "amx_err.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <vector>
+
+namespace {
+
+constexpr unsigned FULLM = 0xffffffffu;
+constexpr int CH = 32;           // voxels per chunk (one per lane)
+constexpr int PRE_BLOCK_VOX = 1024;  // voxels per mask-count block
+
+struct PreParams {
+    const float *dwi; long long n_total; int nS, stride;  // stride = nS | 1 (words per shared-memory row)
+    const unsigned char *mask;
+    const int *b0_idx; int b0_count;
+    const int *dwi_idx; int dwi_count;
+    const int *shell_idx; const int *shell_off; int n_shells;
+    unsigned flags; float thr, repl;
+    int m_out;
+    float *y; long long y_cap; int *vox_idx; float *mean_b0s;
+    const long long *block_off;  // exclusive prefix of kept voxels per PRE_BLOCK_VOX block
+    unsigned *status;            // [0] bit0: non-finite raw value, bit1: non-finite pre-processed value, bit2: y overflow
+};
+
+// ---- mask compaction: counts per block of 1024 voxels, exclusive scan, total -------------------------------------
+__global__ void k_mask_count(const unsigned char *__restrict__ mask, long long n, long long *counts)
+{
+    const long long base = (long long)blockIdx.x * PRE_BLOCK_VOX;
+    int c = 0;
+    for (int i = threadIdx.x; i < PRE_BLOCK_VOX; i += blockDim.x) {
+        const long long v = base + i;
+        if (v < n) c += mask ? (mask[v] == 1) : 1;
+    }
+    __shared__ int ws[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULLM, c, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULLM, t, o);
+        if (threadIdx.x == 0) counts[blockIdx.x] = t;
+    }
+}
+
+// single-block exclusive scan over n_blocks counts (in place), total -> counts[n_blocks]
+__global__ void k_scan_counts(long long *counts, int n_blocks)
+{
+    __shared__ long long wtot[32], wexcl[32];
+    __shared__ long long carry, tot;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int b0 = 0; b0 < n_blocks; b0 += blockDim.x) {
+        const int i = b0 + threadIdx.x;
+        const long long v = i < n_blocks ? counts[i] : 0;
+        long long inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(FULLM, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            const long long w = lane < nw ? wtot[lane] : 0;
+            long long winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(FULLM, winc, o);
+                if (lane >= o) winc += t;
+            }
+            wexcl[lane] = winc - w;
+            if (lane == 31) tot = winc;
+        }
+        __syncthreads();
+        if (i < n_blocks) counts[i] = carry + wexcl[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) counts[n_blocks] = carry;
+}
+
+// ---- shared-memory staging of a chunk ------------------------------------------------------------------------------
+// count = nvox * nS consecutive floats starting at src (16-byte aligned: chunks start at multiples of 32 voxels) ->
+// rows of `stride` words.  Returns true when a non-finite value passed through (raw-signal check of core.py:151).
+__device__ __forceinline__ bool stage_rows(float *rows, const float *__restrict__ src, int count, int nS, int stride, int lane,
+                                           bool replace, float repl)
+{
+    bool bad = false;
+    int e = lane * 4;
+    int v = e / nS, j = e - v * nS;
+    const int count4 = count & ~3;
+    while (e < count4) {
+        float4 q = __ldcs(reinterpret_cast<const float4 *>(src + e));
+        float x[4] = {q.x, q.y, q.z, q.w};
+        int vv = v, jj = j;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float f = x[t];
+            if (!isfinite(f)) {
+                bad = true;
+                if (replace) f = repl;
+            }
+            rows[vv * stride + jj] = f;
+            if (++jj == nS) { jj = 0; ++vv; }
+        }
+        e += 128;
+        j += 128;
+        while (j >= nS) { j -= nS; ++v; }
+    }
+    // tail (count not a multiple of 4 can only happen in the last, partial chunk)
+    for (int t = count4 + lane; t < count; t += 32) {
+        float f = __ldcs(src + t);
+        if (!isfinite(f)) {
+            bad = true;
+            if (replace) f = repl;
+        }
+        const int vv = t / nS;
+        rows[vv * stride + (t - vv * nS)] = f;
+    }
+    return bad;
+}
+
+// sequential float32 mean, index order: what numpy does for np.mean(img[:, :, :, idx], axis=3) (the fancy-indexed copy
+// has the indexed axis slowest in memory, so the reduction is a plain in-order accumulation, then one division)
+template <typename F>
+__device__ __forceinline__ float seq_mean(int n, F get)
+{
+    float s = get(0);
+    for (int i = 1; i < n; ++i) s = __fadd_rn(s, get(i));
+    return __fdiv_rn(s, (float)n);
+}
+
+// One warp per chunk of 32 voxels.
+__global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long n_chunks)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const int nS = p.nS, stride = p.stride, m_out = p.m_out;
+    float *rows = smem + (size_t)warp * (CH * stride + CH);
+    float *nfs = rows + CH * stride;  // per-voxel norm factor
+    const bool replace = p.flags & AMX_PRE_REPLACE_BAD;
+    unsigned st = 0;
+    for (long long c = (long long)blockIdx.x * wpb + warp; c < n_chunks; c += (long long)gridDim.x * wpb) {
+        const long long v0 = c * CH;
+        const int nvox = (int)min((long long)CH, p.n_total - v0);
+        if (stage_rows(rows, p.dwi + v0 * nS, nvox * nS, nS, stride, lane, replace, p.repl)) st |= 1u;
+        __syncwarp();
+        // ---- lane v: the voxel's short sequential arithmetic
+        const bool have = lane < nvox;
+        float *r = rows + lane * stride;
+        bool keep = false;
+        if (have) {
+            keep = p.mask ? (p.mask[v0 + lane] == 1) : true;
+            float nf = 1.0f;
+            if (p.b0_count > 0 && ((p.flags & AMX_PRE_NORMALIZE) || p.mean_b0s)) {
+                const float mb = seq_mean(p.b0_count, [&](int i) { return r[p.b0_idx[i]]; });
+                if (p.mean_b0s) p.mean_b0s[v0 + lane] = mb;
+                if (p.flags & AMX_PRE_NORMALIZE) {
+                    // norm_factor = mean_b0s; idx = nf <= thr; nf[idx] = 1; nf = 1 / nf; nf[idx] = 0   (core.py:215-219)
+                    const bool off = mb <= p.thr;
+                    nf = off ? 0.0f : __fdiv_rn(1.0f, mb);
+                }
+            }
+            nfs[lane] = nf;
+            const bool norm = p.flags & AMX_PRE_NORMALIZE;
+            if (p.flags & AMX_PRE_MERGE_B0) {
+                // out = [mean of the (normalised) b0 volumes | (normalised) dwi volumes]   (core.py:226-227)
+                const float mb0 = seq_mean(p.b0_count, [&](int i) { const float x = r[p.b0_idx[i]]; return norm ? __fmul_rn(x, nf) : x; });
+                // in place: dwi_idx is ascending, so dwi_idx[k] >= k and compacting forward to r[k] never overwrites an
+                // unread source; then shift up by one (slot dwi_count exists: there is at least one b0)
+                for (int k = 0; k < p.dwi_count; ++k) {
+                    const float x = r[p.dwi_idx[k]];
+                    r[k] = norm ? __fmul_rn(x, nf) : x;
+                }
+                for (int k = p.dwi_count; k > 0; --k) r[k] = r[k - 1];
+                r[0] = mb0;
+            } else if (p.flags & AMX_PRE_DIR_AVG) {
+                // dir_avg_img is a VIEW of the first n_shells+1 volumes (core.py:234): every mean is written in place and
+                // later means read the already overwritten volumes.  Normalise the row first, then replay that.
+                if (norm)
+                    for (int j = 0; j < nS; ++j) r[j] = __fmul_rn(r[j], nf);
+                const float a0 = seq_mean(p.b0_count, [&](int i) { return r[p.b0_idx[i]]; });
+                r[0] = a0;
+                for (int s = 0; s < p.n_shells; ++s) {
+                    const int o = p.shell_off[s], cnt = p.shell_off[s + 1] - o;
+                    const float a = seq_mean(cnt, [&](int i) { return r[p.shell_idx[o + i]]; });
+                    r[s + 1] = a;
+                }
+            } else if (norm) {
+                for (int j = 0; j < nS; ++j) r[j] = __fmul_rn(r[j], nf);
+            }
+        }
+        const unsigned keepmask = __ballot_sync(FULLM, keep);
+        __syncwarp();
+        // ---- output: the kept voxels' rows are consecutive in y
+        const int nkeep = __popc(keepmask);
+        if (nkeep) {
+            const long long blk = v0 / PRE_BLOCK_VOX;
+            // rank of this chunk's first kept voxel inside its 1024-voxel block
+            long long pos0 = p.block_off[blk];
+            {
+                const long long b0v = blk * PRE_BLOCK_VOX;
+                int before = 0;
+                if (p.mask) {
+                    for (long long v = b0v + lane; v < v0; v += 32) before += (p.mask[v] == 1);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULLM, before, o);
+                } else {
+                    before = (int)(v0 - b0v);
+                }
+                pos0 += before;
+            }
+            if (pos0 + nkeep > p.y_cap) {
+                st |= 4u;
+            } else {
+                if (keep) p.vox_idx[pos0 + __popc(keepmask & ((1u << lane) - 1u))] = (int)(v0 + lane);
+                float *out = p.y + pos0 * m_out;
+                const int total = nkeep * m_out;
+                int rr = 0, j = lane;
+                while (j >= m_out) { j -= m_out; ++rr; }
+                bool bad = false;
+                for (int e = lane; e < total; e += 32) {
+                    const int v = keepmask == FULLM ? rr : (int)__fns(keepmask, 0, rr + 1);
+                    float f = rows[v * stride + j];
+                    if (!isfinite(f)) {
+                        bad = true;
+                        if (replace) f = p.repl;
+                    }
+                    out[e] = f < 0.0f ? 0.0f : f;  // y[y < 0] = 0 (core.py:452)
+                    j += 32;
+                    while (j >= m_out) { j -= m_out; ++rr; }
+                }
+                if (bad) st |= 2u;
+            }
+        }
+        __syncwarp();
+    }
+    st = __reduce_or_sync(FULLM, st);
+    if (lane == 0 && st) atomicOr(p.status, st);
+}
+
+// mean b0 only (amx_mean_b0): same staging, one value per voxel out
+__global__ void __launch_bounds__(128) k_mean_b0(const float *__restrict__ dwi, long long n_total, int nS, int stride,
+                                                 const int *__restrict__ b0_idx, int b0_count, float *mean_b0s, long long n_chunks)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    float *rows = smem + (size_t)warp * (CH * stride + CH);
+    for (long long c = (long long)blockIdx.x * wpb + warp; c < n_chunks; c += (long long)gridDim.x * wpb) {
+        const long long v0 = c * CH;
+        const int nvox = (int)min((long long)CH, n_total - v0);
+        stage_rows(rows, dwi + v0 * nS, nvox * nS, nS, stride, lane, false, 0.0f);
+        __syncwarp();
+        if (lane < nvox) {
+            const float *r = rows + lane * stride;
+            mean_b0s[v0 + lane] = seq_mean(b0_count, [&](int i) { return r[b0_idx[i]]; });
+        }
+        __syncwarp();
+    }
+}
+
+// ---- DTI principal direction ---------------------------------------------------------------------------------------
+// cyclic Jacobi on the symmetric 3x3 tensor (fp64): a = {xx, xy, yy, xz, yz, zz}; returns the unit eigenvector of the
+// largest eigenvalue (the column dipy's decompose_tensor puts first, dipy/reconst/dti.py `decompose_tensor`)
+__device__ __forceinline__ void principal_evec(double a00, double a01, double a11, double a02, double a12, double a22, double *out)
+{
+    double A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+#pragma unroll 1
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+        if (off == 0.0) break;
+        const double dg = fabs(A[0][0]) + fabs(A[1][1]) + fabs(A[2][2]);
+        if (off <= 1e-18 * dg) break;
+#pragma unroll
+        for (int pq = 0; pq < 3; ++pq) {
+            const int pI = pq == 2 ? 1 : 0, qI = pq == 0 ? 1 : 2;
+            const double apq = A[pI][qI];
+            if (apq == 0.0) continue;
+            const double theta = (A[qI][qI] - A[pI][pI]) / (2.0 * apq);
+            double t;
+            if (fabs(theta) > 1e150) t = 0.5 / theta;
+            else t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+            const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+            const int rI = 3 - pI - qI;
+            const double app = A[pI][pI], aqq = A[qI][qI];
+            A[pI][pI] = app - t * apq;
+            A[qI][qI] = aqq + t * apq;
+            A[pI][qI] = A[qI][pI] = 0.0;
+            const double arp = A[rI][pI], arq = A[rI][qI];
+            A[rI][pI] = A[pI][rI] = cs * arp - sn * arq;
+            A[rI][qI] = A[qI][rI] = sn * arp + cs * arq;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double vp = V[k][pI], vq = V[k][qI];
+                V[k][pI] = cs * vp - sn * vq;
+                V[k][qI] = sn * vp + cs * vq;
+            }
+        }
+    }
+    int b = 0;
+    if (A[1][1] > A[b][b]) b = 1;
+    if (A[2][2] > (b == 0 ? A[0][0] : A[1][1])) b = 2;
+    double x = b == 0 ? V[0][0] : b == 1 ? V[0][1] : V[0][2];
+    double y = b == 0 ? V[1][0] : b == 1 ? V[1][1] : V[1][2];
+    double z = b == 0 ? V[2][0] : b == 1 ? V[2][1] : V[2][2];
+    const double nrm = sqrt(x * x + y * y + z * z);
+    out[0] = x / nrm; out[1] = y / nrm; out[2] = z / nrm;
+}
+
+template <typename T>
+__device__ __forceinline__ void stage_plain(T *rows, const T *__restrict__ src, int count, int m, int stride, int lane)
+{
+    int v = 0, j = lane;
+    while (j >= m) { j -= m; ++v; }
+    for (int e = lane; e < count; e += 32) {
+        rows[v * stride + j] = __ldcs(src + e);
+        j += 32;
+        while (j >= m) { j -= m; ++v; }
+    }
+}
+
+// W (6 x m, fp64) sits at the start of shared memory; one warp per chunk of 32 voxels
+template <typename T>
+__global__ void __launch_bounds__(128) k_dti(const T *__restrict__ y, long long n_vox, int m, int stride, const double *__restrict__ W,
+                                             double min_signal, double *dirs, long long n_chunks)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sW = reinterpret_cast<double *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 6 * m; i += blockDim.x) sW[i] = W[i];
+    __syncthreads();
+    T *rows = reinterpret_cast<T *>(sW + 6 * m) + (size_t)warp * CH * stride;
+    for (long long c = (long long)blockIdx.x * wpb + warp; c < n_chunks; c += (long long)gridDim.x * wpb) {
+        const long long v0 = c * CH;
+        const int nvox = (int)min((long long)CH, n_vox - v0);
+        stage_plain<T>(rows, y + v0 * m, nvox * m, m, stride, lane);
+        __syncwarp();
+        if (lane < nvox) {
+            const T *r = rows + lane * stride;
+            double d[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+            for (int j = 0; j < m; ++j) {
+                const double ls = log(fmax((double)r[j], min_signal));
+#pragma unroll
+                for (int k = 0; k < 6; ++k) d[k] = fma(sW[k * m + j], ls, d[k]);
+            }
+            double e[3];
+            principal_evec(d[0], d[1], d[2], d[3], d[4], d[5], e);
+            double *o = dirs + (v0 + lane) * 3;
+            o[0] = e[0]; o[1] = e[1]; o[2] = e[2];
+        }
+        __syncwarp();
+    }
+}
+
+// ---- result scatter ----------------------------------------------------------------------------------------------------
+__global__ void k_scatter_maps(const double *__restrict__ values, long long n_vox, int k, const int *__restrict__ vox_idx,
+                               float *volume)
+{
+    const long long total = n_vox * k;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long i = e / k;
+        const int c = (int)(e - i * k);
+        volume[(long long)vox_idx[i] * k + c] = (float)values[e];
+    }
+}
+
+// ---- host helpers ------------------------------------------------------------------------------------------------------
+struct Tmp {  // stream-ordered temporaries
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit Tmp(cudaStream_t s_) : s(s_) {}
+    ~Tmp() { for (void *p : ptrs) cudaFreeAsync(p, s); }
+    cudaError_t alloc(void **p, size_t bytes)
+    {
+        cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 16, s);
+        if (e == cudaSuccess) ptrs.push_back(*p);
+        return e;
+    }
+};
+
+int pick_device(int device, int *sm_count, int *max_smem)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return amx::set_error(AMX_E_CUDA, "no CUDA device available (%s): amico_b200 has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return amx::set_error(AMX_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
+    AMX_CK(cudaSetDevice(device));
+    AMX_CK(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
+    AMX_CK(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    return AMX_OK;
+}
+
+// warps per CTA such that `fixed + warps * per_warp` bytes fit the opt-in shared-memory limit (<= 4)
+int warps_for(size_t fixed, size_t per_warp, int max_smem)
+{
+    int w = 4;
+    while (w > 0 && fixed + (size_t)w * per_warp > (size_t)max_smem) --w;
+    return w;
+}
+
+int check_idx(const int32_t *idx, int n, int nS, const char *what)
+{
+    if (n < 0 || (n > 0 && !idx)) return amx::set_error(AMX_E_INVALID, "%s: bad index list", what);
+    for (int i = 0; i < n; ++i)
+        if (idx[i] < 0 || idx[i] >= nS) return amx::set_error(AMX_E_INVALID, "%s[%d]=%d outside [0,%d)", what, i, idx[i], nS);
+    return AMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int amx_preprocess(const amx_pre_args *a, int64_t *n_kept, int *m_out_p)
+{
+    if (!a || !n_kept) return amx::set_error(AMX_E_INVALID, "NULL argument");
+    *n_kept = 0;
+    if (!a->dwi || a->n_total <= 0 || a->nS <= 0 || !a->y || !a->vox_idx || a->y_capacity < 0)
+        return amx::set_error(AMX_E_INVALID, "bad volume / output arguments");
+    if (a->n_total > 0x7fffffffLL) return amx::set_error(AMX_E_INVALID, "more than 2^31 voxels");
+    if ((a->flags & AMX_PRE_MERGE_B0) && (a->flags & AMX_PRE_DIR_AVG))
+        return amx::set_error(AMX_E_INVALID, "doMergeB0 together with doDirectionalAverage is not meaningful: the reference "
+                                             "indexes the merged volume with the un-merged scheme (amico/core.py:225-245)");
+    int rc;
+    if ((rc = check_idx(a->b0_idx, a->b0_count, a->nS, "b0_idx")) || (rc = check_idx(a->dwi_idx, a->dwi_count, a->nS, "dwi_idx"))) return rc;
+    const bool needs_b0 = a->flags & (AMX_PRE_NORMALIZE | AMX_PRE_MERGE_B0 | AMX_PRE_DIR_AVG);
+    if (needs_b0 && a->b0_count <= 0)
+        return amx::set_error(AMX_E_INVALID, "No b0 volume to normalize signal with");  // core.py:214
+    int m_out = a->nS;
+    int n_shell_idx = 0;
+    if (a->flags & AMX_PRE_MERGE_B0) {
+        m_out = 1 + a->dwi_count;
+        for (int k = 1; k < a->dwi_count; ++k)
+            if (a->dwi_idx[k] <= a->dwi_idx[k - 1]) return amx::set_error(AMX_E_INVALID, "dwi_idx must be ascending");
+    }
+    if (a->flags & AMX_PRE_DIR_AVG) {
+        if (a->n_shells <= 0 || !a->shell_off || !a->shell_idx || a->n_shells + 1 > a->nS)
+            return amx::set_error(AMX_E_INVALID, "bad shell lists");
+        n_shell_idx = a->shell_off[a->n_shells];
+        for (int s = 0; s < a->n_shells; ++s)
+            if (a->shell_off[s + 1] <= a->shell_off[s] || a->shell_off[0] != 0) return amx::set_error(AMX_E_INVALID, "bad shell offsets");
+        if ((rc = check_idx(a->shell_idx, n_shell_idx, a->nS, "shell_idx"))) return rc;
+        m_out = 1 + a->n_shells;
+    }
+    if (m_out_p) *m_out_p = m_out;
+    int sm = 0, max_smem = 0;
+    if ((rc = pick_device(a->device, &sm, &max_smem))) return rc;
+    cudaStream_t s = (cudaStream_t)a->stream;
+    Tmp tmp(s);
+    const bool host = a->space == AMX_SPACE_HOST;
+    if (!host && a->space != AMX_SPACE_DEVICE) return amx::set_error(AMX_E_INVALID, "bad space");
+
+    PreParams p{};
+    p.n_total = a->n_total; p.nS = a->nS; p.stride = a->nS | 1;
+    p.b0_count = a->b0_count; p.dwi_count = a->dwi_count; p.n_shells = (a->flags & AMX_PRE_DIR_AVG) ? a->n_shells : 0;
+    p.flags = a->flags; p.thr = a->b0_threshold; p.repl = a->replace_bad; p.m_out = m_out; p.y_cap = a->y_capacity;
+
+    // small index lists -> one device buffer
+    std::vector<int> idx;
+    idx.insert(idx.end(), a->b0_idx, a->b0_idx + a->b0_count);
+    const size_t o_dwi = idx.size();
+    idx.insert(idx.end(), a->dwi_idx, a->dwi_idx + a->dwi_count);
+    const size_t o_sh = idx.size();
+    if (p.n_shells) idx.insert(idx.end(), a->shell_idx, a->shell_idx + n_shell_idx);
+    const size_t o_off = idx.size();
+    if (p.n_shells) idx.insert(idx.end(), a->shell_off, a->shell_off + p.n_shells + 1);
+    int *d_idx = nullptr;
+    AMX_CK(tmp.alloc((void **)&d_idx, idx.size() * sizeof(int)));
+    if (!idx.empty()) AMX_CK(cudaMemcpyAsync(d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice, s));
+    p.b0_idx = d_idx; p.dwi_idx = d_idx + o_dwi; p.shell_idx = d_idx + o_sh; p.shell_off = d_idx + o_off;
+
+    const size_t vol_bytes = (size_t)a->n_total * a->nS * sizeof(float);
+    float *d_dwi = nullptr, *d_y = nullptr, *d_mb = nullptr;
+    unsigned char *d_mask = nullptr;
+    int *d_vidx = nullptr;
+    if (host) {
+        AMX_CK(tmp.alloc((void **)&d_dwi, vol_bytes));
+        AMX_CK(cudaMemcpyAsync(d_dwi, a->dwi, vol_bytes, cudaMemcpyHostToDevice, s));
+        if (a->mask) {
+            AMX_CK(tmp.alloc((void **)&d_mask, (size_t)a->n_total));
+            AMX_CK(cudaMemcpyAsync(d_mask, a->mask, (size_t)a->n_total, cudaMemcpyHostToDevice, s));
+        }
+        AMX_CK(tmp.alloc((void **)&d_y, (size_t)a->y_capacity * m_out * sizeof(float)));
+        AMX_CK(tmp.alloc((void **)&d_vidx, (size_t)a->y_capacity * sizeof(int)));
+        if (a->mean_b0s) AMX_CK(tmp.alloc((void **)&d_mb, (size_t)a->n_total * sizeof(float)));
+        p.dwi = d_dwi; p.mask = d_mask; p.y = d_y; p.vox_idx = d_vidx; p.mean_b0s = d_mb;
+    } else {
+        p.dwi = a->dwi; p.mask = a->mask; p.y = a->y; p.vox_idx = a->vox_idx; p.mean_b0s = a->mean_b0s;
+    }
+    if (((uintptr_t)p.dwi & 15) != 0) return amx::set_error(AMX_E_INVALID, "dwi must be 16-byte aligned");
+
+    const int n_blocks = (int)((a->n_total + PRE_BLOCK_VOX - 1) / PRE_BLOCK_VOX);
+    long long *d_counts = nullptr;
+    unsigned *d_status = nullptr;
+    AMX_CK(tmp.alloc((void **)&d_counts, (size_t)(n_blocks + 1) * sizeof(long long)));
+    AMX_CK(tmp.alloc((void **)&d_status, 16));
+    AMX_CK(cudaMemsetAsync(d_status, 0, 16, s));
+    k_mask_count<<<n_blocks, 256, 0, s>>>(p.mask, a->n_total, d_counts);
+    k_scan_counts<<<1, 1024, 0, s>>>(d_counts, n_blocks);
+    p.block_off = d_counts; p.status = d_status;
+
+    const size_t per_warp = (size_t)(CH * p.stride + CH) * sizeof(float);
+    const int warps = warps_for(0, per_warp, max_smem);
+    if (warps <= 0) return amx::set_error(AMX_E_INVALID, "nS=%d too large for the shared-memory staging", a->nS);
+    const size_t smem = (size_t)warps * per_warp;
+    AMX_CK(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_chunks = (a->n_total + CH - 1) / CH;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / smem));
+    const long long want = (n_chunks + warps - 1) / warps;
+    const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * ctas_per_sm));
+    k_preprocess<<<grid, warps * 32, smem, s>>>(p, n_chunks);
+    AMX_CK(cudaGetLastError());
+
+    long long total = 0;
+    unsigned status = 0;
+    AMX_CK(cudaMemcpyAsync(&total, d_counts + n_blocks, sizeof total, cudaMemcpyDeviceToHost, s));
+    AMX_CK(cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, s));
+    AMX_CK(cudaStreamSynchronize(s));
+    *n_kept = total;
+    if (status & 4u) return amx::set_error(AMX_E_INVALID, "y_capacity=%lld is smaller than the %lld mask voxels", (long long)a->y_capacity, total);
+    if ((status & 1u) && !(a->flags & AMX_PRE_REPLACE_BAD))
+        return amx::set_error(AMX_E_NONFINITE, "Nan or Inf values in the raw signal. Try using the \"replace_bad_voxels\" or "
+                                               "\"b0_min_signal\" parameters when calling \"load_data()\"");
+    if ((status & 2u) && !(a->flags & AMX_PRE_REPLACE_BAD))
+        return amx::set_error(AMX_E_NONFINITE, "Nan or Inf values in the signal after the pre-processing. Try using the "
+                                               "\"replace_bad_voxels\" or \"b0_min_signal\" parameters when calling \"load_data()\"");
+    if (host) {
+        AMX_CK(cudaMemcpyAsync(a->y, d_y, (size_t)total * m_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+        AMX_CK(cudaMemcpyAsync(a->vox_idx, d_vidx, (size_t)total * sizeof(int), cudaMemcpyDeviceToHost, s));
+        if (a->mean_b0s) AMX_CK(cudaMemcpyAsync(a->mean_b0s, d_mb, (size_t)a->n_total * sizeof(float), cudaMemcpyDeviceToHost, s));
+        AMX_CK(cudaStreamSynchronize(s));
+    }
+    return AMX_OK;
+}
+
+int amx_mean_b0(int space, int device, const float *dwi, int64_t n_total, int nS, const int32_t *b0_idx, int b0_count,
+                float *mean_b0s, void *stream)
+{
+    if (!dwi || !mean_b0s || n_total <= 0 || nS <= 0) return amx::set_error(AMX_E_INVALID, "bad arguments");
+    if (b0_count <= 0) return amx::set_error(AMX_E_INVALID, "No b0 volume to normalize signal with");
+    int rc;
+    if ((rc = check_idx(b0_idx, b0_count, nS, "b0_idx"))) return rc;
+    int sm = 0, max_smem = 0;
+    if ((rc = pick_device(device, &sm, &max_smem))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tmp tmp(s);
+    const bool host = space == AMX_SPACE_HOST;
+    int *d_idx = nullptr;
+    AMX_CK(tmp.alloc((void **)&d_idx, (size_t)b0_count * sizeof(int)));
+    AMX_CK(cudaMemcpyAsync(d_idx, b0_idx, (size_t)b0_count * sizeof(int), cudaMemcpyHostToDevice, s));
+    const float *src = dwi;
+    float *dst = mean_b0s;
+    if (host) {
+        float *d_dwi = nullptr, *d_mb = nullptr;
+        AMX_CK(tmp.alloc((void **)&d_dwi, (size_t)n_total * nS * sizeof(float)));
+        AMX_CK(cudaMemcpyAsync(d_dwi, dwi, (size_t)n_total * nS * sizeof(float), cudaMemcpyHostToDevice, s));
+        AMX_CK(tmp.alloc((void **)&d_mb, (size_t)n_total * sizeof(float)));
+        src = d_dwi; dst = d_mb;
+    }
+    const int stride = nS | 1;
+    const size_t per_warp = (size_t)(CH * stride + CH) * sizeof(float);
+    const int warps = warps_for(0, per_warp, max_smem);
+    if (warps <= 0) return amx::set_error(AMX_E_INVALID, "nS=%d too large for the shared-memory staging", nS);
+    const size_t smem = (size_t)warps * per_warp;
+    AMX_CK(cudaFuncSetAttribute(k_mean_b0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const long long n_chunks = (n_total + CH - 1) / CH;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / smem));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_chunks + warps - 1) / warps, (long long)sm * ctas_per_sm));
+    k_mean_b0<<<grid, warps * 32, smem, s>>>(src, n_total, nS, stride, d_idx, b0_count, dst, n_chunks);
+    AMX_CK(cudaGetLastError());
+    if (host) AMX_CK(cudaMemcpyAsync(mean_b0s, dst, (size_t)n_total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    AMX_CK(cudaStreamSynchronize(s));
+    return AMX_OK;
+}
+
+int amx_dti_directions(int device, int space, const void *y, int y_dtype, int64_t n_vox, int m, const double *W,
+                       double min_signal, double *dirs, void *stream)
+{
+    if (!y || !W || !dirs || n_vox < 0 || m <= 0) return amx::set_error(AMX_E_INVALID, "bad arguments");
+    if (y_dtype != AMX_F32 && y_dtype != AMX_F64) return amx::set_error(AMX_E_INVALID, "bad y_dtype");
+    int rc, sm = 0, max_smem = 0;
+    if ((rc = pick_device(device, &sm, &max_smem))) return rc;
+    if (n_vox == 0) return AMX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tmp tmp(s);
+    const bool host = space == AMX_SPACE_HOST;
+    const size_t esz = y_dtype == AMX_F64 ? 8 : 4;
+    double *d_W = nullptr;
+    AMX_CK(tmp.alloc((void **)&d_W, (size_t)6 * m * sizeof(double)));
+    AMX_CK(cudaMemcpyAsync(d_W, W, (size_t)6 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+    const void *src = y;
+    double *dst = dirs;
+    if (host) {
+        void *d_y = nullptr;
+        double *d_d = nullptr;
+        AMX_CK(tmp.alloc(&d_y, (size_t)n_vox * m * esz));
+        AMX_CK(cudaMemcpyAsync(d_y, y, (size_t)n_vox * m * esz, cudaMemcpyHostToDevice, s));
+        AMX_CK(tmp.alloc((void **)&d_d, (size_t)n_vox * 3 * sizeof(double)));
+        src = d_y; dst = d_d;
+    }
+    const int stride = m | 1;
+    const size_t fixed = (size_t)6 * m * sizeof(double), per_warp = (size_t)CH * stride * esz;
+    const int warps = warps_for(fixed, per_warp, max_smem);
+    if (warps <= 0) return amx::set_error(AMX_E_INVALID, "m=%d too large for the shared-memory staging", m);
+    const size_t smem = fixed + (size_t)warps * per_warp;
+    const long long n_chunks = (n_vox + CH - 1) / CH;
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / smem));
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_chunks + warps - 1) / warps, (long long)sm * ctas_per_sm));
+    if (y_dtype == AMX_F64) {
+        AMX_CK(cudaFuncSetAttribute(k_dti<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dti<double><<<grid, warps * 32, smem, s>>>((const double *)src, n_vox, m, stride, d_W, min_signal, dst, n_chunks);
+    } else {
+        AMX_CK(cudaFuncSetAttribute(k_dti<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dti<float><<<grid, warps * 32, smem, s>>>((const float *)src, n_vox, m, stride, d_W, min_signal, dst, n_chunks);
+    }
+    AMX_CK(cudaGetLastError());
+    if (host) {
+        AMX_CK(cudaMemcpyAsync(dirs, dst, (size_t)n_vox * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        AMX_CK(cudaStreamSynchronize(s));
+    }
+    return AMX_OK;
+}
+
+int amx_scatter_maps(int device, int space, const double *values, int64_t n_vox, int k, const int32_t *vox_idx, float *volume,
+                     int64_t n_total, void *stream)
+{
+    if (!volume || n_total <= 0 || k <= 0 || n_vox < 0 || (n_vox > 0 && (!values || !vox_idx)))
+        return amx::set_error(AMX_E_INVALID, "bad arguments");
+    int rc, sm = 0, max_smem = 0;
+    if ((rc = pick_device(device, &sm, &max_smem))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tmp tmp(s);
+    const bool host = space == AMX_SPACE_HOST;
+    const double *src = values;
+    const int *idx = vox_idx;
+    float *dst = volume;
+    if (host) {
+        double *d_v = nullptr;
+        int *d_i = nullptr;
+        float *d_o = nullptr;
+        AMX_CK(tmp.alloc((void **)&d_v, (size_t)n_vox * k * sizeof(double)));
+        AMX_CK(tmp.alloc((void **)&d_i, (size_t)n_vox * sizeof(int)));
+        AMX_CK(tmp.alloc((void **)&d_o, (size_t)n_total * k * sizeof(float)));
+        if (n_vox) {
+            AMX_CK(cudaMemcpyAsync(d_v, values, (size_t)n_vox * k * sizeof(double), cudaMemcpyHostToDevice, s));
+            AMX_CK(cudaMemcpyAsync(d_i, vox_idx, (size_t)n_vox * sizeof(int), cudaMemcpyHostToDevice, s));
+        }
+        src = d_v; idx = d_i; dst = d_o;
+    }
+    AMX_CK(cudaMemsetAsync(dst, 0, (size_t)n_total * k * sizeof(float), s));
+    if (n_vox) {
+        const long long total = (long long)n_vox * k;
+        const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, (long long)sm * 8));
+        k_scatter_maps<<<grid, 256, 0, s>>>(src, n_vox, k, idx, dst);
+        AMX_CK(cudaGetLastError());
+    }
+    if (host) {
+        AMX_CK(cudaMemcpyAsync(volume, dst, (size_t)n_total * k * sizeof(float), cudaMemcpyDeviceToHost, s));
+        AMX_CK(cudaStreamSynchronize(s));
+    }
+    return AMX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,302 @@
+"""``Evaluation``: the reference's ``amico.Evaluation`` flow around ``model.fit()`` with the volume resident in HBM.
+
+Mirrors the part of ``amico/core.py`` that sits either side of the per-voxel fit:
+
+* ``load_data``  -- NaN policy, b0 normalisation, b0 merge, directional average (``core.py:151-156, 209-278``),
+                    mask compaction and ``y < 0 -> 0`` (``core.py:451-452``): one streaming kernel (``amx_preprocess``);
+* ``fit``        -- principal directions (``core.py:430-436, 456-458``; dipy ``TensorModel(OLS)``): ``amx_dti_directions``;
+                    ``model.fit`` (``core.py:465``): ``amx_fit`` on device pointers; result scatter (``core.py:472-498``):
+                    ``amx_scatter_maps``.
+
+The raw volume is uploaded once; ``y``, ``DIRs`` and the estimates never leave the GPU until ``RESULTS`` is read.  File
+I/O (NIfTI, scheme text files), kernel generation/resampling and saving stay with the caller: ``load_data`` takes arrays,
+``load_kernels`` takes the ``KERNELS`` dict a ``<Model>.resample`` produced.  torch is used for device memory and streams
+only.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import _lib as L
+from . import models as _models
+from .scheme import Scheme
+
+MIN_POSITIVE_SIGNAL = 0.0001  # dipy.reconst.dti.MIN_POSITIVE_SIGNAL
+_DIPY_B0_THRESHOLD = 50       # dipy.core.gradients.gradient_table default
+
+
+def dti_design_matrix(bvals, bvecs):
+    """dipy's ``design_matrix(gtab)`` (lower-triangular order Dxx, Dxy, Dyy, Dxz, Dyz, Dzz, dummy; negated)."""
+    bvals = np.asarray(bvals, dtype=np.float64)
+    g = np.array(bvecs, dtype=np.float64)
+    g[bvals <= _DIPY_B0_THRESHOLD] = 0.0
+    B = np.empty((len(bvals), 7))
+    B[:, 0] = g[:, 0] * g[:, 0] * bvals
+    B[:, 1] = g[:, 0] * g[:, 1] * 2.0 * bvals
+    B[:, 2] = g[:, 1] * g[:, 1] * bvals
+    B[:, 3] = g[:, 0] * g[:, 2] * 2.0 * bvals
+    B[:, 4] = g[:, 1] * g[:, 2] * 2.0 * bvals
+    B[:, 5] = g[:, 2] * g[:, 2] * bvals
+    B[:, 6] = 1.0
+    return -B
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Evaluation:
+    """GPU-resident counterpart of ``amico.core.Evaluation`` (``core.py:34-498``) for the load -> fit -> maps flow."""
+
+    def __init__(self, device=0):
+        self.device = int(device)
+        self.scheme = None
+        self.model = None
+        self.KERNELS = None
+        self.htable = None
+        self.RESULTS = None
+        self.mean_b0s = None
+        self.nthreads = None
+        self.niiMASK_img = None
+        self._y = self._vox_idx = self._dirs = None
+        self._dim = None
+        self.CONFIG = {}
+        # defaults of core.py:82-96
+        for k, v in (("peaks_filename", None), ("doNormalizeSignal", True), ("doKeepb0Intact", False), ("doComputeRMSE", False),
+                     ("doComputeNRMSE", False), ("doSaveModulatedMaps", False), ("doSaveCorrectedDWI", False),
+                     ("doMergeB0", False), ("doDebiasSignal", False), ("DWI-SNR", None), ("doDirectionalAverage", False),
+                     ("nthreads", -1), ("DTI_fit_method", "OLS"), ("BLAS_nthreads", 1), ("ndirs", 500)):
+            self.CONFIG[k] = v
+
+    def set_config(self, key, value):
+        self.CONFIG[key] = value
+
+    def get_config(self, key):
+        return self.CONFIG.get(key)
+
+    # ------------------------------------------------------------------ load_data (core.py:107-283)
+    def load_data(self, dwi, scheme, mask=None, b0_thr=0, b0_min_signal=0, replace_bad_voxels=None):
+        """``dwi``: (X, Y, Z, nS) array (numpy, or a CUDA float32 torch tensor); ``scheme``: a ``Scheme`` or an Nx4 / Nx7
+        table; ``mask``: (X, Y, Z) array or None.  Same pre-processing, same float32 arithmetic as the reference."""
+        import torch
+        lib = L.load()
+        if self.get_config("doDebiasSignal"):
+            raise NotImplementedError("doDebiasSignal (Rician debiasing, amico/core.py:201-207) is not part of the accelerated path")
+        self.scheme = scheme if isinstance(scheme, Scheme) else Scheme(np.asarray(scheme), b0_thr)
+        sch = self.scheme
+        dev = torch.device("cuda", self.device)
+        if isinstance(dwi, torch.Tensor):
+            vol = dwi.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            host = np.ascontiguousarray(dwi, dtype=np.float32)  # core.py:136
+            vol = torch.from_numpy(host).to(dev, non_blocking=False)
+        if vol.ndim != 4:
+            raise ValueError("DWI file is not a 4D image")
+        if sch.nS != vol.shape[3]:
+            raise ValueError("Scheme does not match with DWI data")
+        self._dim = tuple(int(s) for s in vol.shape[:3])
+        self.set_config("dim", self._dim)
+        n_total = int(np.prod(self._dim))
+        if mask is not None:
+            mask_img = np.asarray(mask).astype(np.uint8)  # core.py:181
+            if mask_img.ndim != 3:
+                raise ValueError("MASK file is not a 3D image")
+            if mask_img.shape != self._dim:
+                raise ValueError("MASK geometry does not match with DWI data")
+            n_kept = int(np.count_nonzero(mask_img == 1))
+            d_mask = torch.from_numpy(np.ascontiguousarray(mask_img).reshape(-1)).to(dev)
+        else:
+            mask_img = np.ones(self._dim)  # core.py:190
+            n_kept, d_mask = n_total, None
+        self.niiMASK_img = mask_img
+        flags = 0
+        if self.get_config("doNormalizeSignal"):
+            flags |= L.PRE_NORMALIZE
+        if self.get_config("doMergeB0"):
+            flags |= L.PRE_MERGE_B0
+        if self.get_config("doDirectionalAverage"):
+            flags |= L.PRE_DIR_AVG
+        if replace_bad_voxels is not None:
+            flags |= L.PRE_REPLACE_BAD
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        b0_idx, dwi_idx = _i32(sch.b0_idx), _i32(sch.dwi_idx)
+        want_b0 = bool(flags & L.PRE_NORMALIZE) and sch.b0_count > 0
+        thr = 0.0
+        if want_b0 and b0_min_signal != 0:
+            # threshold of core.py:216: needs the global mean of the positive b0 means -> one extra streaming pass
+            mb = torch.empty(n_total, dtype=torch.float32, device=dev)
+            L.check(lib.amx_mean_b0(L.SPACE_DEVICE, self.device, vol.data_ptr(), n_total, sch.nS, b0_idx.ctypes.data, len(b0_idx),
+                                    mb.data_ptr(), stream))
+            nf = mb.cpu().numpy()
+            with np.errstate(all="ignore"):
+                thr = float(np.float32(b0_min_signal * nf[nf > 0].mean()))
+        shells = sorted(sch.shells, key=lambda s: s["b"])  # np.argsort(bvals) order (core.py:245)
+        sh_idx = _i32(np.concatenate([s["idx"] for s in shells])) if shells else _i32([])
+        sh_off = _i32(np.concatenate([[0], np.cumsum([len(s["idx"]) for s in shells])])) if shells else _i32([0])
+        m_out = 1 + sch.dwi_count if flags & L.PRE_MERGE_B0 else 1 + len(shells) if flags & L.PRE_DIR_AVG else sch.nS
+        y = torch.empty((max(n_kept, 1), m_out), dtype=torch.float32, device=dev)
+        vox_idx = torch.empty(max(n_kept, 1), dtype=torch.int32, device=dev)
+        mean_b0s = torch.empty(n_total, dtype=torch.float32, device=dev) if want_b0 else None
+        a = L.PreArgs()
+        a.space, a.device, a.dwi, a.n_total, a.nS = L.SPACE_DEVICE, self.device, vol.data_ptr(), n_total, sch.nS
+        a.mask = d_mask.data_ptr() if d_mask is not None else None
+        a.b0_idx, a.b0_count, a.dwi_idx, a.dwi_count = b0_idx.ctypes.data, len(b0_idx), dwi_idx.ctypes.data, len(dwi_idx)
+        a.shell_idx, a.shell_off, a.n_shells = sh_idx.ctypes.data, sh_off.ctypes.data, len(shells)
+        a.flags, a.b0_threshold = flags, thr
+        a.replace_bad = float(replace_bad_voxels) if replace_bad_voxels is not None else 0.0
+        a.y, a.y_capacity, a.vox_idx = y.data_ptr(), n_kept, vox_idx.data_ptr()
+        a.mean_b0s = mean_b0s.data_ptr() if mean_b0s is not None else None
+        a.stream = stream
+        kept, mo = C.c_int64(0), C.c_int(0)
+        rc = lib.amx_preprocess(C.byref(a), C.byref(kept), C.byref(mo))
+        if rc == L.AMX_E_NONFINITE:
+            raise FloatingPointError(lib.amx_last_error().decode())
+        L.check(rc)
+        assert kept.value == n_kept and mo.value == m_out
+        self._y = y[:n_kept]
+        self._vox_idx = vox_idx[:n_kept]
+        self._mean_b0s_dev = mean_b0s
+        self.mean_b0s = None if mean_b0s is None else mean_b0s.cpu().numpy().reshape(self._dim)
+        self._dirs = None
+        self._fit_scheme = sch
+        if flags & L.PRE_DIR_AVG:
+            # the scheme the fit sees afterwards: one b0 + one row per shell (core.py:236-262)
+            tab = np.zeros((1 + len(shells), 7))
+            tab[0] = [1, 0, 0, 0, 0, 0, 0]
+            for i, s in enumerate(shells):
+                tab[i + 1] = [1, 0, 0, s["G"] or 0, s["Delta"] or 0, s["delta"] or 0, s["TE"] or 0]
+            self.scheme = Scheme(tab, b0_thr)
+        del vol
+        return self
+
+    # ------------------------------------------------------------------ model / kernels
+    def set_model(self, model_name):
+        """``core.py:286-296``: look the model class up by name."""
+        if not hasattr(_models, model_name):
+            raise ValueError(f'Model "{model_name}" not recognized')
+        self.model = getattr(_models, model_name)()
+        self.model.device = self.device
+        self.set_config("ATOMS_path", None)
+        return self.model
+
+    def set_solver(self, **params):
+        """``core.py:316-325``."""
+        if self.model is None:
+            raise RuntimeError('Model not set; call "set_model()" method first')
+        self.model.set_solver(**params)
+
+    def load_kernels(self, KERNELS, htable=None):
+        """Hand over the dictionary ``<Model>.resample`` built (``core.py:368-404``) and the direction hash table
+        (``amico/lut.pyx:71-91``)."""
+        if self.model is None:
+            raise RuntimeError('Model not set; call "set_model()" method first')
+        self.KERNELS = KERNELS
+        self.htable = htable
+        self.model.scheme = self._fit_scheme if not self.get_config("doDirectionalAverage") else self.scheme
+
+    # ------------------------------------------------------------------ fit (core.py:407-498)
+    @property
+    def y(self):
+        """``evaluation.y`` of the reference (n_vox, m) float64 -- downloaded on demand."""
+        return None if self._y is None else self._y.cpu().numpy().astype(np.float64)
+
+    @property
+    def DIRs(self):
+        return None if self._dirs is None else self._dirs.cpu().numpy()
+
+    def _dti_weights(self):
+        sch = self._fit_scheme
+        if self.get_config("doMergeB0"):  # core.py:432-433
+            bvals = np.hstack((0, sch.b[sch.dwi_idx]))
+            bvecs = np.vstack((np.zeros((1, 3)), sch.raw[sch.dwi_idx, :3]))
+        else:
+            bvals, bvecs = sch.b, sch.raw[:, :3]
+        W = np.linalg.pinv(dti_design_matrix(bvals, bvecs))
+        return np.ascontiguousarray(W[:6], dtype=np.float64)
+
+    def estimate_directions(self):
+        """Principal directions of every mask voxel (``core.py:456-458``) -> device tensor (n_vox, 3) float64."""
+        import torch
+        if self.get_config("DTI_fit_method") not in ("OLS", "LS"):
+            raise NotImplementedError("only the default DTI fit method 'OLS' ('LS') runs on the GPU")
+        n_vox, m = self._y.shape
+        dirs = torch.empty((n_vox, 3), dtype=torch.float64, device=self._y.device)
+        W = self._dti_weights()
+        stream = torch.cuda.current_stream(self._y.device).cuda_stream
+        L.check(L.load().amx_dti_directions(self.device, L.SPACE_DEVICE, self._y.data_ptr(), L.F32, n_vox, m, W.ctypes.data,
+                                            MIN_POSITIVE_SIGNAL, dirs.data_ptr(), stream))
+        torch.cuda.current_stream(self._y.device).synchronize()  # W is host memory read by an async copy
+        self._dirs = dirs
+        return dirs
+
+    def fit(self):
+        import torch
+        if self._y is None:
+            raise RuntimeError('Data not loaded; call "load_data()" first')
+        if self.model is None:
+            raise RuntimeError('Model not set; call "set_model()" first')
+        if self.KERNELS is None:
+            raise RuntimeError('Response functions not generated; call "generate_kernels()" and "load_kernels()" first')
+        if self.KERNELS["model"] != self.model.id:
+            raise RuntimeError("Response functions were not created with the same model")
+        dev = self._y.device
+        lib = L.load()
+        t = time.time()
+        if not self.get_config("doDirectionalAverage") and self.model.id != "SANDI":
+            self.estimate_directions()
+        torch.cuda.synchronize(dev)
+        self.set_config("dirs_precomputing_time", time.time() - t)
+        t = time.time()
+        if not hasattr(self.model, "solver_params"):
+            self.model.set_solver()
+        plan = self.model._get_plan(self)
+        cfg = self.get_config
+        extra = bool(cfg("doSaveModulatedMaps")) if self.model.id == "NODDI" else bool(cfg("doSaveCorrectedDWI")) if self.model.id == "FreeWater" else False
+        # the fit flips the directions in place to the y >= 0 hemisphere; RESULTS['DIRs'] holds the DTI output (core.py:477-478)
+        fit_dirs = None if self._dirs is None else self._dirs.clone()
+        res = plan.fit(self._y, fit_dirs, self.model.solver_params["lambda1"], self.model.solver_params["lambda2"],
+                       rmse=bool(cfg("doComputeRMSE")), nrmse=bool(cfg("doComputeNRMSE")), extra=extra)
+        torch.cuda.synchronize(dev)
+        self.set_config("fit_time", time.time() - t)
+        # ---- store results (core.py:469-498)
+        n_total = int(np.prod(self._dim))
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        n_vox = self._y.shape[0]
+
+        def scatter(values, k):
+            vol = torch.empty((n_total, k), dtype=torch.float32, device=dev)
+            L.check(lib.amx_scatter_maps(self.device, L.SPACE_DEVICE, values.data_ptr(), n_vox, k, self._vox_idx.data_ptr(),
+                                         vol.data_ptr(), n_total, stream))
+            return vol
+
+        out = {"MAPs": scatter(res["estimates"], len(self.model.maps_name))}
+        if self._dirs is not None:
+            out["DIRs"] = scatter(self._dirs, 3)
+        if "rmse" in res:
+            out["RMSE"] = scatter(res["rmse"], 1)
+        if "nrmse" in res:
+            out["NRMSE"] = scatter(res["nrmse"], 1)
+        if "estimates_mod" in res:
+            out["MAPs_mod"] = scatter(res["estimates_mod"], 2)
+        if "y_corrected" in res:
+            yc = res["y_corrected"]
+            sch = self._fit_scheme
+            if cfg("doNormalizeSignal") and sch.b0_count > 0:  # core.py:493-494
+                mb = self._mean_b0s_dev[self._vox_idx.long()].to(torch.float64).reshape(-1, 1)
+                yc = yc * mb
+                if cfg("doKeepb0Intact"):  # core.py:495-496
+                    b0 = torch.as_tensor(sch.b0_idx, device=dev)
+                    yc[:, b0] = self._y[:, b0].to(torch.float64) * mb
+            elif cfg("doKeepb0Intact") and sch.b0_count > 0:
+                raise NotImplementedError("doKeepb0Intact without doNormalizeSignal reads mean_b0s the reference never sets")
+            out["DWI_corrected"] = scatter(yc.contiguous(), yc.shape[1])
+        torch.cuda.synchronize(dev)
+        self.RESULTS = {}
+        for k, v in out.items():
+            a = v.cpu().numpy()
+            self.RESULTS[k] = a.reshape(self._dim + ((a.shape[1],) if k not in ("RMSE", "NRMSE") else ()))
+        self._last_fit = res
+        return self.RESULTS

@@ -32,7 +32,6 @@ import numpy as np
 from numpy.polynomial import legendre as npleg
 from scipy import optimize, special
 
-GAMMA = 2.675987e8  # proton gyromagnetic ratio [rad/(s T)]
 LMAX = 12
 
 CONFIGS = {
@@ -46,51 +45,7 @@ CONFIGS = {
 
 
 # --------------------------------------------------------------------------- scheme
-class Scheme:
-    """Acquisition scheme: Nx4 (dir, b) or Nx7 (dir, G, Delta, delta, TE) table.
-
-    Mirrors the attributes of ``amico/scheme.py:50-135`` consumed downstream.
-    """
-
-    def __init__(self, raw, b0_thr=0.0):
-        raw = np.array(raw, dtype=np.float64)
-        if raw.ndim != 2 or raw.shape[1] not in (4, 7):
-            raise ValueError("Unrecognized scheme format")
-        self.raw = raw
-        if raw.shape[1] == 4:
-            self.version = 0
-            self.b = raw[:, 3].copy()
-        else:
-            self.version = 1
-            self.b = (GAMMA * raw[:, 3] * raw[:, 5]) ** 2 * (raw[:, 4] - raw[:, 5] / 3.0) * 1e-6
-        self.b0_thr = b0_thr
-        self.b0_idx = np.where(self.b <= b0_thr)[0]
-        self.b0_count = len(self.b0_idx)
-        self.dwi_idx = np.where(self.b > b0_thr)[0]
-        self.dwi_count = len(self.dwi_idx)
-        flip = self.raw[:, 1] < 0
-        self.raw[flip, 0:3] *= -1.0
-        self.shells = []
-        par = np.ascontiguousarray(self.raw[:, 3:])
-        seen = []
-        for i in range(par.shape[0]):
-            if self.b[i] <= b0_thr:
-                continue
-            key = tuple(par[i])
-            if key in seen:
-                continue
-            seen.append(key)
-            idx = np.where((par == par[i]).all(axis=1))[0]
-            sh = {"b": self.b[i], "idx": idx, "grad": self.raw[idx, 0:3]}
-            if self.version == 1:
-                sh.update(G=par[i, 0], Delta=par[i, 1], delta=par[i, 2], TE=par[i, 3])
-            else:
-                sh.update(G=None, Delta=None, delta=None, TE=None)
-            self.shells.append(sh)
-
-    @property
-    def nS(self):
-        return self.b0_count + self.dwi_count
+from .scheme import GAMMA, Scheme  # noqa: E402,F401  (re-exported: tests and tools import it from here)
 
 
 def fibonacci_sphere(n, phase=0.0):
@@ -493,3 +448,38 @@ def make_problem(cfg, n_vox=None, ndirs=500, model=None, seed=None, snr=30.0):
         n_vox = int(np.prod(CONFIGS[cfg][1]))
     y, dirs = make_voxels(model, K, ht, n_vox, (20251017 + cfg) if seed is None else seed, snr=snr)
     return Problem(cfg, model, scheme, lut, ht, K, p, y, dirs)
+
+
+# --------------------------------------------------------------------------- raw volumes (pre-processing / DTI tests)
+def make_raw_volume(cfg, dims, seed=0, snr=30.0, mask_kind="ellipsoid", model=None, ndirs=500):
+    """A raw (un-normalised) float32 4-D volume of protocol ``cfg`` as ``Evaluation.load_data`` would read it.
+
+    Every voxel: S0 ~ U(400, 1600) times a single-fibre signal of the model's dictionary (direction uniform on the
+    sphere) with an isotropic fraction, Rician noise.  Returns (P, dwi (X, Y, Z, nS) float32, mask (X, Y, Z) uint8)
+    where ``P`` is the ``Problem`` carrying scheme / KERNELS / htable.  SANDI (cfg 4): the un-averaged 192-volume
+    protocol with an isotropic multi-exponential signal (the directional average is what is under test).
+    """
+    rng = np.random.default_rng(seed + 1000 * cfg)
+    n_tot = int(np.prod(dims))
+    mdl = model or CONFIGS[cfg][0]
+    P = make_problem(cfg, n_vox=n_tot, ndirs=ndirs, model=mdl, seed=seed + 77, snr=snr)
+    if mdl == "SANDI":
+        full = make_scheme(cfg)
+        b = full.b * 1e-3
+        d = rng.uniform(0.3, 2.5, (n_tot, 1))
+        f = rng.uniform(0.2, 0.8, (n_tot, 1))
+        sig = f * np.exp(-b[None, :] * d) + (1 - f) * np.exp(-b[None, :] * 0.2 * d)
+        sigma = 1.0 / snr
+        sig = np.sqrt((sig + sigma * rng.standard_normal(sig.shape)) ** 2 + (sigma * rng.standard_normal(sig.shape)) ** 2)
+        P.full_scheme = full
+    else:
+        sig = P.y.astype(np.float64)
+        P.full_scheme = P.scheme
+    s0 = rng.uniform(400.0, 1600.0, (n_tot, 1))
+    dwi = (sig * s0).astype(np.float32).reshape(tuple(dims) + (sig.shape[1],))
+    if mask_kind == "ones":
+        mask = np.ones(dims, dtype=np.uint8)
+    else:
+        g = np.meshgrid(*[np.linspace(-1, 1, d) for d in dims], indexing="ij")
+        mask = ((g[0] ** 2 + g[1] ** 2 + g[2] ** 2) <= 0.9).astype(np.uint8)
+    return P, dwi, mask

@@ -145,6 +145,71 @@ int amx_plan_last_timing(amx_plan *plan, double *out_ms, int n);
  * larger than a warp), out[7] = grid size. */
 int amx_plan_last_counters(amx_plan *plan, int64_t *out, int n);
 
+/* =====================================================================================================
+ * The callers either side of model.fit(): what
+ * amico.Evaluation.load_data() / fit() do around the per-voxel solve, on the GPU, so that a raw 4-D
+ * volume can stay in HBM from load to maps.  These entry points do not need a plan.
+ * ===================================================================================================== */
+
+#define AMX_E_NONFINITE (-5) /* NaN / Inf in the signal and no replacement value given: the reference stops with
+                                ERROR('Nan or Inf values in the raw signal ...'), amico/core.py:151-156, 273-278 */
+
+#define AMX_PRE_NORMALIZE 1u   /* doNormalizeSignal: divide by the voxel's mean b0 (amico/core.py:209-222) */
+#define AMX_PRE_MERGE_B0 2u    /* doMergeB0: [mean of the b0 volumes | dwi volumes] (amico/core.py:224-227) */
+#define AMX_PRE_DIR_AVG 4u     /* doDirectionalAverage: [mean b0 | mean of each shell, ascending b] (amico/core.py:231-266) */
+#define AMX_PRE_REPLACE_BAD 8u /* replace_bad_voxels given: NaN / +-Inf -> replace_bad (np.nan_to_num, core.py:153, :275) */
+
+typedef struct amx_pre_args {
+    int space;          /* AMX_SPACE_HOST | AMX_SPACE_DEVICE for dwi, mask, y, vox_idx, mean_b0s */
+    int device;
+    const float *dwi;   /* [n_total][nS] niiDWI_img (float32, amico/core.py:136), voxel-major C order */
+    int64_t n_total;    /* voxels in the volume */
+    int nS;             /* volumes = scheme.nS */
+    const uint8_t *mask; /* [n_total] niiMASK_img, or NULL (= all ones); voxels with mask == 1 are kept, in C-order
+                            scan order, exactly like `niiDWI_img[niiMASK_img==1, :]` (amico/core.py:451) */
+    /* scheme index lists: HOST pointers in either space (they are tiny) */
+    const int32_t *b0_idx;  int b0_count;   /* scheme.b0_idx */
+    const int32_t *dwi_idx; int dwi_count;  /* scheme.dwi_idx */
+    const int32_t *shell_idx;               /* AMX_PRE_DIR_AVG: the shells' 'idx' lists concatenated in ascending-b order */
+    const int32_t *shell_off;               /* [n_shells + 1] offsets into shell_idx */
+    int n_shells;
+    uint32_t flags;       /* AMX_PRE_* */
+    float b0_threshold;   /* voxels whose mean b0 <= this get norm factor 0; the reference's value is
+                             b0_min_signal * mean(mean_b0s[mean_b0s > 0]) (amico/core.py:216), 0 by default */
+    float replace_bad;    /* AMX_PRE_REPLACE_BAD */
+    /* outputs */
+    float *y;             /* [n_kept][m_out] pre-processed signal of the kept voxels, negative values set to 0
+                             (amico/core.py:452); float32 holds it exactly: the reference's volume is float32 */
+    int64_t y_capacity;   /* rows y can hold (>= number of mask==1 voxels) */
+    int32_t *vox_idx;     /* [n_kept] flat index of each kept voxel (ascending) */
+    float *mean_b0s;      /* optional [n_total]: mean of the raw b0 volumes (evaluation.mean_b0s, core.py:212) */
+    void *stream;         /* AMX_SPACE_DEVICE: cudaStream_t to enqueue on (NULL = legacy default stream) */
+} amx_pre_args;
+
+/* Pre-process a raw volume and compact the mask voxels.  m_out = nS, 1 + dwi_count (MERGE_B0) or 1 + n_shells
+ * (DIR_AVG).  Arithmetic is the reference's float32 arithmetic operation for operation (numpy sums the indexed
+ * volumes sequentially in index order, then divides by the count), so y is bit-identical to
+ * `niiDWI_img[niiMASK_img==1, :]` after load_data().  Returns after the kept-voxel count has been read back. */
+int amx_preprocess(const amx_pre_args *args, int64_t *n_kept, int *m_out);
+
+/* Mean of the raw b0 volumes for every voxel (first half of doNormalizeSignal): lets the caller form
+ * b0_threshold when b0_min_signal != 0.  mean_b0s: [n_total] float32 in `space`. */
+int amx_mean_b0(int space, int device, const float *dwi, int64_t n_total, int nS, const int32_t *b0_idx, int b0_count,
+                float *mean_b0s, void *stream);
+
+/* Principal diffusion direction of every voxel = what `dipy.reconst.dti.TensorModel(gtab, fit_method='OLS')
+ * .fit(y).directions` yields at amico/core.py:436, 458: D = W log(max(y, min_signal)), eigen-decomposition of the
+ * symmetric 3x3 tensor, eigenvector of the largest eigenvalue (unit length; its SIGN is arbitrary, as it is with
+ * LAPACK, and irrelevant downstream: amico/lut.pyx:335-338 flips to the y >= 0 hemisphere).
+ * W: HOST float64 [6][m], the rows Dxx, Dxy, Dyy, Dxz, Dyz, Dzz of pinv(design matrix); dirs: out [n_vox][3] float64. */
+int amx_dti_directions(int device, int space, const void *y, int y_dtype, int64_t n_vox, int m, const double *W,
+                       double min_signal, double *dirs, void *stream);
+
+/* RESULTS['MAPs'][mask==1, :] = estimates (amico/core.py:472-498): zero-fill volume [n_total][k] (float32) and
+ * scatter the float64 rows values[i][0..k) to voxel vox_idx[i]. */
+int amx_scatter_maps(int device, int space, const double *values, int64_t n_vox, int k, const int32_t *vox_idx,
+                     float *volume, int64_t n_total, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,125 @@
+"""CPU oracle of what ``amico.Evaluation`` does either side of ``model.fit()``.
+
+TEST INFRASTRUCTURE ONLY (same rule as ``oracle/oracle.py``): imported by ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU legs, never by the ``amico_b200`` package.
+
+* ``preprocess``      restates ``Evaluation.load_data`` (amico/core.py:151-156, 209-278) and the ``y`` extraction of
+                      ``Evaluation.fit`` (amico/core.py:451-452) with the very same numpy statements, so float32 rounding,
+                      summation order and the in-place aliasing of the directional average are numpy's own.
+* ``dti_directions``  restates what amico/core.py:430-436, 456-458 obtains from dipy (absent here, un-vendored:
+                      ``dipy>=1.4.1`` in the reference's pyproject.toml): ``TensorModel(gtab, fit_method='OLS').fit(y)
+                      .directions`` = design matrix (dipy/reconst/dti.py ``design_matrix``), ``log(max(y, 1e-4))``
+                      (``MIN_POSITIVE_SIGNAL``), ``pinv`` least squares (``ols_fit_tensor``), ``eigh`` and the eigenvector
+                      of the largest eigenvalue (``decompose_tensor``).  PARITY UNPINNED: written from dipy's published
+                      algorithm, not checked against dipy itself.
+* ``scatter_maps``    amico/core.py:472-475.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+MIN_POSITIVE_SIGNAL = 0.0001  # dipy.reconst.dti.MIN_POSITIVE_SIGNAL
+B0_THRESHOLD_DIPY = 50        # dipy.core.gradients.gradient_table default b0_threshold
+
+
+def preprocess(dwi, scheme, mask=None, *, b0_min_signal=0.0, replace_bad_voxels=None, doNormalizeSignal=True,
+               doMergeB0=False, doDirectionalAverage=False):
+    """``load_data`` pre-processing + ``y`` extraction.  ``dwi``: (X, Y, Z, nS) array-like.
+
+    Returns dict(y=(n_kept, m) float64 >= 0, vox_idx=flat indices of the kept voxels, mean_b0s=(X, Y, Z) float32 or None,
+    img=the pre-processed float32 volume, b0_threshold=the float32 threshold used).
+    """
+    img = np.array(dwi, dtype=np.float32)  # core.py:136 (.astype(np.float32)); a copy: everything below is in place
+    if img.ndim != 4:
+        raise ValueError("DWI file is not a 4D image")
+    if np.isnan(img).any() or np.isinf(img).any():  # core.py:151-156
+        if replace_bad_voxels is not None:
+            np.nan_to_num(img, copy=False, nan=replace_bad_voxels, posinf=replace_bad_voxels, neginf=replace_bad_voxels)
+        else:
+            raise FloatingPointError("Nan or Inf values in the raw signal")
+    if mask is None:
+        mask_img = np.ones(img.shape[:3])  # core.py:190
+    else:
+        mask_img = np.asarray(mask).astype(np.uint8)  # core.py:181
+    mean_b0s = None
+    thr = np.float32(0)
+    if doNormalizeSignal:  # core.py:209-222
+        if scheme.b0_count <= 0:
+            raise ValueError("No b0 volume to normalize signal with")
+        mean_b0s = np.mean(img[:, :, :, scheme.b0_idx], axis=3)
+        norm_factor = mean_b0s.copy()
+        with np.errstate(all="ignore"):
+            thr = np.float32(b0_min_signal * norm_factor[norm_factor > 0].mean())  # core.py:216
+            idx = norm_factor <= thr
+            norm_factor[idx] = 1
+            norm_factor = 1 / norm_factor
+            norm_factor[idx] = 0
+            for i in range(scheme.nS):
+                img[:, :, :, i] *= norm_factor
+    if doMergeB0:  # core.py:224-227
+        mean = np.expand_dims(np.mean(img[:, :, :, scheme.b0_idx], axis=3), axis=3)
+        img = np.concatenate((mean, img[:, :, :, scheme.dwi_idx]), axis=3)
+    if doDirectionalAverage:  # core.py:231-254
+        num_shells = len(scheme.shells)
+        dir_avg_img = img[:, :, :, :(num_shells + 1)]  # a VIEW, as in the reference
+        id_bval = 0
+        dir_avg_img[:, :, :, id_bval] = np.mean(img[:, :, :, scheme.b0_idx], axis=3)
+        bvals = [shell["b"] for shell in scheme.shells]
+        for shell_idx in np.argsort(bvals):
+            shell = scheme.shells[shell_idx]
+            id_bval += 1
+            dir_avg_img[:, :, :, id_bval] = np.mean(img[:, :, :, shell["idx"]], axis=3)
+        img = dir_avg_img.astype(np.float32)
+    if np.isnan(img).any() or np.isinf(img).any():  # core.py:273-278
+        if replace_bad_voxels is not None:
+            np.nan_to_num(img, copy=False, nan=replace_bad_voxels, posinf=replace_bad_voxels, neginf=replace_bad_voxels)
+        else:
+            raise FloatingPointError("Nan or Inf values in the signal after the pre-processing")
+    y = img[mask_img == 1, :].astype(np.double)  # core.py:451
+    y[y < 0] = 0  # core.py:452
+    vox_idx = np.flatnonzero(mask_img.reshape(-1) == 1)
+    return {"y": y, "vox_idx": vox_idx, "mean_b0s": mean_b0s, "img": img, "b0_threshold": thr}
+
+
+def dti_design_matrix(bvals, bvecs):
+    """dipy ``design_matrix(gtab)``: columns Dxx, Dxy, Dyy, Dxz, Dyz, Dzz, dummy (lower-triangular order), negated."""
+    bvals = np.asarray(bvals, dtype=np.float64)
+    bvecs = np.array(bvecs, dtype=np.float64)
+    bvecs[bvals <= B0_THRESHOLD_DIPY] = 0.0  # gradient_table zeroes the b0 directions
+    B = np.zeros((len(bvals), 7))
+    B[:, 0] = bvecs[:, 0] * bvecs[:, 0] * 1.0 * bvals
+    B[:, 1] = bvecs[:, 0] * bvecs[:, 1] * 2.0 * bvals
+    B[:, 2] = bvecs[:, 1] * bvecs[:, 1] * 1.0 * bvals
+    B[:, 3] = bvecs[:, 0] * bvecs[:, 2] * 2.0 * bvals
+    B[:, 4] = bvecs[:, 1] * bvecs[:, 2] * 2.0 * bvals
+    B[:, 5] = bvecs[:, 2] * bvecs[:, 2] * 1.0 * bvals
+    B[:, 6] = np.ones(len(bvals))
+    return -B
+
+
+def scheme_gradients(scheme, doMergeB0=False):
+    """(bvals, bvecs) exactly as amico/core.py:432-435 hands them to ``gradient_table``."""
+    if doMergeB0:
+        return (np.hstack((0, scheme.b[scheme.dwi_idx])), np.vstack((np.zeros((1, 3)), scheme.raw[scheme.dwi_idx, :3])))
+    return scheme.b, scheme.raw[:, :3]
+
+
+def dti_directions(y, scheme, doMergeB0=False):
+    """Principal eigenvector of the OLS tensor fit per voxel: (n_vox, 3) float64 (sign arbitrary)."""
+    bvals, bvecs = scheme_gradients(scheme, doMergeB0)
+    W = np.linalg.pinv(dti_design_matrix(bvals, bvecs))
+    data = np.maximum(np.asarray(y, dtype=np.float64), MIN_POSITIVE_SIGNAL)
+    D = np.einsum("ij,nj->ni", W, np.log(data))
+    T = np.empty((len(D), 3, 3))
+    T[:, 0, 0], T[:, 0, 1], T[:, 1, 1], T[:, 0, 2], T[:, 1, 2], T[:, 2, 2] = (D[:, k] for k in range(6))
+    T[:, 1, 0], T[:, 2, 0], T[:, 2, 1] = T[:, 0, 1], T[:, 0, 2], T[:, 1, 2]
+    _, evecs = np.linalg.eigh(T)  # ascending eigenvalues: the principal direction is the last column
+    return np.ascontiguousarray(evecs[:, :, 2])
+
+
+def scatter_maps(values, vox_idx, n_total):
+    """``RESULTS['MAPs'][mask==1, :] = estimates`` into a zero float32 volume (core.py:474-475); flat (n_total, k)."""
+    values = np.asarray(values)
+    vol = np.zeros((n_total, values.shape[1]), dtype=np.float32)
+    vol[np.asarray(vox_idx)] = values
+    return vol

@@ -1,0 +1,235 @@
+"""GPU parity of the callers either side of the fit against oracle/pipeline.py.
+
+Bars: pre-processing (float32 arithmetic, integer compaction) and the result scatter BIT-EXACT; DTI principal directions
+(float64, sign-free) within 1e-9 and LUT-index equality >= 99.9 % (a 1-degree LUT cell can flip on a 1e-15 difference);
+the whole load -> directions -> fit -> maps flow within the fit's own tolerance.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from amico_b200 import _lib as L
+from amico_b200 import synth
+from amico_b200.evaluation import Evaluation, dti_design_matrix
+
+pytestmark = pytest.mark.gpu
+
+
+def opl():
+    from oracle import pipeline
+    return pipeline
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def gpu_preprocess(dwi, sch, mask, *, normalize=True, merge=False, diravg=False, thr=0.0, replace=None, want_b0=True):
+    """Host-space amx_preprocess call (the library stages the copies)."""
+    lib = L.load()
+    dims = dwi.shape[:3]
+    n_total = int(np.prod(dims))
+    flat = np.ascontiguousarray(dwi.reshape(n_total, -1), dtype=np.float32)
+    shells = sorted(sch.shells, key=lambda s: s["b"])
+    sh_idx = _i32(np.concatenate([s["idx"] for s in shells]))
+    sh_off = _i32(np.concatenate([[0], np.cumsum([len(s["idx"]) for s in shells])]))
+    flags = (L.PRE_NORMALIZE if normalize else 0) | (L.PRE_MERGE_B0 if merge else 0) | (L.PRE_DIR_AVG if diravg else 0) \
+        | (L.PRE_REPLACE_BAD if replace is not None else 0)
+    m_out = 1 + sch.dwi_count if merge else 1 + len(shells) if diravg else sch.nS
+    m8 = None if mask is None else np.ascontiguousarray(np.asarray(mask).astype(np.uint8).reshape(-1))
+    cap = n_total if m8 is None else int((m8 == 1).sum())
+    y = np.full((max(cap, 1), m_out), -7.0, dtype=np.float32)
+    vidx = np.full(max(cap, 1), -1, dtype=np.int32)
+    mb = np.zeros(n_total, dtype=np.float32) if want_b0 else None
+    b0, dw = _i32(sch.b0_idx), _i32(sch.dwi_idx)
+    a = L.PreArgs()
+    a.space, a.device, a.dwi, a.n_total, a.nS = L.SPACE_HOST, 0, flat.ctypes.data, n_total, sch.nS
+    a.mask = None if m8 is None else m8.ctypes.data
+    a.b0_idx, a.b0_count, a.dwi_idx, a.dwi_count = b0.ctypes.data, len(b0), dw.ctypes.data, len(dw)
+    a.shell_idx, a.shell_off, a.n_shells = sh_idx.ctypes.data, sh_off.ctypes.data, len(shells)
+    a.flags, a.b0_threshold, a.replace_bad = flags, thr, 0.0 if replace is None else replace
+    a.y, a.y_capacity, a.vox_idx = y.ctypes.data, cap, vidx.ctypes.data
+    a.mean_b0s = None if mb is None else mb.ctypes.data
+    kept, mo = C.c_int64(-1), C.c_int(-1)
+    rc = lib.amx_preprocess(C.byref(a), C.byref(kept), C.byref(mo))
+    return rc, y[:max(kept.value, 0)], vidx[:max(kept.value, 0)], mb, kept.value, mo.value
+
+
+@pytest.mark.parametrize("cfg,dims,kw", [
+    (1, (8, 8, 8), {}),
+    (2, (7, 5, 9), {}),                       # n_total not a multiple of 32
+    (2, (7, 5, 9), {"merge": True}),
+    (2, (16, 16, 6), {"normalize": False}),
+    (5, (6, 6, 5), {"merge": True}),
+    (4, (9, 7, 6), {"diravg": True}),
+    (4, (9, 7, 6), {"diravg": True, "normalize": False}),
+])
+@pytest.mark.parametrize("mask_kind", ["ellipsoid", "ones", "none"])
+def test_preprocess_bit_exact(cfg, dims, kw, mask_kind):
+    P, dwi, mask = synth.make_raw_volume(cfg, dims, seed=cfg, mask_kind="ones" if mask_kind == "none" else mask_kind)
+    if mask_kind == "none":
+        mask = None
+    sch = P.full_scheme
+    ref = opl().preprocess(dwi, sch, mask, doNormalizeSignal=kw.get("normalize", True), doMergeB0=kw.get("merge", False),
+                           doDirectionalAverage=kw.get("diravg", False))
+    rc, y, vidx, mb, kept, m_out = gpu_preprocess(dwi, sch, mask, **kw)
+    assert rc == 0, L.load().amx_last_error()
+    assert kept == len(ref["vox_idx"]) and m_out == ref["y"].shape[1]
+    np.testing.assert_array_equal(vidx, ref["vox_idx"])
+    np.testing.assert_array_equal(y.astype(np.float64), ref["y"])
+    if ref["mean_b0s"] is not None:
+        np.testing.assert_array_equal(mb, ref["mean_b0s"].ravel())
+
+
+def test_preprocess_mask_values_and_empty():
+    P, dwi, mask = synth.make_raw_volume(1, (5, 4, 3), seed=3)
+    sch = P.full_scheme
+    m = (np.arange(60).reshape(5, 4, 3) % 4).astype(np.uint8)  # values 0..3: only == 1 is kept (core.py:451)
+    ref = opl().preprocess(dwi, sch, m)
+    rc, y, vidx, _, kept, _ = gpu_preprocess(dwi, sch, m)
+    assert rc == 0 and kept == 15
+    np.testing.assert_array_equal(vidx, ref["vox_idx"])
+    np.testing.assert_array_equal(y.astype(np.float64), ref["y"])
+    rc, y, vidx, _, kept, _ = gpu_preprocess(dwi, sch, np.zeros((5, 4, 3), np.uint8))
+    assert rc == 0 and kept == 0
+
+
+def test_preprocess_b0_threshold_and_zero_b0():
+    P, dwi, mask = synth.make_raw_volume(2, (6, 6, 6), seed=5)
+    sch = P.full_scheme
+    dwi = dwi.copy()
+    dwi[0, 0, :3] = 0.0                      # dead voxels: mean b0 = 0 -> norm factor 0, not Inf
+    dwi[1, 1, 1, sch.b0_idx] *= 1e-3         # weak b0: cropped by b0_min_signal
+    ref = opl().preprocess(dwi, sch, mask * 0 + 1, b0_min_signal=0.05)
+    rc, y, vidx, mb, kept, _ = gpu_preprocess(dwi, sch, mask * 0 + 1, thr=float(ref["b0_threshold"]))
+    assert rc == 0
+    np.testing.assert_array_equal(y.astype(np.float64), ref["y"])
+    assert (y[:3] == 0).all() and (y[1 * 36 + 1 * 6 + 1] == 0).all()
+    # amx_mean_b0 = first half of the normalisation, lets the host form the threshold exactly like core.py:216
+    lib = L.load()
+    flat = np.ascontiguousarray(dwi.reshape(-1, sch.nS))
+    out = np.zeros(len(flat), np.float32)
+    b0 = _i32(sch.b0_idx)
+    assert lib.amx_mean_b0(L.SPACE_HOST, 0, flat.ctypes.data, len(flat), sch.nS, b0.ctypes.data, len(b0), out.ctypes.data, None) == 0
+    np.testing.assert_array_equal(out, ref["mean_b0s"].ravel())
+    thr = np.float32(0.05 * out[out > 0].mean())
+    assert thr == ref["b0_threshold"]
+
+
+def test_preprocess_nonfinite_policy():
+    P, dwi, mask = synth.make_raw_volume(1, (4, 4, 4), seed=9)
+    sch = P.full_scheme
+    bad = dwi.copy()
+    bad[1, 2, 3, 5] = np.nan
+    bad[0, 0, 1, 2] = np.inf
+    rc, *_ = gpu_preprocess(bad, sch, mask)
+    assert rc == L.AMX_E_NONFINITE and b"Nan or Inf values in the raw signal" in L.load().amx_last_error()
+    ref = opl().preprocess(bad, sch, mask * 0 + 1, replace_bad_voxels=0.0)
+    rc, y, vidx, _, kept, _ = gpu_preprocess(bad, sch, mask * 0 + 1, replace=0.0)
+    assert rc == 0
+    np.testing.assert_array_equal(y.astype(np.float64), ref["y"])
+
+
+def test_preprocess_argument_errors():
+    P, dwi, mask = synth.make_raw_volume(1, (4, 4, 4), seed=9)
+    rc, *_ = gpu_preprocess(dwi, P.full_scheme, mask, merge=True, diravg=True)
+    assert rc == L.AMX_E_INVALID
+
+
+# ----------------------------------------------------------------------------------------------- DTI directions
+def gpu_dti(y, sch, merged=False):
+    lib = L.load()
+    bvals, bvecs = opl().scheme_gradients(sch, merged)
+    W = np.ascontiguousarray(np.linalg.pinv(dti_design_matrix(bvals, bvecs))[:6])
+    y = np.ascontiguousarray(y)
+    dirs = np.zeros((len(y), 3))
+    rc = lib.amx_dti_directions(0, L.SPACE_HOST, y.ctypes.data, L.F64 if y.dtype == np.float64 else L.F32, len(y), y.shape[1],
+                                W.ctypes.data, 1e-4, dirs.ctypes.data, None)
+    assert rc == 0, lib.amx_last_error()
+    return dirs
+
+
+@pytest.mark.parametrize("cfg,n,dtype", [(2, 20000, np.float32), (1, 777, np.float64), (5, 3000, np.float32)])
+def test_dti_directions_match_oracle(cfg, n, dtype):
+    P = synth.make_problem(cfg, n_vox=n)
+    y = P.y.astype(dtype)
+    ref = opl().dti_directions(y, P.scheme)
+    got = gpu_dti(y, P.scheme)
+    np.testing.assert_allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-12)
+    dev = 1.0 - np.abs((got * ref).sum(1))
+    assert np.percentile(dev, 99) < 1e-12 and dev.max() < 1e-9, (np.percentile(dev, 99), dev.max())
+    ht = P.htable
+    a = synth.lut_index_numpy(got.copy(), ht)
+    b = synth.lut_index_numpy(ref.copy(), ht)
+    assert (a == b).mean() >= 0.999
+
+
+def test_dti_degenerate_inputs_are_finite():
+    sch = synth.make_scheme(2)
+    y = np.zeros((40, sch.nS), np.float32)
+    y[20:] = 1.0
+    d = gpu_dti(y, sch)
+    assert np.isfinite(d).all()
+    np.testing.assert_allclose(np.linalg.norm(d, axis=1), 1.0, atol=1e-12)
+
+
+# ----------------------------------------------------------------------------------------------- result scatter
+def test_scatter_maps_bit_exact():
+    lib = L.load()
+    rng = np.random.default_rng(1)
+    n_total, n_vox, k = 5000, 1234, 3
+    idx = _i32(np.sort(rng.choice(n_total, n_vox, replace=False)))
+    vals = rng.standard_normal((n_vox, k))
+    vol = np.full((n_total, k), 9.0, dtype=np.float32)
+    assert lib.amx_scatter_maps(0, L.SPACE_HOST, vals.ctypes.data, n_vox, k, idx.ctypes.data, vol.ctypes.data, n_total, None) == 0
+    np.testing.assert_array_equal(vol, opl().scatter_maps(vals, idx, n_total))
+
+
+# ----------------------------------------------------------------------------------------------- whole flow
+def _oracle_flow(P, dwi, mask, model, **pre):
+    from oracle import oracle as orc
+    r = opl().preprocess(dwi, P.full_scheme, mask, **pre)
+    dirs = opl().dti_directions(r["y"], P.full_scheme) if model != "SANDI" else None
+    l1, l2 = orc.DEFAULT_LAMBDAS[model]
+    fit = orc.fit(model, r["y"], None if dirs is None else dirs.copy(), P.htable, P.KERNELS, P.params, l1, l2,
+                  dwi_idx=P.scheme.dwi_idx)
+    n_total = int(np.prod(dwi.shape[:3]))
+    return r, dirs, opl().scatter_maps(fit["estimates"], r["vox_idx"], n_total).reshape(dwi.shape[:3] + (-1,))
+
+
+@pytest.mark.parametrize("cfg,model,dims", [(1, "FreeWater", (8, 8, 8)), (2, "NODDI", (12, 12, 10)), (5, "CylinderZeppelinBall", (8, 8, 6))])
+def test_evaluation_flow_matches_oracle(cfg, model, dims):
+    P, dwi, mask = synth.make_raw_volume(cfg, dims, seed=11)
+    r, dirs, maps_ref = _oracle_flow(P, dwi, mask, model)
+    ae = Evaluation()
+    ae.load_data(dwi, P.full_scheme, mask)
+    ae.set_model(model)
+    ae.load_kernels(P.KERNELS, P.htable)
+    res = ae.fit()
+    np.testing.assert_array_equal(ae.y, r["y"])
+    d = ae.DIRs
+    assert (1.0 - np.abs((d * dirs).sum(1))).max() < 1e-9
+    maps = res["MAPs"]
+    assert maps.dtype == np.float32 and maps.shape == maps_ref.shape
+    assert (maps[mask != 1] == 0).all()
+    rel = np.abs(maps - maps_ref) / np.maximum(np.abs(maps_ref), 1e-3)
+    frac = float((rel[mask == 1] <= 1e-4).all(axis=1).mean())
+    # the direction's LUT cell can differ for a voxel whose angle sits on a 1-degree boundary
+    assert frac >= 0.995, frac
+    assert res["DIRs"].shape == dims + (3,)
+    assert ae.get_config("fit_time") > 0
+
+
+def test_evaluation_flow_sandi_directional_average():
+    P, dwi, mask = synth.make_raw_volume(4, (8, 7, 6), seed=2)
+    r, _, maps_ref = _oracle_flow(P, dwi, mask, "SANDI", doDirectionalAverage=True)
+    ae = Evaluation()
+    ae.set_config("doDirectionalAverage", True)
+    ae.load_data(dwi, P.full_scheme, mask)
+    ae.set_model("SANDI")
+    ae.load_kernels(P.KERNELS)
+    res = ae.fit()
+    np.testing.assert_array_equal(ae.y, r["y"])
+    assert ae.scheme.nS == 4
+    np.testing.assert_array_equal(res["MAPs"], maps_ref)   # SANDI is bit-exact (float32 cast of equal float64 maps)
