@@ -149,85 +149,167 @@ __device__ __forceinline__ float seq_mean(int n, F get)
     return __fdiv_rn(s, (float)n);
 }
 
-// One warp per chunk of 32 voxels.
-__global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long n_chunks)
+// ---- mbarrier + 1-D bulk (TMA) copy, as in amx_warp.cuh ------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t *bar, int count)
 {
-    extern __shared__ __align__(16) float smem[];
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "PRE_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra PRE_DONE;\n"
+        "bra PRE_WAIT;\n"
+        "PRE_DONE:\n"
+        "}\n" ::"r"(s_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(s_u32(bar))
+                 : "memory");
+}
+
+// bytes of shared memory one warp of k_preprocess needs
+__host__ __device__ inline size_t pre_warp_bytes(int nS, int m_out, bool diravg)
+{
+    size_t b = 2 * (size_t)CH * nS * sizeof(float);                 // two raw chunk buffers (TMA destinations)
+    b += 2 * CH * sizeof(float);                                     // norm factor, merged b0
+    if (diravg) b += (size_t)CH * ((nS | 1) + m_out) * sizeof(float);  // padded copy for the lane-per-voxel sums + averages
+    return (b + 127) & ~(size_t)127;
+}
+
+// One warp per chunk of 32 consecutive voxels = one contiguous block of 32 * nS floats.  Full chunks arrive by ONE bulk
+// (TMA) copy each, double buffered: the copy of the warp's next chunk is in flight while it works on the current one.
+//   pass 1 (cooperative): NaN / Inf policy on the raw values (core.py:151-156)
+//   pass 2 (lane v = voxel v): mean b0, norm factor (core.py:212-219); merged b0 / shell averages when asked
+//   pass 3 (cooperative): y rows of the kept voxels, normalised, clamped at 0, written fully coalesced
+__global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long n_chunks, unsigned warp_bytes)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint64_t bars[4][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const int nS = p.nS, stride = p.stride, m_out = p.m_out;
-    float *rows = smem + (size_t)warp * (CH * stride + CH);
-    float *nfs = rows + CH * stride;  // per-voxel norm factor
+    const int nS = p.nS, m_out = p.m_out;
+    const bool norm = p.flags & AMX_PRE_NORMALIZE, merge = p.flags & AMX_PRE_MERGE_B0, diravg = p.flags & AMX_PRE_DIR_AVG;
     const bool replace = p.flags & AMX_PRE_REPLACE_BAD;
+    float *buf0 = reinterpret_cast<float *>(smem_raw + (size_t)warp * warp_bytes);
+    float *nfs = buf0 + 2 * CH * nS, *mb0s = nfs + CH;
+    const int pstride = nS | 1;
+    float *pad = mb0s + CH, *avg = pad + CH * pstride;  // diravg only
+    uint64_t *bar = bars[warp];
+    if (lane == 0) {
+        mb_init(&bar[0], 1);
+        mb_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const long long step = (long long)gridDim.x * wpb;
+    const uint32_t chunk_bytes = (uint32_t)(CH * nS * sizeof(float));
     unsigned st = 0;
-    for (long long c = (long long)blockIdx.x * wpb + warp; c < n_chunks; c += (long long)gridDim.x * wpb) {
+    long long c = (long long)blockIdx.x * wpb + warp;
+    auto load = [&](long long cc, int b) {  // all lanes call; full chunks: one TMA copy, the partial last chunk: plain loads
+        const long long v0 = cc * CH;
+        const int nvox = (int)min((long long)CH, p.n_total - v0);
+        float *dst = buf0 + (size_t)b * CH * nS;
+        if (nvox == CH) {
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // our earlier generic accesses to dst come first
+                mb_expect_tx(&bar[b], chunk_bytes);
+                tma_g2s(dst, p.dwi + v0 * nS, chunk_bytes, &bar[b]);
+            }
+        } else {
+            const float *src = p.dwi + v0 * nS;
+            for (int e = lane; e < nvox * nS; e += 32) dst[e] = __ldcs(src + e);
+        }
+    };
+    if (c < n_chunks) load(c, 0);
+    for (int it = 0; c < n_chunks; c += step, ++it) {
+        const int b = it & 1;
         const long long v0 = c * CH;
         const int nvox = (int)min((long long)CH, p.n_total - v0);
-        if (stage_rows(rows, p.dwi + v0 * nS, nvox * nS, nS, stride, lane, replace, p.repl)) st |= 1u;
         __syncwarp();
-        // ---- lane v: the voxel's short sequential arithmetic
-        const bool have = lane < nvox;
-        float *r = rows + lane * stride;
-        bool keep = false;
-        if (have) {
-            keep = p.mask ? (p.mask[v0 + lane] == 1) : true;
-            float nf = 1.0f;
-            if (p.b0_count > 0 && ((p.flags & AMX_PRE_NORMALIZE) || p.mean_b0s)) {
-                const float mb = seq_mean(p.b0_count, [&](int i) { return r[p.b0_idx[i]]; });
-                if (p.mean_b0s) p.mean_b0s[v0 + lane] = mb;
-                if (p.flags & AMX_PRE_NORMALIZE) {
-                    // norm_factor = mean_b0s; idx = nf <= thr; nf[idx] = 1; nf = 1 / nf; nf[idx] = 0   (core.py:215-219)
-                    const bool off = mb <= p.thr;
-                    nf = off ? 0.0f : __fdiv_rn(1.0f, mb);
+        if (c + step < n_chunks) load(c + step, b ^ 1);
+        if (nvox == CH) mb_wait(&bar[b], (it >> 1) & 1);
+        __syncwarp();
+        float *raw = buf0 + (size_t)b * CH * nS;
+        // ---- pass 1
+        {
+            bool bad = false;
+            const int cnt = nvox * nS;
+            if (diravg) {  // also copy into rows of odd stride for the conflict-free lane-per-voxel sums below
+                int v = 0, j = lane;
+                while (j >= nS) { j -= nS; ++v; }
+                for (int e = lane; e < cnt; e += 32) {
+                    float f = raw[e];
+                    if (!isfinite(f)) { bad = true; if (replace) f = p.repl; }
+                    pad[v * pstride + j] = f;
+                    j += 32;
+                    while (j >= nS) { j -= nS; ++v; }
+                }
+            } else {
+#pragma unroll 4
+                for (int e = lane; e < cnt; e += 32) {
+                    const float f = raw[e];
+                    if (!isfinite(f)) { bad = true; if (replace) raw[e] = p.repl; }
                 }
             }
+            if (bad) st |= 1u;
+        }
+        __syncwarp();
+        // ---- pass 2
+        bool keep = false;
+        if (lane < nvox) {
+            keep = p.mask ? (p.mask[v0 + lane] == 1) : true;
+            const float *r = diravg ? pad + lane * pstride : raw + lane * nS;
+            float nf = 1.0f;
+            if (p.b0_count > 0 && (norm || p.mean_b0s)) {
+                const float mb = seq_mean(p.b0_count, [&](int i) { return r[p.b0_idx[i]]; });
+                if (p.mean_b0s) p.mean_b0s[v0 + lane] = mb;
+                // norm_factor = mean_b0s; idx = nf <= thr; nf[idx] = 1; nf = 1 / nf; nf[idx] = 0   (core.py:215-219)
+                if (norm) nf = (mb <= p.thr) ? 0.0f : __fdiv_rn(1.0f, mb);
+            }
             nfs[lane] = nf;
-            const bool norm = p.flags & AMX_PRE_NORMALIZE;
-            if (p.flags & AMX_PRE_MERGE_B0) {
-                // out = [mean of the (normalised) b0 volumes | (normalised) dwi volumes]   (core.py:226-227)
-                const float mb0 = seq_mean(p.b0_count, [&](int i) { const float x = r[p.b0_idx[i]]; return norm ? __fmul_rn(x, nf) : x; });
-                // in place: dwi_idx is ascending, so dwi_idx[k] >= k and compacting forward to r[k] never overwrites an
-                // unread source; then shift up by one (slot dwi_count exists: there is at least one b0)
-                for (int k = 0; k < p.dwi_count; ++k) {
-                    const float x = r[p.dwi_idx[k]];
-                    r[k] = norm ? __fmul_rn(x, nf) : x;
-                }
-                for (int k = p.dwi_count; k > 0; --k) r[k] = r[k - 1];
-                r[0] = mb0;
-            } else if (p.flags & AMX_PRE_DIR_AVG) {
-                // dir_avg_img is a VIEW of the first n_shells+1 volumes (core.py:234): every mean is written in place and
-                // later means read the already overwritten volumes.  Normalise the row first, then replay that.
-                if (norm)
-                    for (int j = 0; j < nS; ++j) r[j] = __fmul_rn(r[j], nf);
-                const float a0 = seq_mean(p.b0_count, [&](int i) { return r[p.b0_idx[i]]; });
-                r[0] = a0;
+            if (merge)  // mean of the (normalised) b0 volumes (core.py:226)
+                mb0s[lane] = seq_mean(p.b0_count, [&](int i) { const float x = r[p.b0_idx[i]]; return norm ? __fmul_rn(x, nf) : x; });
+            if (diravg) {
+                // dir_avg_img is a VIEW of the first n_shells+1 volumes (core.py:234): every mean is written in place, so a
+                // later mean that indexes volume i < (volumes written so far) reads the average stored there
+                float *a = avg + lane * m_out;
+                int done = 0;
+                auto val = [&](int i) { return i < done ? a[i] : (norm ? __fmul_rn(r[i], nf) : r[i]); };
+                a[0] = seq_mean(p.b0_count, [&](int i) { return val(p.b0_idx[i]); });
+                done = 1;
                 for (int s = 0; s < p.n_shells; ++s) {
                     const int o = p.shell_off[s], cnt = p.shell_off[s + 1] - o;
-                    const float a = seq_mean(cnt, [&](int i) { return r[p.shell_idx[o + i]]; });
-                    r[s + 1] = a;
+                    a[s + 1] = seq_mean(cnt, [&](int i) { return val(p.shell_idx[o + i]); });
+                    done = s + 2;
                 }
-            } else if (norm) {
-                for (int j = 0; j < nS; ++j) r[j] = __fmul_rn(r[j], nf);
             }
         }
         const unsigned keepmask = __ballot_sync(FULLM, keep);
         __syncwarp();
-        // ---- output: the kept voxels' rows are consecutive in y
+        // ---- pass 3: the kept voxels' rows are consecutive in y
         const int nkeep = __popc(keepmask);
         if (nkeep) {
             const long long blk = v0 / PRE_BLOCK_VOX;
-            // rank of this chunk's first kept voxel inside its 1024-voxel block
-            long long pos0 = p.block_off[blk];
-            {
+            long long pos0 = v0;
+            if (p.mask) {  // rank of the chunk's first kept voxel: block prefix + kept voxels of the block before the chunk
                 const long long b0v = blk * PRE_BLOCK_VOX;
                 int before = 0;
-                if (p.mask) {
-                    for (long long v = b0v + lane; v < v0; v += 32) before += (p.mask[v] == 1);
+                for (long long v = b0v + lane; v < v0; v += 32) before += (p.mask[v] == 1);
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULLM, before, o);
-                } else {
-                    before = (int)(v0 - b0v);
-                }
-                pos0 += before;
+                for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULLM, before, o);
+                pos0 = p.block_off[blk] + before;
             }
             if (pos0 + nkeep > p.y_cap) {
                 st |= 4u;
@@ -238,21 +320,26 @@ __global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long
                 int rr = 0, j = lane;
                 while (j >= m_out) { j -= m_out; ++rr; }
                 bool bad = false;
+#pragma unroll 2
                 for (int e = lane; e < total; e += 32) {
                     const int v = keepmask == FULLM ? rr : (int)__fns(keepmask, 0, rr + 1);
-                    float f = rows[v * stride + j];
-                    if (!isfinite(f)) {
-                        bad = true;
-                        if (replace) f = p.repl;
+                    float f;
+                    if (diravg) {
+                        f = avg[v * m_out + j];
+                    } else if (merge && j == 0) {
+                        f = mb0s[v];
+                    } else {
+                        f = raw[v * nS + (merge ? p.dwi_idx[j - 1] : j)];
+                        if (norm) f = __fmul_rn(f, nfs[v]);
                     }
-                    out[e] = f < 0.0f ? 0.0f : f;  // y[y < 0] = 0 (core.py:452)
+                    if (!isfinite(f)) { bad = true; if (replace) f = p.repl; }
+                    __stcs(out + e, f < 0.0f ? 0.0f : f);  // y[y < 0] = 0 (core.py:452)
                     j += 32;
                     while (j >= m_out) { j -= m_out; ++rr; }
                 }
                 if (bad) st |= 2u;
             }
         }
-        __syncwarp();
     }
     st = __reduce_or_sync(FULLM, st);
     if (lane == 0 && st) atomicOr(p.status, st);
@@ -516,25 +603,29 @@ int amx_preprocess(const amx_pre_args *a, int64_t *n_kept, int *m_out_p)
     AMX_CK(tmp.alloc((void **)&d_counts, (size_t)(n_blocks + 1) * sizeof(long long)));
     AMX_CK(tmp.alloc((void **)&d_status, 16));
     AMX_CK(cudaMemsetAsync(d_status, 0, 16, s));
-    k_mask_count<<<n_blocks, 256, 0, s>>>(p.mask, a->n_total, d_counts);
-    k_scan_counts<<<1, 1024, 0, s>>>(d_counts, n_blocks);
-    p.block_off = d_counts; p.status = d_status;
+    if (p.mask) {  // order-preserving compaction: kept voxels per 1024-voxel block, exclusive scan
+        k_mask_count<<<n_blocks, 256, 0, s>>>(p.mask, a->n_total, d_counts);
+        k_scan_counts<<<1, 1024, 0, s>>>(d_counts, n_blocks);
+    }
+    p.block_off = p.mask ? d_counts : nullptr;  // no mask: block b starts at row 1024 b
+    p.status = d_status;
 
-    const size_t per_warp = (size_t)(CH * p.stride + CH) * sizeof(float);
-    const int warps = warps_for(0, per_warp, max_smem);
+    const size_t per_warp = pre_warp_bytes(a->nS, m_out, a->flags & AMX_PRE_DIR_AVG);
+    const int warps = warps_for(1024, per_warp, max_smem);
     if (warps <= 0) return amx::set_error(AMX_E_INVALID, "nS=%d too large for the shared-memory staging", a->nS);
     const size_t smem = (size_t)warps * per_warp;
     AMX_CK(cudaFuncSetAttribute(k_preprocess, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long n_chunks = (a->n_total + CH - 1) / CH;
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / smem));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / (smem + 1024)));
     const long long want = (n_chunks + warps - 1) / warps;
     const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)sm * ctas_per_sm));
-    k_preprocess<<<grid, warps * 32, smem, s>>>(p, n_chunks);
+    k_preprocess<<<grid, warps * 32, smem, s>>>(p, n_chunks, (unsigned)per_warp);
     AMX_CK(cudaGetLastError());
 
     long long total = 0;
     unsigned status = 0;
-    AMX_CK(cudaMemcpyAsync(&total, d_counts + n_blocks, sizeof total, cudaMemcpyDeviceToHost, s));
+    if (p.mask) AMX_CK(cudaMemcpyAsync(&total, d_counts + n_blocks, sizeof total, cudaMemcpyDeviceToHost, s));
+    else total = a->n_total;
     AMX_CK(cudaMemcpyAsync(&status, d_status, sizeof status, cudaMemcpyDeviceToHost, s));
     AMX_CK(cudaStreamSynchronize(s));
     *n_kept = total;

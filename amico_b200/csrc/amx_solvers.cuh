@@ -96,7 +96,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
         }
         // candidate selection
         int j = -1;
-        double v = 0.0, d2 = 0.0, znew = 0.0;
+        double v = 0.0, d2 = 0.0, znum = 0.0;
         for (;;) {
             double bv = 0.0;
             int bj = -1;
@@ -111,16 +111,12 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             double vv = warp_sum(lane < np ? v * v : 0.0);
             double vz = warp_sum(lane < np ? v * zl : 0.0);
             d2 = T[(size_t)j * ldT + j] - vv;
-            bool ok = false;
-            if (d2 > 0.0) {
-                double unorm = sqrt(vv), dd = sqrt(d2);
-                double tt = unorm + dd * 0.01;
-                if (tt - unorm > 0.0) {
-                    znew = (c[j] - vz) / dd;
-                    ok = znew > 0.0;
-                }
-            }
-            if (ok) break;
+            // Lawson-Hanson's tests on the candidate: (i) independence, `unorm + 0.01 dd - unorm > 0` with unorm = |v|,
+            // dd = sqrt(d2), i.e. 0.01 dd above half an ulp of unorm -- evaluated on the squares (1.2326e-28 =
+            // (2^-53 / 0.01)^2) so that no square root is needed; (ii) the new coefficient z / dd must be positive, and
+            // dd > 0, so the sign of c_j - v.z decides.
+            znum = c[j] - vz;
+            if (d2 > 0.0 && d2 > 1.2325951644078309e-28 * vv && znum > 0.0) break;
             // reject: drop j from this round's candidates
             if ((j & 31) == lane) {
 #pragma unroll
@@ -131,11 +127,12 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
         if (j < 0) break;
         // move j to the passive set: append a row to the factor
         {
-            double dd = sqrt(d2);
+            const double ird = rsqrt(d2), dd = d2 * ird;
+            const double znew = znum * ird;
             if (lane < np) Lp[tri(np, lane)] = v;
             if (lane == np) {
                 Lp[tri(np, np)] = dd;
-                rd[np] = 1.0 / dd;
+                rd[np] = ird;
                 P[np] = j;
                 zl = znew;
                 xp = 0.0;
@@ -214,7 +211,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                     for (int r = q; r < pn - 1; ++r) {
                         const double a = Lp[tri(r, r)];
                         const double b = shfl(e, r);
-                        const double ir = 1.0 / sqrt(fma(a, a, b * b));
+                        const double ir = rsqrt(fma(a, a, b * b));  // = 1 / (new diagonal element)
                         const double cs = a * ir, sn = b * ir;
                         if (lane >= r && lane < pn - 1) {
                             const double u1 = (lane == r) ? a : Lp[tri(lane, r)];
@@ -222,7 +219,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                             const double n1 = fma(cs, u1, sn * u2), n2 = fma(cs, u2, -sn * u1);
                             Lp[tri(lane, r)] = n1;
                             if (lane > r) Lp[tri(lane, r + 1)] = n2;
-                            else rd[r] = 1.0 / n1;
+                            else rd[r] = ir;
                         }
                         const double zr = shfl(zl, r), zr1 = shfl(zl, r + 1);
                         if (lane == r) zl = fma(cs, zr, sn * zr1);
