@@ -624,7 +624,8 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         // stage 1 (NNLS on the full dictionary) never holds more than ~8 passive atoms on NODDI dictionaries (rank ~11):
         // a 16-atom workspace leaves ~85 KB more L1 for its Gram rows; rarer larger sets go to the slow path
         p.cap_stage[0] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE1", 16)));
-        p.cap_stage[1] = p.cap_stage[2] = LC;
+        p.cap_stage[1] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE2", LC)));
+        p.cap_stage[2] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE3", LC)));
         for (int k = 0; k < 3; ++k) p.ws_doubles_stage[k] = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, 1, p.cap_stage[k]);
     }
     const size_t ws_bytes = (size_t)p.ws_doubles * sizeof(double);

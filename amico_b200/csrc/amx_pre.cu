@@ -196,13 +196,13 @@ __host__ __device__ inline size_t pre_warp_bytes(int nS, int m_out, bool diravg)
 //   pass 3 (cooperative): y rows of the kept voxels, normalised, clamped at 0, written fully coalesced
 __global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long n_chunks, unsigned warp_bytes)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char pre_smem[];
     __shared__ uint64_t bars[4][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const int nS = p.nS, m_out = p.m_out;
     const bool norm = p.flags & AMX_PRE_NORMALIZE, merge = p.flags & AMX_PRE_MERGE_B0, diravg = p.flags & AMX_PRE_DIR_AVG;
     const bool replace = p.flags & AMX_PRE_REPLACE_BAD;
-    float *buf0 = reinterpret_cast<float *>(smem_raw + (size_t)warp * warp_bytes);
+    float *buf0 = reinterpret_cast<float *>(pre_smem + (size_t)warp * warp_bytes);
     float *nfs = buf0 + 2 * CH * nS, *mb0s = nfs + CH;
     const int pstride = nS | 1;
     float *pad = mb0s + CH, *avg = pad + CH * pstride;  // diravg only
@@ -469,6 +469,47 @@ __global__ void k_scatter_maps(const double *__restrict__ values, long long n_vo
         const long long i = e / k;
         const int c = (int)(e - i * k);
         volume[(long long)vox_idx[i] * k + c] = (float)values[e];
+    }
+}
+
+
+// ---- kernel resampling (amico/lut.pyx:274-311) --------------------------------------------------------------------
+// out[row][j] = 1 when scheme row merge_idx[j] is not a dwi row, else sum_k Ylm[p][k] * KRlm[row][k] with p the dwi position of
+// that row; rows = (atom, direction) pairs.  CTA tile: RT rows x JT output columns; the K tile and the (transposed)
+// Ylm tile sit in shared memory; accumulation in fp64, one rounding to fp32 (the reference's np.dot is a float32 BLAS
+// gemv whose summation order depends on the BLAS build: this result is within 0.5 ulp of the exact dot product).
+constexpr int RS_RT = 32, RS_JT = 32;
+__global__ void __launch_bounds__(256) k_resample(const float *__restrict__ KRlm, long long n_rows, int n_coef,
+                                                  const float *__restrict__ Ylm, const int *__restrict__ colsrc, int nS_out, float *out)
+{
+    extern __shared__ __align__(16) float rs_smem[];
+    float *Ks = rs_smem;                       // [RS_RT][n_coef]
+    float *Ys = Ks + (size_t)RS_RT * n_coef;   // [n_coef][RS_JT]  (transposed: threads of a warp read consecutive words)
+    __shared__ int src[RS_JT];
+    const long long r0 = (long long)blockIdx.x * RS_RT;
+    const int j0 = blockIdx.y * RS_JT;
+    const int nr = (int)min((long long)RS_RT, n_rows - r0), nj = min(RS_JT, nS_out - j0);
+    if (threadIdx.x < RS_JT) src[threadIdx.x] = threadIdx.x < nj ? colsrc[j0 + threadIdx.x] : -1;
+    __syncthreads();
+    for (int e = threadIdx.x; e < nr * n_coef; e += blockDim.x) Ks[e] = KRlm[r0 * n_coef + e];
+    for (int e = threadIdx.x; e < RS_JT * n_coef; e += blockDim.x) {
+        const int jj = e / n_coef, k = e - jj * n_coef;
+        const int p = src[jj];
+        Ys[k * RS_JT + jj] = p >= 0 ? Ylm[(size_t)p * n_coef + k] : 0.0f;
+    }
+    __syncthreads();
+    const int jj = threadIdx.x & (RS_JT - 1);
+    for (int rr = threadIdx.x / RS_JT; rr < nr; rr += blockDim.x / RS_JT) {
+        if (jj >= nj) continue;
+        float v = 1.0f;  // KR = np.ones(...) (lut.pyx:297): rows outside idx_out (the b0 volumes) stay 1
+        if (src[jj] >= 0) {
+            const float *kr = Ks + (size_t)rr * n_coef;
+            double acc = 0.0;
+#pragma unroll 4
+            for (int k = 0; k < n_coef; ++k) acc = fma((double)Ys[k * RS_JT + jj], (double)kr[k], acc);
+            v = (float)acc;
+        }
+        out[(r0 + rr) * nS_out + j0 + jj] = v;
     }
 }
 
@@ -770,6 +811,47 @@ int amx_scatter_maps(int device, int space, const double *values, int64_t n_vox,
         AMX_CK(cudaMemcpyAsync(volume, dst, (size_t)n_total * k * sizeof(float), cudaMemcpyDeviceToHost, s));
         AMX_CK(cudaStreamSynchronize(s));
     }
+    return AMX_OK;
+}
+
+int amx_resample_kernels(int device, int space, const float *KRlm, int64_t n_rows, int n_coef, const float *Ylm_out,
+                         const int32_t *idx_out, int dwi_count, const int32_t *merge_idx, int nS_out, int nS, float *out,
+                         void *stream)
+{
+    if (!KRlm || !Ylm_out || !idx_out || !merge_idx || !out || n_rows <= 0 || n_coef <= 0 || dwi_count <= 0 || nS_out <= 0 || nS <= 0)
+        return amx::set_error(AMX_E_INVALID, "bad arguments");
+    int rc, sm = 0, max_smem = 0;
+    if ((rc = check_idx(idx_out, dwi_count, nS, "idx_out")) || (rc = check_idx(merge_idx, nS_out, nS, "merge_idx"))) return rc;
+    if ((rc = pick_device(device, &sm, &max_smem))) return rc;
+    const size_t smem = (size_t)(RS_RT + RS_JT) * n_coef * sizeof(float);
+    if (smem > (size_t)max_smem) return amx::set_error(AMX_E_INVALID, "n_coef=%d too large for the shared-memory tiles", n_coef);
+    // output column j <- dwi position of scheme row merge_idx[j] (or -1: stays 1)
+    std::vector<int> pos(nS, -1), colsrc(nS_out);
+    for (int p = 0; p < dwi_count; ++p) pos[idx_out[p]] = p;
+    for (int j = 0; j < nS_out; ++j) colsrc[j] = pos[merge_idx[j]];
+    cudaStream_t s = (cudaStream_t)stream;
+    Tmp tmp(s);
+    const bool host = space == AMX_SPACE_HOST;
+    int *d_col = nullptr;
+    AMX_CK(tmp.alloc((void **)&d_col, (size_t)nS_out * sizeof(int)));
+    AMX_CK(cudaMemcpyAsync(d_col, colsrc.data(), (size_t)nS_out * sizeof(int), cudaMemcpyHostToDevice, s));
+    const float *d_K = KRlm, *d_Y = Ylm_out;
+    float *d_o = out;
+    if (host) {
+        float *k = nullptr, *yl = nullptr, *o = nullptr;
+        AMX_CK(tmp.alloc((void **)&k, (size_t)n_rows * n_coef * sizeof(float)));
+        AMX_CK(tmp.alloc((void **)&yl, (size_t)dwi_count * n_coef * sizeof(float)));
+        AMX_CK(tmp.alloc((void **)&o, (size_t)n_rows * nS_out * sizeof(float)));
+        AMX_CK(cudaMemcpyAsync(k, KRlm, (size_t)n_rows * n_coef * sizeof(float), cudaMemcpyHostToDevice, s));
+        AMX_CK(cudaMemcpyAsync(yl, Ylm_out, (size_t)dwi_count * n_coef * sizeof(float), cudaMemcpyHostToDevice, s));
+        d_K = k; d_Y = yl; d_o = o;
+    }
+    AMX_CK(cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)((n_rows + RS_RT - 1) / RS_RT), (unsigned)((nS_out + RS_JT - 1) / RS_JT));
+    k_resample<<<grid, 256, smem, s>>>(d_K, n_rows, n_coef, d_Y, d_col, nS_out, d_o);
+    AMX_CK(cudaGetLastError());
+    if (host) AMX_CK(cudaMemcpyAsync(out, d_o, (size_t)n_rows * nS_out * sizeof(float), cudaMemcpyDeviceToHost, s));
+    AMX_CK(cudaStreamSynchronize(s));
     return AMX_OK;
 }
 

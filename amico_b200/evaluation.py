@@ -214,8 +214,11 @@ class Evaluation:
             bvecs = np.vstack((np.zeros((1, 3)), sch.raw[sch.dwi_idx, :3]))
         else:
             bvals, bvecs = sch.b, sch.raw[:, :3]
-        W = np.linalg.pinv(dti_design_matrix(bvals, bvecs))
-        return np.ascontiguousarray(W[:6], dtype=np.float64)
+        key = (bvals.tobytes(), np.ascontiguousarray(bvecs).tobytes())
+        if getattr(self, "_dti_W_key", None) != key:  # the SVD behind pinv costs milliseconds on the host: once per scheme
+            W = np.linalg.pinv(dti_design_matrix(bvals, bvecs))
+            self._dti_W, self._dti_W_key = np.ascontiguousarray(W[:6], dtype=np.float64), key
+        return self._dti_W
 
     def estimate_directions(self):
         """Principal directions of every mask voxel (``core.py:456-458``) -> device tensor (n_vox, 3) float64."""

@@ -10,13 +10,17 @@ They can be injected into the reference without editing it through its own plugi
 (``$AMICO_WIP_MODELS`` -> ``from amicowipmodels import *``, ``amico/models.pyx:20-26``; lookup by name in
 ``amico/core.py:290-291``) -- see INTEGRATION.md.
 
-``generate`` / ``resample`` (kernel synthesis and SH resampling: offline, outside the hot path --
-SURVEY section 8f-3) are not provided here.
+``resample`` reads the ``A_###.npy`` files the reference's ``generate`` wrote and builds the same
+``KERNELS`` dict as the reference, with the SH -> signal-space projection on the GPU (``amx_resample_kernels``).
+``generate`` (kernel synthesis: offline, once per protocol) is not provided here.
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
+from . import lut as _lut
 from .plan import Plan
 
 __all__ = ["NODDI", "FreeWater", "CylinderZeppelinBall", "SANDI", "BaseModel"]
@@ -43,7 +47,27 @@ class BaseModel:
         raise NotImplementedError("kernel generation is outside the accelerated hot path (use the reference's generate)")
 
     def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
-        raise NotImplementedError("kernel resampling is outside the accelerated hot path (use the reference's resample)")
+        raise NotImplementedError
+
+    # -- shared pieces of the four resample() bodies -------------------------------------------------
+    def _merge_idx(self, doMergeB0):
+        """(nS, merge_idx) of ``amico/models.pyx:756-761`` (identical in every model)."""
+        if doMergeB0:
+            return 1 + self.scheme.dwi_count, np.hstack((self.scheme.b0_idx[0], self.scheme.dwi_idx))
+        return self.scheme.nS, np.arange(self.scheme.nS)
+
+    def _resample_atoms(self, in_path, first, count, isotropic, idx_out, Ylm_out, merge_idx, ndirs):
+        """Atoms ``A_{first+1:03d}.npy`` ... of ``generate``'s output, projected to the scheme: float32
+        (count, ndirs, len(merge_idx)), or (count, len(merge_idx)) for isotropic atoms."""
+        if count == 0:
+            return np.zeros((0, ndirs, len(merge_idx)) if not isotropic else (0, len(merge_idx)), dtype=np.float32)
+        lms = []
+        for i in range(count):
+            lm = np.load(os.path.join(in_path, f"A_{first + i + 1:03d}.npy"))
+            if not isotropic and lm.shape[0] != ndirs:
+                raise RuntimeError('Outdated LUT. Call "generate_kernels( regenerate=True )" to update the LUT')
+            lms.append(lm)
+        return _lut.resample_kernels(np.stack(lms), self.scheme.nS, idx_out, Ylm_out, merge_idx, device=self.device)
 
     # -- plan cache: one upload + Gram precompute per (KERNELS, htable) -------------------------
     def _model_params(self):
@@ -126,6 +150,20 @@ class NODDI(BaseModel):
     def _model_params(self):
         return {"isExvivo": bool(self.isExvivo)}
 
+    def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
+        """``amico/models.pyx:754-792``."""
+        n_wm = len(self.IC_ODs) * len(self.IC_VFs)
+        nS, merge_idx = self._merge_idx(doMergeB0)
+        K = {"model": self.id}
+        K["wm"] = self._resample_atoms(in_path, 0, n_wm, False, idx_out, Ylm_out, merge_idx, ndirs)
+        K["iso"] = self._resample_atoms(in_path, n_wm, 1, True, idx_out, Ylm_out, merge_idx, ndirs)[0]
+        K["kappa"] = np.repeat(1.0 / np.tan(np.asarray(self.IC_ODs) * np.pi / 2.0), len(self.IC_VFs)).astype(np.float32)
+        K["icvf"] = np.tile(np.asarray(self.IC_VFs), len(self.IC_ODs)).astype(np.float32)
+        rows = slice(1, None) if doMergeB0 else self.scheme.dwi_idx
+        K["norms"] = np.zeros((self.scheme.dwi_count, n_wm))
+        K["norms"][:, :] = 1.0 / np.array([np.linalg.norm(K["wm"][k, 0, rows]) for k in range(n_wm)])  # LUT direction 0 only
+        return K
+
 
 class FreeWater(BaseModel):
     """Free-Water (``amico/models.pyx:994-1286``): one non-negative elastic net on [zeppelins | balls]."""
@@ -164,6 +202,14 @@ class FreeWater(BaseModel):
     def _model_params(self):
         return {"type": self.type}
 
+    def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
+        """``amico/models.pyx:1113-1144``."""
+        nS, merge_idx = self._merge_idx(doMergeB0)
+        n_perp, n_iso = len(self.d_perps), len(self.d_isos)
+        return {"model": self.id,
+                "D": self._resample_atoms(in_path, 0, n_perp, False, idx_out, Ylm_out, merge_idx, ndirs),
+                "CSF": self._resample_atoms(in_path, n_perp, n_iso, True, idx_out, Ylm_out, merge_idx, ndirs)}
+
 
 class CylinderZeppelinBall(BaseModel):
     """Cylinder-Zeppelin-Ball / ActiveAx-style (``amico/models.pyx:374-652``)."""
@@ -196,6 +242,15 @@ class CylinderZeppelinBall(BaseModel):
     def _model_params(self):
         return {"Rs": np.asarray(self.Rs, dtype=np.float64)}
 
+    def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
+        """``amico/models.pyx:482-523``."""
+        nS, merge_idx = self._merge_idx(doMergeB0)
+        n_rs, n_perp, n_iso = len(self.Rs), len(self.d_perps), len(self.d_isos)
+        return {"model": self.id,
+                "wmr": self._resample_atoms(in_path, 0, n_rs, False, idx_out, Ylm_out, merge_idx, ndirs),
+                "wmh": self._resample_atoms(in_path, n_rs, n_perp, False, idx_out, Ylm_out, merge_idx, ndirs),
+                "iso": self._resample_atoms(in_path, n_rs + n_perp, n_iso, True, idx_out, Ylm_out, merge_idx, ndirs)}
+
 
 class SANDI(BaseModel):
     """SANDI (``amico/models.pyx:1343-1627``): one shared, column-normalised dictionary; no direction LUT."""
@@ -227,3 +282,14 @@ class SANDI(BaseModel):
     def _model_params(self):
         return {"Rs": np.asarray(self.Rs, dtype=np.float64), "d_in": np.asarray(self.d_in, dtype=np.float64),
                 "d_isos": np.asarray(self.d_isos, dtype=np.float64)}
+
+    def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
+        """``amico/models.pyx:1446-1486``: every atom is isotropic; columns are L2-normalised."""
+        n_atoms = len(self.Rs) + len(self.d_in) + len(self.d_isos)
+        nS, merge_idx = self._merge_idx(doMergeB0)
+        sig = self._resample_atoms(in_path, 0, n_atoms, True, idx_out, Ylm_out, merge_idx, ndirs)  # (n_atoms, nS) float32
+        K = {"model": self.id, "signal": np.zeros((nS, n_atoms), dtype=np.float64, order="F"), "norms": np.zeros(n_atoms)}
+        for k in range(n_atoms):
+            K["norms"][k] = 1.0 / np.linalg.norm(sig[k])
+            K["signal"][:, k] = sig[k] * K["norms"][k]
+        return K

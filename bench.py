@@ -13,6 +13,8 @@ the timed steps).
 `e2e`    : the same through the host-buffer C-ABI call (pinned host y/dirs -> H2D -> fit -> D2H maps).
 `roofline`: fused fit kernel, algorithmic bytes/voxel (4m + 24 + 4 m n_rot + 4 n_maps) / its
            CUDA-event duration, against the measured HBM copy peak (MEASURED_PEAKS.json).
+`pipeline` (N=1): the callers either side of the fit -- amx_preprocess / amx_dti_directions / amx_scatter_maps GB/s and the
+           whole raw-volume -> maps flow (tools/bench_pipeline.py); an extra, not the headline.
 `cpu_baseline` (N=1): the CPU oracle (oracle/) on a bounded sample of the same workload, all host cores.
 `--impl reference`: the reference's own CPU path -- daducci/AMICO's Cython `NODDI.fit` compiled
            unmodified (oracle/_ref; its absent third-party spams-cython solvers bound to the restated
@@ -195,6 +197,7 @@ def main():
     ap.add_argument("--nvox", type=int, default=0, help="voxels per GPU (default: the whole cfg volume)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="skip the raw-volume -> maps flow (pre-processing, DTI, fit, scatter)")
     args = ap.parse_args()
     from amico_b200 import synth
     if not args.nvox:
@@ -335,6 +338,15 @@ def main():
             dt = cpu_fit(P, n_s, "port", cores)
             line["cpu_baseline"] = {"value": n_s / dt, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"first {n_s} voxels of the same volume, oracle/amico_oracle.c, {cores} pthreads"}
+        if world == 1 and not args.no_pipeline and mid == "NODDI":
+            # the callers either side of the fit: per-kernel GB/s and the whole raw-volume -> maps flow
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import bench_pipeline
+                del plan
+                line["pipeline"] = bench_pipeline.measure(args.cfg, steps=max(2, min(args.steps, 5)), P=P)
+            except Exception as e:  # an extra, never the headline
+                line["pipeline"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -210,6 +210,17 @@ int amx_dti_directions(int device, int space, const void *y, int y_dtype, int64_
 int amx_scatter_maps(int device, int space, const double *values, int64_t n_vox, int k, const int32_t *vox_idx,
                      float *volume, int64_t n_total, void *stream);
 
+/* Row f-3: `amico.lut.resample_kernel` (amico/lut.pyx:274-311) for a stack of atoms: project the rotated response
+ * functions from SH space to the subject's acquisition scheme.  KRlm: [n_rows][n_coef] float32, n_rows = atoms x LUT
+ * directions of the `A_###.npy` files `generate` wrote (n_rows = atoms for isotropic atoms); Ylm_out: [dwi_count][n_coef]
+ * float32 and idx_out: int32 [dwi_count] from `aux_structures_resample` (lut.pyx:199-224); merge_idx: int32 [nS_out], the
+ * scheme row each output column takes (`[b0_idx[0], dwi_idx...]` with doMergeB0, else 0..nS-1; amico/models.pyx:756-761).
+ * out: [n_rows][nS_out] float32 = KR[:, merge_idx]; columns that are not dwi rows are 1 (lut.pyx:297).  idx_out and
+ * merge_idx are HOST pointers in either space.  Accumulates in fp64 and rounds once. */
+int amx_resample_kernels(int device, int space, const float *KRlm, int64_t n_rows, int n_coef, const float *Ylm_out,
+                         const int32_t *idx_out, int dwi_count, const int32_t *merge_idx, int nS_out, int nS, float *out,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,3 +123,93 @@ def scatter_maps(values, vox_idx, n_total):
     vol = np.zeros((n_total, values.shape[1]), dtype=np.float32)
     vol[np.asarray(vox_idx)] = values
     return vol
+
+
+# --------------------------------------------------------------------------- kernel resampling (row f-3)
+def resample_kernel(KRlm, nS, idx_out, Ylm_out, is_isotropic, ndirs):
+    """``amico/lut.pyx:274-311`` statement for statement (numpy float32 ``np.dot``)."""
+    if not is_isotropic:
+        KR = np.ones((ndirs, nS), dtype=np.float32)
+        for i in range(ndirs):
+            KR[i, idx_out] = np.dot(Ylm_out, KRlm[i, :]).astype(np.float32)
+    else:
+        KR = np.ones(nS, dtype=np.float32)
+        KR[idx_out] = np.dot(Ylm_out, KRlm)
+    return KR
+
+
+def resample_kernel_exact(KRlm, nS, idx_out, Ylm_out, is_isotropic, ndirs):
+    """The same projection with the dot products in float64, rounded once: the value every float32 BLAS summation order
+    approximates (the GPU kernel must match THIS to 1 ulp)."""
+    Y = np.asarray(Ylm_out, dtype=np.float64)
+    K = np.asarray(KRlm, dtype=np.float64)
+    if not is_isotropic:
+        KR = np.ones((ndirs, nS), dtype=np.float32)
+        KR[:, idx_out] = (K @ Y.T).astype(np.float32)
+    else:
+        KR = np.ones(nS, dtype=np.float32)
+        KR[idx_out] = (Y @ K).astype(np.float32)
+    return KR
+
+
+def model_resample(model, params, scheme, in_path, idx_out, Ylm_out, doMergeB0, ndirs, kernel=resample_kernel):
+    """``<Model>.resample`` of amico/models.pyx (:754-792 NODDI, :1113-1144 FreeWater, :482-523 CylinderZeppelinBall,
+    :1446-1486 SANDI) on the ``A_###.npy`` files of ``in_path``."""
+    import os
+    if doMergeB0:
+        nS = 1 + scheme.dwi_count
+        merge_idx = np.hstack((scheme.b0_idx[0], scheme.dwi_idx))
+    else:
+        nS = scheme.nS
+        merge_idx = np.arange(nS)
+    load = lambda i: np.load(os.path.join(in_path, f"A_{i + 1:03d}.npy"))
+    K = {"model": model}
+    if model == "NODDI":
+        ods, vfs = params["IC_ODs"], params["IC_VFs"]
+        n = len(ods) * len(vfs)
+        K["wm"] = np.zeros((n, ndirs, nS), dtype=np.float32)
+        K["kappa"] = np.zeros(n, dtype=np.float32)
+        K["icvf"] = np.zeros(n, dtype=np.float32)
+        K["norms"] = np.zeros((scheme.dwi_count, n))
+        idx = 0
+        for i in range(len(ods)):
+            for j in range(len(vfs)):
+                K["wm"][idx] = kernel(load(idx), scheme.nS, idx_out, Ylm_out, False, ndirs)[:, merge_idx]
+                K["kappa"][idx] = 1.0 / np.tan(ods[i] * np.pi / 2.0)
+                K["icvf"][idx] = vfs[j]
+                if doMergeB0:
+                    K["norms"][:, idx] = 1 / np.linalg.norm(K["wm"][idx, 0, 1:])
+                else:
+                    K["norms"][:, idx] = 1 / np.linalg.norm(K["wm"][idx, 0, scheme.dwi_idx])
+                idx += 1
+        K["iso"] = kernel(load(n), scheme.nS, idx_out, Ylm_out, True, ndirs)[merge_idx]
+    elif model == "FreeWater":
+        n_perp, n_iso = len(params["d_perps"]), len(params["d_isos"])
+        K["D"] = np.zeros((n_perp, ndirs, nS), dtype=np.float32)
+        K["CSF"] = np.zeros((n_iso, nS), dtype=np.float32)
+        for i in range(n_perp):
+            K["D"][i] = kernel(load(i), scheme.nS, idx_out, Ylm_out, False, ndirs)[:, merge_idx]
+        for i in range(n_iso):
+            K["CSF"][i] = kernel(load(n_perp + i), scheme.nS, idx_out, Ylm_out, True, ndirs)[merge_idx]
+    elif model == "CylinderZeppelinBall":
+        n_rs, n_perp, n_iso = len(params["Rs"]), len(params["d_perps"]), len(params["d_isos"])
+        K["wmr"] = np.zeros((n_rs, ndirs, nS), dtype=np.float32)
+        K["wmh"] = np.zeros((n_perp, ndirs, nS), dtype=np.float32)
+        K["iso"] = np.zeros((n_iso, nS), dtype=np.float32)
+        for i in range(n_rs):
+            K["wmr"][i] = kernel(load(i), scheme.nS, idx_out, Ylm_out, False, ndirs)[:, merge_idx]
+        for i in range(n_perp):
+            K["wmh"][i] = kernel(load(n_rs + i), scheme.nS, idx_out, Ylm_out, False, ndirs)[:, merge_idx]
+        for i in range(n_iso):
+            K["iso"][i] = kernel(load(n_rs + n_perp + i), scheme.nS, idx_out, Ylm_out, True, ndirs)[merge_idx]
+    elif model == "SANDI":
+        n = len(params["Rs"]) + len(params["d_in"]) + len(params["d_isos"])
+        K["signal"] = np.zeros((nS, n), dtype=np.float64, order="F")
+        K["norms"] = np.zeros(n, dtype=np.float64)
+        for idx in range(n):
+            signal = kernel(load(idx), scheme.nS, idx_out, Ylm_out, True, ndirs)[merge_idx].T
+            K["norms"][idx] = 1.0 / np.linalg.norm(signal)
+            K["signal"][:, idx] = signal * K["norms"][idx]
+    else:
+        raise ValueError(model)
+    return K

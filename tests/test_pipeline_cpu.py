@@ -89,3 +89,46 @@ def test_scatter_oracle():
     assert vol.dtype == np.float32 and vol.shape == (6, 2)
     np.testing.assert_array_equal(vol[[1, 4]], [[3, 4], [1, 2]])
     assert vol.sum() == 10
+
+
+def test_real_sh_basis_addition_theorem():
+    """The SH basis restated from dipy's definition: sum_m Y_lm(g) Y_lm(d) = (2l+1)/(4 pi) P_l(g.d) for every even l <= 12
+    (holds for any orthonormal real basis of each order), and the m = 0 column is the zonal harmonic the reference's
+    rotation relies on (amico/lut.pyx:129-138: idx_m0 = (l*l + l + 2)/2 - 1)."""
+    from numpy.polynomial import legendre as npleg
+    from amico_b200 import lut
+    rng = np.random.default_rng(0)
+    g = rng.standard_normal((40, 3)); g /= np.linalg.norm(g, axis=1, keepdims=True)
+    d = rng.standard_normal((9, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    Yg, m, l = lut.real_sh_descoteaux(12, *lut.cart2sphere(*g.T)[1:])
+    Yd, _, _ = lut.real_sh_descoteaux(12, *lut.cart2sphere(*d.T)[1:])
+    assert Yg.shape == (40, 91)
+    for ll in range(0, 13, 2):
+        sel = l == ll
+        c = np.zeros(ll + 1); c[ll] = 1
+        np.testing.assert_allclose(Yg[:, sel] @ Yd[:, sel].T, (2 * ll + 1) / (4 * np.pi) * npleg.legval(g @ d.T, c), atol=1e-12)
+        i0 = (ll * ll + ll + 2) // 2 - 1
+        assert m[i0] == 0 and l[i0] == ll
+        np.testing.assert_allclose(Yg[:, i0], np.sqrt((2 * ll + 1) / (4 * np.pi)) * npleg.legval(g[:, 2], c), atol=1e-12)
+
+
+def test_aux_structures_resample_layout():
+    from amico_b200 import lut
+    sch = synth.make_scheme(2)
+    idx_out, Ylm = lut.aux_structures_resample(sch, 12)
+    assert idx_out.dtype == np.int32 and Ylm.dtype == np.float32 and Ylm.shape == (sch.dwi_count, 91 * 2)
+    np.testing.assert_array_equal(np.sort(idx_out), sch.dwi_idx)
+    n0 = len(sch.shells[0]["idx"])
+    assert (Ylm[:n0, 91:] == 0).all() and (Ylm[n0:, :91] == 0).all()
+
+
+def test_resample_oracle_exact_vs_float32_statement():
+    rng = np.random.default_rng(2)
+    from amico_b200 import lut
+    sch = synth.make_scheme(1)
+    idx_out, Ylm = lut.aux_structures_resample(sch, 12)
+    lm = (rng.standard_normal((6, Ylm.shape[1])) * 0.3).astype(np.float32)
+    a = opl.resample_kernel(lm, sch.nS, idx_out, Ylm, False, 6)
+    b = opl.resample_kernel_exact(lm, sch.nS, idx_out, Ylm, False, 6)
+    assert a.dtype == np.float32 and (a[:, sch.b0_idx] == 1).all()
+    np.testing.assert_allclose(a, b, atol=2e-6)
