@@ -242,8 +242,15 @@ __global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long
         if (nvox == CH) mb_wait(&bar[b], (it >> 1) & 1);
         __syncwarp();
         float *raw = buf0 + (size_t)b * CH * nS;
+        // mask first: whether pass 1 can be folded into the vectorised pass 3 depends on it
+        bool keep = false;
+        if (lane < nvox) keep = p.mask ? (p.mask[v0 + lane] == 1) : true;
+        const unsigned keepmask = __ballot_sync(FULLM, keep);
+        // fast path: every voxel of a full chunk is kept and the output row is the whole input row -> pass 3 streams the
+        // chunk as float4 and checks the raw values on the way, no separate pass 1
+        const bool fast = !merge && !diravg && !replace && keepmask == FULLM && (nS & 3) == 0 && nvox == CH;
         // ---- pass 1
-        {
+        if (!fast) {
             bool bad = false;
             const int cnt = nvox * nS;
             if (diravg) {  // also copy into rows of odd stride for the conflict-free lane-per-voxel sums below
@@ -267,9 +274,7 @@ __global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long
         }
         __syncwarp();
         // ---- pass 2
-        bool keep = false;
         if (lane < nvox) {
-            keep = p.mask ? (p.mask[v0 + lane] == 1) : true;
             const float *r = diravg ? pad + lane * pstride : raw + lane * nS;
             float nf = 1.0f;
             if (p.b0_count > 0 && (norm || p.mean_b0s)) {
@@ -296,11 +301,48 @@ __global__ void __launch_bounds__(128) k_preprocess(const PreParams p, long long
                 }
             }
         }
-        const unsigned keepmask = __ballot_sync(FULLM, keep);
         __syncwarp();
         // ---- pass 3: the kept voxels' rows are consecutive in y
         const int nkeep = __popc(keepmask);
-        if (nkeep) {
+        if (fast) {
+            long long pos = v0;
+            if (p.mask) {
+                const long long b0v = (v0 / PRE_BLOCK_VOX) * PRE_BLOCK_VOX;
+                int before = 0;
+                for (long long v = b0v + lane; v < v0; v += 32) before += (p.mask[v] == 1);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(FULLM, before, o);
+                pos = p.block_off[v0 / PRE_BLOCK_VOX] + before;
+            }
+            if (pos + CH > p.y_cap) {
+                st |= 4u;
+            } else {
+                p.vox_idx[pos + lane] = (int)(v0 + lane);
+                const float4 *src4 = reinterpret_cast<const float4 *>(raw);
+                float4 *out4 = reinterpret_cast<float4 *>(p.y + pos * nS);
+                const int q4 = nS >> 2, total4 = CH * q4;
+                int v = 0, j4 = lane;
+                while (j4 >= q4) { j4 -= q4; ++v; }
+                float chk_raw = 0.0f, chk_out = 0.0f;  // x * 0 is NaN exactly when x is NaN or +-Inf
+#pragma unroll 2
+                for (int e = lane; e < total4; e += 32) {
+                    float4 q = src4[e];
+                    chk_raw = fmaf(q.x, 0.0f, fmaf(q.y, 0.0f, fmaf(q.z, 0.0f, fmaf(q.w, 0.0f, chk_raw))));
+                    if (norm) {
+                        const float nf = nfs[v];
+                        q.x = __fmul_rn(q.x, nf); q.y = __fmul_rn(q.y, nf); q.z = __fmul_rn(q.z, nf); q.w = __fmul_rn(q.w, nf);
+                        chk_out = fmaf(q.x, 0.0f, fmaf(q.y, 0.0f, fmaf(q.z, 0.0f, fmaf(q.w, 0.0f, chk_out))));
+                    }
+                    q.x = q.x < 0.0f ? 0.0f : q.x; q.y = q.y < 0.0f ? 0.0f : q.y;  // y[y < 0] = 0 (core.py:452)
+                    q.z = q.z < 0.0f ? 0.0f : q.z; q.w = q.w < 0.0f ? 0.0f : q.w;
+                    __stcs(out4 + e, q);
+                    j4 += 32;
+                    while (j4 >= q4) { j4 -= q4; ++v; }
+                }
+                if (chk_raw != 0.0f) st |= 1u;        // NaN != 0
+                else if (chk_out != 0.0f) st |= 2u;
+            }
+        } else if (nkeep) {
             const long long blk = v0 / PRE_BLOCK_VOX;
             long long pos0 = v0;
             if (p.mask) {  // rank of the chunk's first kept voxel: block prefix + kept voxels of the block before the chunk
