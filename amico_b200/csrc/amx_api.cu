@@ -730,9 +730,33 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     // (measured: for device-resident data one chunk on one stream is fastest -- per-chunk binning and smaller direction
     //  bins cost more than the ragged kernel ends -- so chunking defaults on for host buffers only, and the second
     //  compute stream stays an option, AMX_COMPUTE_STREAMS=2)
-    long long chunk = std::max(8192, env_int(host ? "AMX_HOST_CHUNK" : "AMX_DEVICE_CHUNK", host ? 262144 : 0x7fffffff));
-    if ((long long)n <= chunk + chunk / 2) chunk = (long long)n;
-    const long long n_chunks = ((long long)n + chunk - 1) / chunk;
+    //  Host buffers: the copy engine moves a voxel ~5x faster than the fit consumes it, so the chunks GROW geometrically
+    //  (n/16, n/4, rest): only the small first chunk's upload and the last chunk's download are exposed, and the stage
+    //  kernels see three ragged ends instead of one per fixed-size chunk.  AMX_HOST_CHUNK=<voxels> restores equal chunks.
+    std::vector<long long> bounds{0};
+    {
+        const long long fixed = env_int(host ? "AMX_HOST_CHUNK" : "AMX_DEVICE_CHUNK", host ? 0 : 0x7fffffff);
+        if (fixed > 0) {
+            const long long c = std::max<long long>(8192, fixed);
+            if ((long long)n <= c + c / 2) bounds.push_back((long long)n);
+            else for (long long o = c; ; o += c) { bounds.push_back(std::min<long long>(o, (long long)n)); if (o >= (long long)n) break; }
+        } else if ((long long)n < 131072) {
+            bounds.push_back((long long)n);
+        } else {
+            const long long first = std::max(2, env_int("AMX_HOST_FIRST", 16)), growth = std::max(1, env_int("AMX_HOST_GROWTH", 4));
+            long long c = (((long long)n / first) + 7) & ~7LL, o = 0;
+            for (;;) {
+                o += c;
+                if (o + c / 2 >= (long long)n) break;  // the last chunk takes the remainder
+                bounds.push_back(o);
+                c *= growth;
+            }
+            bounds.push_back((long long)n);
+        }
+    }
+    const long long n_chunks = (long long)bounds.size() - 1;
+    long long chunk = 0;
+    for (long long i = 0; i < n_chunks; ++i) chunk = std::max(chunk, bounds[i + 1] - bounds[i]);
     const int nset = n_chunks > 1 ? 2 : 1;
     const int ncs = (nset > 1 && env_int("AMX_COMPUTE_STREAMS", 1) > 1) ? 2 : 1;
     for (int b = 0; b < ncs; ++b) CK(pl->work[b].status.reserve(64));
@@ -768,7 +792,7 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     }
     for (long long i = 0; i < n_chunks; ++i) {
         const int b = (int)(i % nset), wb = (int)(i % ncs);
-        const size_t off = (size_t)(i * chunk), cnt = (size_t)std::min<long long>(chunk, (long long)n - i * chunk);
+        const size_t off = (size_t)bounds[i], cnt = (size_t)(bounds[i + 1] - bounds[i]);
         amx_fit_args c = d;
         c.n_vox = (int64_t)cnt;
         if (host) {
