@@ -95,7 +95,7 @@ struct amx_plan {
     float *d_icvf = nullptr, *d_kappa = nullptr;
     double *d_Rs = nullptr, *d_sandi_norms = nullptr, *d_d_in = nullptr, *d_d_isos = nullptr;
     cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
-    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr}, ev_lut[2] = {nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
     // per-launch workspace; two sets so that consecutive voxel chunks can be in flight on two compute streams
@@ -142,6 +142,7 @@ int plan_common_init(amx_plan *pl, int device)
         CK(cudaEventCreateWithFlags(&pl->ev_in[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pl->ev_comp[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&pl->ev_out[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&pl->ev_lut[i], cudaEventDisableTiming));
     }
     return AMX_OK;
 }
@@ -251,6 +252,7 @@ int amx_plan_destroy(amx_plan *pl)
         if (pl->ev_in[i]) cudaEventDestroy(pl->ev_in[i]);
         if (pl->ev_comp[i]) cudaEventDestroy(pl->ev_comp[i]);
         if (pl->ev_out[i]) cudaEventDestroy(pl->ev_out[i]);
+        if (pl->ev_lut[i]) cudaEventDestroy(pl->ev_lut[i]);
     }
     if (pl->stream) cudaStreamDestroy(pl->stream);
     if (pl->s_in) cudaStreamDestroy(pl->s_in);
@@ -526,7 +528,7 @@ int prepare_tables(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *la
 // Enqueue LUT index + binning + fit kernels for device-resident voxels; fully asynchronous (the tile count stays on the
 // device, the error / overflow words are read by the caller at the end).  All pointers are device pointers.
 int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStream_t st, int *launches, long long vox_offset,
-               bool record_events)
+               bool record_events, cudaEvent_t after_lut = nullptr)
 {
     const long long n_vox = a->n_vox;
     const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
@@ -594,6 +596,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         if (a->lut_out) CK(cudaMemsetAsync(a->lut_out, 0, (size_t)n_vox * sizeof(int), st));
     }
     if (record_events) CK(cudaEventRecord(pl->ev[1], st));
+    if (after_lut) CK(cudaEventRecord(after_lut, st));  // dirs are final (flipped) from here on
 
     FitParams p;
     memset(&p, 0, sizeof p);
@@ -797,7 +800,10 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
         c.n_vox = (int64_t)cnt;
         if (host) {
             amx_plan::Stage &sg = pl->stg[b];
-            if (i >= 2) CK(cudaStreamWaitEvent(s_in, pl->ev_comp[b], 0));  // inputs of this set consumed by chunk i-2
+            if (i >= 2) {
+                CK(cudaStreamWaitEvent(s_in, pl->ev_comp[b], 0));  // inputs of this set consumed by chunk i-2 ...
+                CK(cudaStreamWaitEvent(s_in, pl->ev_out[b], 0));   // ... and its flipped dirs (same buffer) read back
+            }
             CK(cudaMemcpyAsync(sg.y.p, (const char *)a->y + off * m * ysz, cnt * m * ysz, cudaMemcpyHostToDevice, s_in));
             if (a->dirs) CK(cudaMemcpyAsync(sg.dirs.p, a->dirs + off * 3, cnt * 3 * sizeof(double), cudaMemcpyHostToDevice, s_in));
             c.y = sg.y.p; c.estimates = (double *)sg.est.p;
@@ -824,15 +830,21 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             c.coeff_out = a->coeff_out ? a->coeff_out + off * pl->n : nullptr;
             c.lut_out = a->lut_out ? a->lut_out + off : nullptr;
         }
-        int rc = fit_device(pl, pl->work[wb], &c, cs[wb], &launches, (long long)off, i == 0);
+        const bool early_dirs = host && nset > 1 && a->dirs;
+        int rc = fit_device(pl, pl->work[wb], &c, cs[wb], &launches, (long long)off, i == 0, early_dirs ? pl->ev_lut[b] : nullptr);
         if (rc) { cudaDeviceSynchronize(); return rc; }
         if (host) {
+            // the reference flips DIRs in place (amico/lut.pyx:335-338): hand the flipped directions back -- as soon as the LUT
+            // kernel has flipped them, i.e. behind the fit instead of after it
+            if (early_dirs) {
+                CK(cudaStreamWaitEvent(s_out, pl->ev_lut[b], 0));
+                CK(cudaMemcpyAsync(a->dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            }
             if (nset > 1) {
                 CK(cudaEventRecord(pl->ev_comp[b], cs[wb]));
                 CK(cudaStreamWaitEvent(s_out, pl->ev_comp[b], 0));
             }
-            // the reference flips DIRs in place (amico/lut.pyx:335-338): hand the flipped directions back
-            if (a->dirs) CK(cudaMemcpyAsync(a->dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (a->dirs && !early_dirs) CK(cudaMemcpyAsync(a->dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             CK(cudaMemcpyAsync(a->estimates + off * nm, c.estimates, cnt * nm * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             if (c.rmse) CK(cudaMemcpyAsync(a->rmse + off, c.rmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             if (c.nrmse) CK(cudaMemcpyAsync(a->nrmse + off, c.nrmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));

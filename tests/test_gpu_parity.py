@@ -308,6 +308,21 @@ def test_chunked_host_pipeline_matches_single_shot(monkeypatch):
             plan.fit(P.y, np.array(P.DIRs), l1, l2)
 
 
+def test_default_geometric_host_schedule_matches_single_shot(monkeypatch):
+    """Default host schedule (chunks n/16, n/4, rest; flipped dirs copied back right after the LUT kernel) = one shot."""
+    P = synth.make_problem(1, n_vox=300000, seed=5)
+    l1, l2 = orc().DEFAULT_LAMBDAS["FreeWater"]
+    with make_plan(P) as plan:
+        d0 = np.array(P.DIRs)
+        a = plan.fit(P.y, d0, l1, l2, rmse=True, debug=True)
+        monkeypatch.setenv("AMX_HOST_CHUNK", "100000000")
+        d1 = np.array(P.DIRs)
+        b = plan.fit(P.y, d1, l1, l2, rmse=True, debug=True)
+    for k in ("estimates", "rmse", "lut", "x"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(d0, d1) and (d0[:, 1] >= 0).all()
+
+
 @pytest.mark.parametrize("env", [{"AMX_NODDI_SPLIT": "0"}, {"AMX_NODDI_BATCHED": "0"}, {"AMX_NODDI_BATCHED": "0", "AMX_NO_TMA": "1"},
                                  {"AMX_WARPS": "8"}, {"AMX_NODDI_W32": "1"}, {"AMX_NODDI_W32": "1", "AMX_W32_TILE": "64"}])
 def test_noddi_kernel_variants_agree(monkeypatch, env):
