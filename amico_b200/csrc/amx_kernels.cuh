@@ -225,6 +225,7 @@ struct FitParams {
     int cap_stage[3]; unsigned ws_doubles_stage[3];  // stage kernels: per-stage active-set capacity and workspace size
     int m_pad, dc_pad;
     int fast_lars;    // NODDI stage 2: throughput-oriented LARS (same path, fused arithmetic)
+    int compact3;     // NODDI stage 3: NNLS on the compact support system (one atom per lane) when the support fits a warp
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
     double *xiso;        // split NODDI path: [n_vox][2] (x_iso, x_dot) by sorted position
@@ -897,12 +898,42 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                         allowed |= ((w >> lane) & 1u) << s;
                         support += __popc(w);
                     }
-                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr, cap);
+                    int ov;
+                    const double *xf = ws.x;  // coefficients by atom index
+                    if (support <= 32 && p.compact3) {
+                        // compact system: lane q owns the q-th atom of the support (ascending atom order)
+                        int *map = (int *)ws.u;
+                        int q = lane, atom = 0;
+#pragma unroll
+                        for (int s = 0; s < NPL; ++s) {
+                            const unsigned w = p.supmask[(size_t)pos * NPL + s];
+                            const int cnt = __popc(w);
+                            if (q >= 0 && q < cnt) { atom = 32 * s + (int)__fns(w, 0, q + 1); q = -1; }
+                            else if (q >= 0) q -= cnt;
+                        }
+                        const double cq = lane < support ? ws.c1[atom] : 0.0;
+                        __syncwarp();
+                        map[lane] = atom;
+                        ws.c1[lane] = cq;  // c of the compact system, in place (every lane has read its entry)
+                        __syncwarp();
+                        ov = warp_nnls<1, true>(T1, p.ldT1, support, m, 3 * support, ws.c1, ws.x, lane < support ? 1u : 0u, ws.mat, ws.rd,
+                                                ws.P, lane, nullptr, cap, map);
+                        const double xq = lane < support ? ws.x[lane] : 0.0;
+                        __syncwarp();
+#pragma unroll
+                        for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = 0.0;
+                        __syncwarp();
+                        if (lane < support) ws.c1[atom] = xq;
+                        __syncwarp();
+                        xf = ws.c1;
+                    } else {
+                        ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr, cap);
+                    }
                     noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
-                                    (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
+                                    (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, xf, lane);
                     if (p.support_out && lane == 0) p.support_out[vox] = support;
                     if (p.coeff_out)
-                        for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
+                        for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = xf[j];
                     if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {
                         if (p.y_f64) {
                             const double *yg = (const double *)p.y + vox * m;
@@ -914,7 +945,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                             for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
                         }
                         __syncwarp();
-                        fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
+                        fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, xf, p.flags, p.rmse ? p.rmse + vox : nullptr,
                                             p.nrmse ? p.nrmse + vox : nullptr, lane);
                     }
                     if (ov) queue_slow(p, vox, lane);

@@ -49,10 +49,17 @@ struct NnlsStat {
 // min 1/2 x'Tx - c'x, x >= 0 over the atoms whose bit is set in `allowed` (bit s of lane l <-> atom
 // l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays.  mcap = number of rows of the
 // least-squares system (the reference stops growing the passive set at m).  Returns overflow flag.
-template <int NPL>
+// MAPPED (NPL must be 1): the system is the sub-system of T on the atoms map[0..n) (n <= 32, one per lane): c, x, P
+// live in that compact numbering and T is addressed through map -- NODDI stage 3, where the support holds ~10 of 145
+// atoms, so the dual pass touches one Gram entry per lane and row instead of NPL.
+template <int NPL, bool MAPPED = false>
 __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
-                         unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st, int cap = LC)
+                         unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st, int cap = LC,
+                         const int *map = nullptr)
 {
+    static_assert(!MAPPED || NPL == 1, "the mapped variant keeps one atom per lane");
+    auto AT = [&](int q) { return MAPPED ? map[q] : q; };  // compact index -> atom (= Gram table row / column)
+    const int mycol = MAPPED ? map[lane < n ? lane : 0] : 0;
     int np = 0, iter = 0, overflow = 0;
     cap = min(cap, c_lc_cap);
     unsigned inP = 0;
@@ -80,9 +87,9 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                 double gq[GD][NPL];
 #pragma unroll
                 for (int q = 0; q < GD; ++q) {
-                    const double *row = T + (size_t)P[min(k0 + q, np - 1)] * ldT;
+                    const double *row = T + (size_t)AT(P[min(k0 + q, np - 1)]) * ldT;
 #pragma unroll
-                    for (int s = 0; s < NPL; ++s) gq[q][s] = ((valid >> s) & 1u) ? row[lane + 32 * s] : 0.0;
+                    for (int s = 0; s < NPL; ++s) gq[q][s] = ((valid >> s) & 1u) ? row[MAPPED ? mycol : lane + 32 * s] : 0.0;
                 }
 #pragma unroll
                 for (int q = 0; q < GD; ++q) {
@@ -106,11 +113,11 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             warp_argmax(bv, bj);
             if (bj < 0 || !(bv > 0.0)) { j = -1; break; }
             j = bj;
-            double t = (lane < np) ? T[(size_t)P[lane] * ldT + j] : 0.0;
+            double t = (lane < np) ? T[(size_t)AT(P[lane]) * ldT + AT(j)] : 0.0;
             v = fwd_subst(Lp, rd, np, t, lane);
             double vv = warp_sum(lane < np ? v * v : 0.0);
             double vz = warp_sum(lane < np ? v * zl : 0.0);
-            d2 = T[(size_t)j * ldT + j] - vv;
+            d2 = T[(size_t)AT(j) * (ldT + 1)] - vv;
             // Lawson-Hanson's tests on the candidate: (i) independence, `unorm + 0.01 dd - unorm > 0` with unorm = |v|,
             // dd = sqrt(d2), i.e. 0.01 dd above half an ulp of unorm -- evaluated on the squares (1.2326e-28 =
             // (2^-53 / 0.01)^2) so that no square root is needed; (ii) the new coefficient z / dd must be positive, and
