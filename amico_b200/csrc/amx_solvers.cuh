@@ -592,29 +592,28 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
                 for (int s = 0; s < NPL; ++s) sl[s] = fma(gq[q][s], uj, sl[s]);
             }
         }
-        // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index
-        double tl[NPL];
-        double bt = INFINITY;
-        int bk = -1;
+        // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index.  Each lane first
+        // picks the best of its own atoms by cross-multiplication (|a/b| < |c/d| <=> |a| d < |c| b for b, d > 0), so only one
+        // reciprocal per lane and step is needed.
+        double bnum = 0.0, bden = 0.0;  // best candidate of this lane: step = bnum / bden (bden > 0), none while bden == 0
+        int mk = -1;                    // its atom; lanes without a candidate still offer their lowest atom (step = inf)
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
-            int k = lane + 32 * s;
-            tl[s] = INFINITY;
+            const int k = lane + 32 * s;
             if (k < K) {
-                if (!((act >> s) & 1u) && sl[s] < 1.0) tl[s] = (cc - DtR[k]) * __drcp_rn(1.0 - sl[s]);
-                double at = fabs(tl[s]);
-                if (bk < 0 || at < bt) { bt = at; bk = k; }
+                if (mk < 0) mk = k;
+                if (!((act >> s) & 1u) && sl[s] < 1.0) {
+                    const double num = cc - DtR[k], den = 1.0 - sl[s];
+                    if (bden == 0.0 || fabs(num) * bden < fabs(bnum) * den) { bnum = num; bden = den; mk = k; }
+                }
             }
         }
+        const double mine = bden != 0.0 ? bnum * __drcp_rn(bden) : INFINITY;
+        double bt = fabs(mine);
+        int bk = mk;
         warp_argmin<true>(bt, bk);
-        double step;
-        {
-            double mine = 0.0;
-#pragma unroll
-            for (int s = 0; s < NPL; ++s)
-                if (s == (bk >> 5)) mine = tl[s];
-            step = shfl(mine, bk & 31);
-        }
+        const double step0 = shfl(mine, bk & 31);  // lane (bk & 31) owns atom bk and offered exactly it
+        double step = step0;
         cur = bk;
         const double coeff1 = warp_sum(lane <= i ? sg * ul : 0.0);
         const double coeff2 = warp_sum(lane <= i ? dl * ul : 0.0);
