@@ -476,6 +476,21 @@ __device__ __noinline__ int warp_lars(const double *__restrict__ T, int ldT, dou
 // the small sums, reciprocal instead of division for the candidate steps.  Used by NODDI stage 2, where only the SUPPORT
 // of the (unique) elastic-net minimiser is consumed (amico/models.pyx:929-936) and its input already differs from the
 // CPU's at the 1e-12 level through stage 1.
+// sum_{c < n} M(r, c) v[c] for the packed symmetric matrix M (element (a, b), a >= b, at tri(a, b)); c runs uniformly over
+// the warp, the index needs one select: (c < r) ? tri(r, 0) + c : tri(c, 0) + r
+__device__ __forceinline__ double sym_row_dot(const double *Mi, int r, int n, const double *v)
+{
+    double acc = 0.0;
+    const int base = tri(r, 0);
+    int tc = 0;  // tri(c, 0)
+    #pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        acc = fma(Mi[c < r ? base + c : tc + r], v[c], acc);
+        tc += c + 1;
+    }
+    return acc;
+}
+
 template <int NPL>
 __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT, int K, int Ltrue, double lambda1, double *DtR,
                                            double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane, int cap = LC)
@@ -528,8 +543,7 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
             } else {
                 double ur = 0.0;
                 if (lane < i) {
-#pragma unroll 1
-                    for (int c = 0; c < i; ++c) ur = fma(sym_at(Mi, lane, c), gs[c], ur);
+                    ur = sym_row_dot(Mi, lane, i, gs);
                     u[lane] = ur;
                 }
                 const double dot = warp_sum(lane < i ? ur * g : 0.0);
@@ -556,8 +570,7 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         __syncwarp();
         double ul = 0.0;
         if (lane <= i) {
-#pragma unroll 1
-            for (int c = 0; c <= i; ++c) ul = fma(sym_at(Mi, lane, c), gs[c], ul);
+            ul = sym_row_dot(Mi, lane, i + 1, gs);
             u[lane] = ul;
         }
         __syncwarp();
