@@ -1,7 +1,7 @@
 import numpy as np, ctypes as C, sys, time
 from amico_b200 import synth
 from oracle import oracle as orc
-lib = C.CDLL('/root/repo/scratch/libgm.so')
+lib = C.CDLL(__import__('os').path.join(__import__('os').path.dirname(__import__('os').path.abspath(__file__)), 'libgm.so'))
 dp = C.POINTER(C.c_double)
 def P_(a): return a.ctypes.data_as(dp)
 n_vox = int(sys.argv[1]); mode = int(sys.argv[2])
