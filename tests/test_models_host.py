@@ -39,12 +39,22 @@ def test_default_grids():
     assert len(s.Rs) == 5 and len(s.d_in) == 5 and len(s.d_isos) == 5 and s.d_is == 3e-3
 
 
-def test_generate_and_resample_are_out_of_scope():
+def test_generate_is_out_of_scope_and_resample_needs_the_gpu(tmp_path):
     m = models.NODDI()
     with pytest.raises(NotImplementedError):
         m.generate(None, None, None, None, 500)
-    with pytest.raises(NotImplementedError):
-        m.resample(None, None, None, False, 500)
+    # resample is provided (GPU projection): without a device it must fail loudly, never fall back to the CPU
+    from amico_b200 import lut, synth
+    sch = synth.make_scheme(1)
+    fw = models.FreeWater()
+    fw.scheme = sch
+    idx_out, Ylm = lut.aux_structures_resample(sch, 12)
+    for i in range(11):
+        np.save(tmp_path / f"A_{i + 1:03d}.npy", np.zeros((3, Ylm.shape[1]) if i < 10 else (Ylm.shape[1],), np.float32))
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            fw.resample(str(tmp_path), idx_out, Ylm, False, 3)
 
 
 def test_kernels_model_id_is_checked():
