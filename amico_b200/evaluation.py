@@ -16,12 +16,16 @@ only.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import glob
+import os
+import pickle
 import time
 
 import numpy as np
 
 from . import _lib as L
 from . import models as _models
+from . import nifti as _nifti
 from .scheme import Scheme
 
 MIN_POSITIVE_SIGNAL = 0.0001  # dipy.reconst.dti.MIN_POSITIVE_SIGNAL
@@ -51,8 +55,10 @@ def _i32(a):
 class Evaluation:
     """GPU-resident counterpart of ``amico.core.Evaluation`` (``core.py:34-498``) for the load -> fit -> maps flow."""
 
-    def __init__(self, device=0):
+    def __init__(self, study_path=".", subject=".", output_path=None, device=0):
+        """``study_path`` / ``subject`` / ``output_path`` as in ``core.py:36-80``; ``device``: the CUDA device to use."""
         self.device = int(device)
+        self.niiDWI = None
         self.scheme = None
         self.model = None
         self.KERNELS = None
@@ -63,7 +69,8 @@ class Evaluation:
         self.niiMASK_img = None
         self._y = self._vox_idx = self._dirs = None
         self._dim = None
-        self.CONFIG = {}
+        self.CONFIG = {"version": "amico_b200", "study_path": study_path, "subject": subject,
+                       "DATA_path": os.path.join(study_path, subject), "OUTPUT_path": output_path}
         # defaults of core.py:82-96
         for k, v in (("peaks_filename", None), ("doNormalizeSignal", True), ("doKeepb0Intact", False), ("doComputeRMSE", False),
                      ("doComputeNRMSE", False), ("doSaveModulatedMaps", False), ("doSaveCorrectedDWI", False),
@@ -85,6 +92,30 @@ class Evaluation:
         lib = L.load()
         if self.get_config("doDebiasSignal"):
             raise NotImplementedError("doDebiasSignal (Rician debiasing, amico/core.py:201-207) is not part of the accelerated path")
+        data_path = self.get_config("DATA_path")
+        if isinstance(dwi, (str, os.PathLike)):  # file names relative to the subject folder, like core.py:132-141
+            fn = os.path.join(data_path, dwi)
+            if not os.path.isfile(fn):
+                raise FileNotFoundError("DWI file not found")
+            self.set_config("dwi_filename", dwi)
+            self.niiDWI = _nifti.load(fn)
+            dwi = self.niiDWI.get_fdata().astype(np.float32)
+            self.set_config("pixdim", self.niiDWI.zooms[:3])
+        if isinstance(scheme, (str, os.PathLike)):
+            fn = os.path.join(data_path, scheme)
+            if not os.path.isfile(fn):
+                raise FileNotFoundError("SCHEME file not found")
+            self.set_config("scheme_filename", scheme)
+            scheme = _nifti.load_scheme_table(fn)
+        if isinstance(mask, (str, os.PathLike)):
+            fn = os.path.join(data_path, mask)
+            if not os.path.isfile(fn):
+                raise FileNotFoundError("MASK file not found")
+            self.set_config("mask_filename", mask)
+            mask = _nifti.load(fn).get_fdata()
+        self.set_config("b0_thr", b0_thr)
+        self.set_config("b0_min_signal", b0_min_signal)
+        self.set_config("replace_bad_voxels", replace_bad_voxels)
         self.scheme = scheme if isinstance(scheme, Scheme) else Scheme(np.asarray(scheme), b0_thr)
         sch = self.scheme
         dev = torch.device("cuda", self.device)
@@ -303,3 +334,48 @@ class Evaluation:
             self.RESULTS[k] = a.reshape(self._dim + ((a.shape[1],) if k not in ("RMSE", "NRMSE") else ()))
         self._last_fit = res
         return self.RESULTS
+
+    # ------------------------------------------------------------------ save_results (core.py:501-648)
+    def save_results(self, path_suffix=None):
+        """Write ``config.pickle``, ``fit_dir.nii.gz``, ``fit_<map>.nii.gz`` (+ RMSE / NRMSE / modulated maps / corrected DWI)
+        with the reference's file names, header fields and output-folder rule."""
+        if self.RESULTS is None:
+            raise RuntimeError('Model not fitted to the data; call "fit()" first')
+        if self.get_config("OUTPUT_path") is None:
+            rel = os.path.join("AMICO", self.model.id) + (("_" + path_suffix) if path_suffix else "")
+            self.RESULTS["RESULTS_path"] = rel
+            out = os.path.join(self.get_config("DATA_path"), rel)
+        else:
+            out = self.get_config("OUTPUT_path") + (("_" + path_suffix) if path_suffix else "")
+            self.RESULTS["RESULTS_path"] = out
+        if not os.path.exists(out):
+            os.makedirs(out)
+        else:
+            for f in glob.glob(os.path.join(out, "*")):
+                os.remove(f)
+        with open(os.path.join(out, "config.pickle"), "wb+") as fid:
+            pickle.dump(self.CONFIG, fid, protocol=2)
+        like = self.niiDWI
+        ver = self.get_config("version")
+
+        def put(name, img, cal_min, cal_max, descrip=None):
+            _nifti.save(os.path.join(out, name), img, like=like, cal_min=cal_min, cal_max=cal_max, descrip=descrip)
+
+        R = self.RESULTS
+        if not self.get_config("doDirectionalAverage") and "DIRs" in R:
+            put("fit_dir.nii.gz", R["DIRs"], -1, 1)
+        if self.get_config("doComputeRMSE"):
+            put("fit_RMSE.nii.gz", R["RMSE"], 0, 1)
+        if self.get_config("doComputeNRMSE"):
+            put("fit_NRMSE.nii.gz", R["NRMSE"], 0, 1)
+        if self.get_config("doSaveCorrectedDWI") and self.model.name == "Free-Water":
+            put("DWI_corrected.nii.gz", R["DWI_corrected"], 0, 1)
+        for i, name in enumerate(self.model.maps_name):
+            img = R["MAPs"][:, :, :, i]
+            put(f"fit_{name}.nii.gz", img, img.min(), img.max(), f"{self.model.maps_descr[i]} (AMICO v{ver})")
+        if self.get_config("doSaveModulatedMaps") and self.model.name == "NODDI":
+            for i in range(2):
+                img = R["MAPs_mod"][:, :, :, i]
+                put(f"fit_{self.model.maps_name[i]}_modulated.nii.gz", img, img.min(), img.max(),
+                    f"{self.model.maps_descr[i]} modulated (AMICO v{ver})")
+        return out

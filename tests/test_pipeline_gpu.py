@@ -233,3 +233,40 @@ def test_evaluation_flow_sandi_directional_average():
     np.testing.assert_array_equal(ae.y, r["y"])
     assert ae.scheme.nS == 4
     np.testing.assert_array_equal(res["MAPs"], maps_ref)   # SANDI is bit-exact (float32 cast of equal float64 maps)
+
+
+def test_file_based_flow_and_save_results(tmp_path):
+    """DWI.nii.gz + DWI.scheme + mask.nii.gz in a subject folder -> load_data(file names) -> fit -> save_results: the same
+    maps as the array-based flow, written under AMICO/<model>/ with the reference's file names (core.py:501-648)."""
+    import os
+    from amico_b200 import nifti
+    P, dwi, mask = synth.make_raw_volume(1, (6, 7, 5), seed=21)
+    subj = tmp_path / "study" / "subj"
+    os.makedirs(subj)
+    A = np.diag([2.0, 2.0, 2.5, 1.0])
+    nifti.save(subj / "DWI.nii.gz", dwi, affine=A)
+    nifti.save(subj / "mask.nii", mask.astype(np.float32), affine=A)
+    np.savetxt(subj / "DWI.scheme", P.full_scheme.raw, fmt="%.8f", header="VERSION: BVECTOR", comments="")
+    ae = Evaluation(str(tmp_path / "study"), "subj")
+    ae.set_config("doComputeRMSE", True)
+    ae.load_data("DWI.nii.gz", "DWI.scheme", "mask.nii")
+    ae.set_model("FreeWater")
+    ae.load_kernels(P.KERNELS, P.htable)
+    res = ae.fit()
+    ref = Evaluation()
+    ref.set_config("doComputeRMSE", True)
+    ref.load_data(dwi, P.full_scheme.raw, mask)
+    ref.set_model("FreeWater")
+    ref.load_kernels(P.KERNELS, P.htable)
+    want = ref.fit()
+    np.testing.assert_array_equal(res["MAPs"], want["MAPs"])
+    out = ae.save_results()
+    assert out.endswith(os.path.join("AMICO", "FreeWater"))
+    names = sorted(os.listdir(out))
+    assert names == ["config.pickle", "fit_FW.nii.gz", "fit_FiberVolume.nii.gz", "fit_RMSE.nii.gz", "fit_dir.nii.gz"]
+    fw = nifti.load(os.path.join(out, "fit_FW.nii.gz"))
+    np.testing.assert_array_equal(fw.data, res["MAPs"][..., 1])
+    np.testing.assert_allclose(fw.affine, A)
+    assert fw.header[148:228].startswith(b"Isotropic free-water volume fraction (AMICO v")
+    d = nifti.load(os.path.join(out, "fit_dir.nii.gz"))
+    assert d.shape == (6, 7, 5, 3)
