@@ -422,7 +422,18 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3));
     // carve-out hint: what is not shared memory is L1 (Gram rows)
     CK(cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1 * 100 + 233471) / 233472 + 1)));
-    k1<<<grid, block, s1, st>>>(p);
+    // Stage 1's workspace is small (active sets <= 16): 32 warps fit next to ~90 KB of L1 when the kernel is compiled for
+    // 1024 threads (64 registers, a few spilled words); more resident warps hide the L2 latency of the Gram rows.
+    const int w1 = env_int("AMX_STAGE1_WARPS", 32);
+    const size_t s1w = fixed + (size_t)p.ws_doubles_stage[0] * 8 * 32;
+    if (MAXT == 768 && block == 768 && w1 == 32 && s1w <= 227 * 1024) {
+        auto k1w = k_noddi_stage<1, NPL, float, 1024>;
+        CK(cudaFuncSetAttribute(k1w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1w));
+        CK(cudaFuncSetAttribute(k1w, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1w * 100 + 233471) / 233472 + 1)));
+        k1w<<<grid, 1024, s1w, st>>>(p);
+    } else {
+        k1<<<grid, block, s1, st>>>(p);
+    }
     k2<<<grid, block, s2, st>>>(p);
     k3<<<grid, block, s3, st>>>(p);
     CK(cudaGetLastError());
@@ -656,7 +667,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count));
     }
     if (p.batched) {
-        CK(wk.scratch.reserve((size_t)grid * std::max(nwarps, w32 ? 12 : 0) * std::max(2 * BV, w32 ? 32 : 0) * p.NA * sizeof(double)));
+        CK(wk.scratch.reserve((size_t)grid * 32 * std::max(2 * BV, w32 ? 32 : 0) * p.NA * sizeof(double)));
         p.scratch = (double *)wk.scratch.p;
         CK(wk.xiso.reserve((size_t)n_vox * 2 * sizeof(double)));
         CK(wk.supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));

@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
     WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles_stage[STAGE - 1], p.NA, p.m_pad, p.dc_pad, 1, cap);
     constexpr int NT = 4 * NPL, TP = (MAXT > 512 && NT % 2 == 0) ? NT / 2 : NT;
     const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
-    double *scr = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)BV * NA;
+    double *scr = p.scratch + ((size_t)blockIdx.x * 32 + warp) * (size_t)BV * NA;  // 32 = most warps any stage launches
     const int g = lane >> 2;
     unsigned all = 0;
 #pragma unroll
