@@ -577,6 +577,17 @@ int pick_device(int device, int *sm_count, int *max_smem)
         return amx::set_error(AMX_E_CUDA, "no CUDA device available (%s): amico_b200 has no CPU fallback", cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return amx::set_error(AMX_E_INVALID, "device %d out of range (0..%d)", device, ndev - 1);
     AMX_CK(cudaSetDevice(device));
+    {   // stream-ordered temporaries: keep freed blocks in the pool across synchronisations (default: trimmed at every sync)
+        static bool pool_set[64];
+        if (!pool_set[device & 63]) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+                unsigned long long keep = 1ull << 30;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_set[device & 63] = true;
+        }
+    }
     AMX_CK(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, device));
     AMX_CK(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     return AMX_OK;

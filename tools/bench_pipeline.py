@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def measure(cfg=2, steps=5, warmup=2, n_vox=None, P=None):
+def measure(cfg=2, steps=5, warmup=3, n_vox=None, P=None):
     import torch
     from amico_b200 import _lib as L
     from amico_b200 import synth
