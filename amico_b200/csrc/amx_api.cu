@@ -166,8 +166,10 @@ int build_gram(amx_plan *pl, double **G, int K, int *ld, size_t *stride, const i
 {
     *ld = (K + 3) & ~3;
     *stride = (size_t)K * *ld;
-    CK(cudaMalloc((void **)G, (size_t)pl->ndirs * *stride * sizeof(double)));
-    CK(cudaMemsetAsync(*G, 0, (size_t)pl->ndirs * *stride * sizeof(double), pl->stream));
+    // + 256 doubles: the warp solvers read whole 32-lane column groups of a row without bounds predicates, i.e. up to
+    // 32 * NPL - K entries past a row's end (the next row; past the very last row: this zero padding)
+    CK(cudaMalloc((void **)G, ((size_t)pl->ndirs * *stride + 256) * sizeof(double)));
+    CK(cudaMemsetAsync(*G, 0, ((size_t)pl->ndirs * *stride + 256) * sizeof(double), pl->stream));
     int by = std::max(1, std::min(64, (K * K + 8 * 256 - 1) / (8 * 256)));
     dim3 grid(pl->ndirs, by);
     if (pl->slab_f64)

@@ -89,7 +89,8 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                 for (int q = 0; q < GD; ++q) {
                     const double *row = T + (size_t)AT(P[min(k0 + q, np - 1)]) * ldT;
 #pragma unroll
-                    for (int s = 0; s < NPL; ++s) gq[q][s] = ((valid >> s) & 1u) ? row[MAPPED ? mycol : lane + 32 * s] : 0.0;
+                    for (int s = 0; s < NPL; ++s) gq[q][s] = row[MAPPED ? mycol : lane + 32 * s];  // slots that are not `valid` pick up
+                                                                                                // finite garbage nobody reads (table is padded)
                 }
 #pragma unroll
                 for (int q = 0; q < GD; ++q) {
@@ -596,7 +597,8 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
             for (int q = 0; q < GD; ++q) {
                 const double *row = T + (size_t)ind[min(j0 + q, i)] * ldT + lane;
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) gq[q][s] = (lane + 32 * s < K) ? row[32 * s] : 0.0;
+                for (int s = 0; s < NPL; ++s) gq[q][s] = row[32 * s];  // columns >= K: finite values of the next row / the padding,
+                                                                       // only ever combined into slots that are masked by k < K
             }
 #pragma unroll
             for (int q = 0; q < GD; ++q) {
