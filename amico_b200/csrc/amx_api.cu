@@ -643,7 +643,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         p.cap_stage[0] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE1", 16)));
         p.cap_stage[1] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE2", LC)));
         p.cap_stage[2] = std::max(4, std::min(LC, env_int("AMX_CAP_STAGE3", LC)));
-        for (int k = 0; k < 3; ++k) p.ws_doubles_stage[k] = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, 1, p.cap_stage[k]);
+        for (int k = 0; k < 3; ++k) p.ws_doubles_stage[k] = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, (k == 1 && p.fast_lars) ? 2 : 1, p.cap_stage[k]);
     }
     const size_t ws_bytes = (size_t)p.ws_doubles * sizeof(double);
     const size_t budget = (size_t)pl->max_smem;

@@ -248,7 +248,7 @@ constexpr int BV = 8;  // voxels per DMMA micro-batch (the M of m8n8k4)
 // holds more than ~8 passive atoms -- because every KB of shared memory given back is L1 for the Gram rows
 __host__ __device__ inline unsigned ws_doubles_for(int NA, int m_pad, int dc_pad, int alias = 0, int cap = LC)
 {
-    return (alias ? 2u : 3u) * NA + (unsigned)(cap * (cap + 1) / 2) + 3u * cap + (unsigned)((cap + 1) / 2) + 3 * BV + m_pad + dc_pad;
+    return (alias == 2 ? 1u : alias ? 2u : 3u) * NA + (unsigned)(cap * (cap + 1) / 2) + 3u * cap + (unsigned)((cap + 1) / 2) + 3 * BV + m_pad + dc_pad;
 }
 
 __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_pad, int alias = 0, int cap = LC)
@@ -256,7 +256,7 @@ __device__ __forceinline__ WarpWS carve(double *base, int NA, int m_pad, int dc_
     WarpWS w;
     w.c1 = base; base += NA;
     w.dtr = alias ? w.c1 : base; base += alias ? 0 : NA;
-    w.x = base; base += NA;
+    w.x = alias == 2 ? w.c1 : base; base += alias == 2 ? 0 : NA;  // alias 2 (NODDI stage 2): no coefficient vector at all
     w.mat = base; base += cap * (cap + 1) / 2;
     w.rd = base; base += cap;
     w.u = base; base += cap;
@@ -823,7 +823,8 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int cap = p.cap_stage[STAGE - 1];
-    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles_stage[STAGE - 1], p.NA, p.m_pad, p.dc_pad, 1, cap);
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles_stage[STAGE - 1], p.NA, p.m_pad, p.dc_pad,
+                      (STAGE == 2 && p.fast_lars) ? 2 : 1, cap);
     constexpr int NT = 4 * NPL, TP = (MAXT > 512 && NT % 2 == 0) ? NT / 2 : NT;
     const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
     double *scr = p.scratch + ((size_t)blockIdx.x * 32 + warp) * (size_t)BV * NA;  // 32 = most warps any stage launches
@@ -858,16 +859,26 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
-                int ov = p.fast_lars
-                             ? warp_lars_fast<NPL>(T2, p.ldT2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat, ws.u,
-                                                   ws.gs, ws.P, ws.x, lane, cap)
-                             : warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat,
-                                              ws.u, ws.gs, ws.P, ws.x, lane, nullptr, cap);
+                int ov;
+                if (p.fast_lars) {  // the support comes back as bit words: no coefficient vector in shared memory
+                    unsigned sup[NPL];
+                    ov = warp_lars_fast<NPL>(T2, p.ldT2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat, ws.u, ws.gs,
+                                             ws.P, nullptr, lane, cap, sup);
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) {
-                    const int j = lane + 32 * s;
-                    const unsigned w = __ballot_sync(FULL, (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n));
-                    if (lane == s) p.supmask[(size_t)(tile.y + v) * NPL + s] = w;
+                    for (int s = 0; s < NPL; ++s) {
+                        const int j = lane + 32 * s;
+                        const unsigned w = sup[s] | __ballot_sync(FULL, j >= n_wm && j < n);  // dot / iso columns always belong
+                        if (lane == s) p.supmask[(size_t)(tile.y + v) * NPL + s] = w;
+                    }
+                } else {
+                    ov = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr, ws.bx[v], ws.mat, ws.u,
+                                        ws.gs, ws.P, ws.x, lane, nullptr, cap);
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        const int j = lane + 32 * s;
+                        const unsigned w = __ballot_sync(FULL, (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n));
+                        if (lane == s) p.supmask[(size_t)(tile.y + v) * NPL + s] = w;
+                    }
                 }
                 if (ov) queue_slow(p, (long long)p.order[tile.y + v], lane);
                 __syncwarp();

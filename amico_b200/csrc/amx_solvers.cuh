@@ -494,14 +494,21 @@ __device__ __forceinline__ double sym_row_dot(const double *Mi, int r, int n, co
 
 template <int NPL>
 __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT, int K, int Ltrue, double lambda1, double *DtR,
-                                           double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane, int cap = LC)
+                                           double normX, double *Mi, double *u, double *gs, int *ind, double *x, int lane, int cap,
+                                           unsigned (&sup)[NPL])
 {
+    // Result: sup[s] bit l set <=> atom l + 32 s ends with a positive coefficient (all lanes hold the words); when x is
+    // not NULL the coefficients are also written there (exact zeros off-support).
     cap = min(cap, c_lc_cap);
     int L = Ltrue < K ? Ltrue : K;
     int overflow = 0;
 #pragma unroll
-    for (int s = 0; s < NPL; ++s) x[lane + 32 * s] = 0.0;
-    __syncwarp();
+    for (int s = 0; s < NPL; ++s) sup[s] = 0u;
+    if (x) {
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) x[lane + 32 * s] = 0.0;
+        __syncwarp();
+    }
     if (L <= 0) return 0;
     int cur;
     {
@@ -683,8 +690,15 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         }
         if (iter >= length_path - 1 || fabs(step) < 1e-15 || step == step_max2 || normX < 1e-15 || i == L - 1) break;
     }
-    if (lane < na && ind_l >= 0) x[ind_l] = coef_l;
-    __syncwarp();
+    {
+        const bool on = lane < na && ind_l >= 0 && coef_l > 0.0;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) sup[s] = __reduce_or_sync(FULL, (on && (ind_l >> 5) == s) ? (1u << (ind_l & 31)) : 0u);
+    }
+    if (x) {
+        if (lane < na && ind_l >= 0) x[ind_l] = coef_l;
+        __syncwarp();
+    }
     return overflow;
 }
 
