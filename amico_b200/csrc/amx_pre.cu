@@ -555,6 +555,38 @@ __global__ void __launch_bounds__(256) k_resample(const float *__restrict__ KRlm
     }
 }
 
+
+// ---- on-disk volume -> voxel-major float32 ------------------------------------------------------------------------
+// A NIfTI image stores x fastest and the volume index slowest: memory [nS][n_total].  The fit wants each voxel's nS
+// values contiguous: [n_total][nS].  Classic tiled transpose through shared memory (both sides coalesced), fused with the
+// dtype conversion and the header's slope / intercept (nibabel's get_fdata computes raw * slope + inter in float64; the
+// reference then casts to float32, amico/core.py:136): same two roundings here.
+template <typename T>
+__global__ void __launch_bounds__(256) k_to_voxel_major(const T *__restrict__ src, long long n_total, int nS, double slope, double inter,
+                                                        int scale, float *__restrict__ dst)
+{
+    __shared__ float tile[32][33];
+    const long long v0 = (long long)blockIdx.x * 32;
+    const int s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int sI = s0 + r;
+        const long long v = v0 + tx;
+        if (sI < nS && v < n_total) {
+            const T raw = src[(long long)sI * n_total + v];
+            tile[r][tx] = scale ? (float)((double)raw * slope + inter) : (float)raw;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const long long v = v0 + r;
+        const int sI = s0 + tx;
+        if (sI < nS && v < n_total) dst[v * nS + sI] = tile[tx][r];
+    }
+}
+
 // ---- host helpers ------------------------------------------------------------------------------------------------------
 struct Tmp {  // stream-ordered temporaries
     cudaStream_t s;
@@ -905,6 +937,56 @@ int amx_resample_kernels(int device, int space, const float *KRlm, int64_t n_row
     AMX_CK(cudaGetLastError());
     if (host) AMX_CK(cudaMemcpyAsync(out, d_o, (size_t)n_rows * nS_out * sizeof(float), cudaMemcpyDeviceToHost, s));
     AMX_CK(cudaStreamSynchronize(s));
+    return AMX_OK;
+}
+
+int amx_volume_to_voxel_major(int device, int space, const void *src, int nifti_datatype, int64_t n_total, int nS, double scl_slope,
+                              double scl_inter, float *dst, void *stream)
+{
+    if (!src || !dst || n_total <= 0 || nS <= 0) return amx::set_error(AMX_E_INVALID, "bad arguments");
+    size_t esz;
+    switch (nifti_datatype) {
+        case 2: case 256: esz = 1; break;
+        case 4: case 512: esz = 2; break;
+        case 8: case 16: case 768: esz = 4; break;
+        case 64: esz = 8; break;
+        default: return amx::set_error(AMX_E_INVALID, "unsupported NIfTI datatype %d", nifti_datatype);
+    }
+    int rc, sm = 0, max_smem = 0;
+    if ((rc = pick_device(device, &sm, &max_smem))) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tmp tmp(s);
+    const bool host = space == AMX_SPACE_HOST;
+    const void *d_src = src;
+    float *d_dst = dst;
+    if (host) {
+        void *a = nullptr;
+        float *o = nullptr;
+        AMX_CK(tmp.alloc(&a, (size_t)n_total * nS * esz));
+        AMX_CK(tmp.alloc((void **)&o, (size_t)n_total * nS * sizeof(float)));
+        AMX_CK(cudaMemcpyAsync(a, src, (size_t)n_total * nS * esz, cudaMemcpyHostToDevice, s));
+        d_src = a; d_dst = o;
+    }
+    // nibabel applies the scaling only when it is meaningful (finite, slope != 0, not the identity)
+    const int scale = std::isfinite(scl_slope) && std::isfinite(scl_inter) && scl_slope != 0.0 && (scl_slope != 1.0 || scl_inter != 0.0);
+    dim3 grid((unsigned)((n_total + 31) / 32), (unsigned)((nS + 31) / 32));
+#define AMX_TVM(T) k_to_voxel_major<T><<<grid, 256, 0, s>>>((const T *)d_src, n_total, nS, scl_slope, scl_inter, scale, d_dst)
+    switch (nifti_datatype) {
+        case 2: AMX_TVM(unsigned char); break;
+        case 256: AMX_TVM(signed char); break;
+        case 4: AMX_TVM(short); break;
+        case 512: AMX_TVM(unsigned short); break;
+        case 8: AMX_TVM(int); break;
+        case 768: AMX_TVM(unsigned int); break;
+        case 16: AMX_TVM(float); break;
+        default: AMX_TVM(double); break;
+    }
+#undef AMX_TVM
+    AMX_CK(cudaGetLastError());
+    if (host) {
+        AMX_CK(cudaMemcpyAsync(dst, d_dst, (size_t)n_total * nS * sizeof(float), cudaMemcpyDeviceToHost, s));
+        AMX_CK(cudaStreamSynchronize(s));
+    }
     return AMX_OK;
 }
 

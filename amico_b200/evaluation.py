@@ -99,7 +99,7 @@ class Evaluation:
                 raise FileNotFoundError("DWI file not found")
             self.set_config("dwi_filename", dwi)
             self.niiDWI = _nifti.load(fn)
-            dwi = self.niiDWI.get_fdata().astype(np.float32)
+            dwi = self.niiDWI  # stays in its on-disk dtype and order: converted and transposed on the GPU below
             self.set_config("pixdim", self.niiDWI.zooms[:3])
         if isinstance(scheme, (str, os.PathLike)):
             fn = os.path.join(data_path, scheme)
@@ -119,18 +119,41 @@ class Evaluation:
         self.scheme = scheme if isinstance(scheme, Scheme) else Scheme(np.asarray(scheme), b0_thr)
         sch = self.scheme
         dev = torch.device("cuda", self.device)
-        if isinstance(dwi, torch.Tensor):
-            vol = dwi.to(device=dev, dtype=torch.float32).contiguous()
+        # Voxel order inside the pipeline: C order (z fastest) for arrays, the file's own order (x fastest) for NIfTI input --
+        # voxels are independent, so only the flattening of the mask and the final reshape of the volumes depend on it.
+        self._forder = isinstance(dwi, _nifti.NiftiImage)
+        if self._forder:
+            img = dwi
+            if img.ndim != 4:
+                raise ValueError("DWI file is not a 4D image")
+            if sch.nS != img.shape[3]:
+                raise ValueError("Scheme does not match with DWI data")
+            self._dim = tuple(int(d) for d in img.shape[:3])
+            n_total = int(np.prod(self._dim))
+            code = {v: k for k, v in _nifti._DTYPES.items()}[img.data.dtype.type]
+            raw = np.ascontiguousarray(img.data.ravel(order="K")).view(np.uint8)  # the data block as stored: [nS][n_total]
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")  # read-only buffer: it is only copied to the device
+                d_raw = torch.from_numpy(raw).to(dev)
+            vol = torch.empty((n_total, sch.nS), dtype=torch.float32, device=dev)
+            L.check(lib.amx_volume_to_voxel_major(self.device, L.SPACE_DEVICE, d_raw.data_ptr(), code, n_total, sch.nS, img.scl_slope,
+                                                  img.scl_inter, vol.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+            del d_raw
         else:
-            host = np.ascontiguousarray(dwi, dtype=np.float32)  # core.py:136
-            vol = torch.from_numpy(host).to(dev, non_blocking=False)
-        if vol.ndim != 4:
-            raise ValueError("DWI file is not a 4D image")
-        if sch.nS != vol.shape[3]:
-            raise ValueError("Scheme does not match with DWI data")
-        self._dim = tuple(int(s) for s in vol.shape[:3])
+            if isinstance(dwi, torch.Tensor):
+                vol = dwi.to(device=dev, dtype=torch.float32).contiguous()
+            else:
+                host = np.ascontiguousarray(dwi, dtype=np.float32)  # core.py:136
+                vol = torch.from_numpy(host).to(dev, non_blocking=False)
+            if vol.ndim != 4:
+                raise ValueError("DWI file is not a 4D image")
+            if sch.nS != vol.shape[3]:
+                raise ValueError("Scheme does not match with DWI data")
+            self._dim = tuple(int(s) for s in vol.shape[:3])
+            n_total = int(np.prod(self._dim))
         self.set_config("dim", self._dim)
-        n_total = int(np.prod(self._dim))
+        order = "F" if self._forder else "C"
         if mask is not None:
             mask_img = np.asarray(mask).astype(np.uint8)  # core.py:181
             if mask_img.ndim != 3:
@@ -138,7 +161,7 @@ class Evaluation:
             if mask_img.shape != self._dim:
                 raise ValueError("MASK geometry does not match with DWI data")
             n_kept = int(np.count_nonzero(mask_img == 1))
-            d_mask = torch.from_numpy(np.ascontiguousarray(mask_img).reshape(-1)).to(dev)
+            d_mask = torch.from_numpy(np.ascontiguousarray(mask_img.reshape(-1, order=order))).to(dev)
         else:
             mask_img = np.ones(self._dim)  # core.py:190
             n_kept, d_mask = n_total, None
@@ -190,7 +213,7 @@ class Evaluation:
         self._y = y[:n_kept]
         self._vox_idx = vox_idx[:n_kept]
         self._mean_b0s_dev = mean_b0s
-        self.mean_b0s = None if mean_b0s is None else mean_b0s.cpu().numpy().reshape(self._dim)
+        self.mean_b0s = None if mean_b0s is None else mean_b0s.cpu().numpy().reshape(self._dim, order=order)
         self._dirs = None
         self._fit_scheme = sch
         if flags & L.PRE_DIR_AVG:
@@ -232,11 +255,21 @@ class Evaluation:
     @property
     def y(self):
         """``evaluation.y`` of the reference (n_vox, m) float64 -- downloaded on demand."""
-        return None if self._y is None else self._y.cpu().numpy().astype(np.float64)
+        return None if self._y is None else self._rows_in_reference_order(self._y.cpu().numpy().astype(np.float64))
+
+    def _rows_in_reference_order(self, rows):
+        """Per-voxel rows in the reference's order (C-order scan of the mask); identity unless the volume came from a file."""
+        if not getattr(self, "_forder", False):
+            return rows
+        f = self._vox_idx.cpu().numpy().astype(np.int64)  # flat index with x fastest
+        X, Y, Z = self._dim
+        x, yz = f % X, f // X
+        c = (x * Y + yz % Y) * Z + yz // Y
+        return rows[np.argsort(c, kind="stable")]
 
     @property
     def DIRs(self):
-        return None if self._dirs is None else self._dirs.cpu().numpy()
+        return None if self._dirs is None else self._rows_in_reference_order(self._dirs.cpu().numpy())
 
     def _dti_weights(self):
         sch = self._fit_scheme
@@ -331,7 +364,12 @@ class Evaluation:
         self.RESULTS = {}
         for k, v in out.items():
             a = v.cpu().numpy()
-            self.RESULTS[k] = a.reshape(self._dim + ((a.shape[1],) if k not in ("RMSE", "NRMSE") else ()))
+            tail = (a.shape[1],) if k not in ("RMSE", "NRMSE") else ()
+            if self._forder:  # memory [z][y][x][c] -> logical (x, y, z, c) as a view
+                a = a.reshape(self._dim[::-1] + tail)
+                self.RESULTS[k] = a.transpose((2, 1, 0, 3) if tail else (2, 1, 0))
+            else:
+                self.RESULTS[k] = a.reshape(self._dim + tail)
         self._last_fit = res
         return self.RESULTS
 

@@ -221,6 +221,14 @@ int amx_resample_kernels(int device, int space, const float *KRlm, int64_t n_row
                          const int32_t *idx_out, int dwi_count, const int32_t *merge_idx, int nS_out, int nS, float *out,
                          void *stream);
 
+/* On-disk image -> the layout the fit wants.  src: the NIfTI data block as stored, memory order [nS][n_total] (x fastest,
+ * volume index slowest), element type `nifti_datatype` (NIfTI-1 codes: 2 uint8, 4 int16, 8 int32, 16 float32, 64 float64,
+ * 256 int8, 512 uint16, 768 uint32); dst: float32 [n_total][nS] (voxels in the file's own x-fastest order).  Applies
+ * `raw * scl_slope + scl_inter` in float64 when the header's scaling is meaningful, then rounds to float32 -- what
+ * `nibabel.load(...).get_fdata().astype(np.float32)` yields at amico/core.py:135-136. */
+int amx_volume_to_voxel_major(int device, int space, const void *src, int nifti_datatype, int64_t n_total, int nS,
+                              double scl_slope, double scl_inter, float *dst, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -260,6 +260,9 @@ def test_file_based_flow_and_save_results(tmp_path):
     ref.load_kernels(P.KERNELS, P.htable)
     want = ref.fit()
     np.testing.assert_array_equal(res["MAPs"], want["MAPs"])
+    np.testing.assert_array_equal(res["RMSE"], want["RMSE"])
+    np.testing.assert_array_equal(ae.y, ref.y)          # rows come back in the reference's C-scan order
+    np.testing.assert_array_equal(ae.mean_b0s, ref.mean_b0s)
     out = ae.save_results()
     assert out.endswith(os.path.join("AMICO", "FreeWater"))
     names = sorted(os.listdir(out))
@@ -270,3 +273,49 @@ def test_file_based_flow_and_save_results(tmp_path):
     assert fw.header[148:228].startswith(b"Isotropic free-water volume fraction (AMICO v")
     d = nifti.load(os.path.join(out, "fit_dir.nii.gz"))
     assert d.shape == (6, 7, 5, 3)
+
+
+@pytest.mark.parametrize("dtype,code,slope,inter", [(np.float32, 16, 1.0, 0.0), (np.int16, 4, 0.37, 11.5), (np.uint8, 2, float("nan"), 0.0),
+                                                    (np.uint16, 512, 2.0, 0.0), (np.float64, 64, 1.0, 0.0), (np.int32, 8, 0.0, 5.0)])
+def test_volume_to_voxel_major_matches_numpy(dtype, code, slope, inter):
+    """On-disk block [nS][n_total] of any NIfTI dtype -> float32 [n_total][nS], scaling like nibabel's get_fdata + astype."""
+    lib = L.load()
+    rng = np.random.default_rng(3)
+    n_total, nS = 1000, 37      # neither a multiple of the 32 x 32 tile
+    info = np.iinfo(dtype) if np.issubdtype(dtype, np.integer) else None
+    src = (rng.integers(max(info.min, -3000), min(info.max, 3000), (nS, n_total)).astype(dtype) if info
+           else (rng.standard_normal((nS, n_total)) * 100).astype(dtype))
+    dst = np.zeros((n_total, nS), np.float32)
+    rc = lib.amx_volume_to_voxel_major(0, L.SPACE_HOST, src.ctypes.data, code, n_total, nS, slope, inter, dst.ctypes.data, None)
+    assert rc == 0, lib.amx_last_error()
+    f = src.astype(np.float64)
+    if np.isfinite(slope) and np.isfinite(inter) and slope != 0 and (slope != 1 or inter != 0):
+        f = f * slope + inter
+    np.testing.assert_array_equal(dst, f.astype(np.float32).T)
+
+
+def test_file_based_flow_int16_scaled(tmp_path):
+    """An int16 image with scl_slope / scl_inter goes through the same flow as its float32 array."""
+    import os
+    import struct
+    from amico_b200 import nifti
+    P, dwi, mask = synth.make_raw_volume(1, (5, 6, 4), seed=8)
+    q = np.round(dwi / 0.25).astype(np.int16)            # quantised: raw * 0.25 reproduces a float32-exact volume
+    vol = (q.astype(np.float64) * 0.25).astype(np.float32)
+    hdr = bytearray(348)
+    struct.pack_into("<i", hdr, 0, 348)
+    struct.pack_into("<8h", hdr, 40, 4, 5, 6, 4, q.shape[3], 1, 1, 1)
+    struct.pack_into("<h", hdr, 70, 4)
+    struct.pack_into("<h", hdr, 72, 16)
+    struct.pack_into("<8f", hdr, 76, 1, 2, 2, 2, 1, 1, 1, 1)
+    struct.pack_into("<f", hdr, 108, 352.0)
+    struct.pack_into("<f", hdr, 112, 0.25)
+    hdr[344:348] = b"n+1\0"
+    os.makedirs(tmp_path / "s")
+    with open(tmp_path / "s" / "DWI.nii", "wb") as f:
+        f.write(bytes(hdr) + bytes(4) + q.tobytes(order="F"))
+    ae = Evaluation(str(tmp_path), "s")
+    ae.load_data("DWI.nii", P.full_scheme.raw, mask)
+    ref = Evaluation()
+    ref.load_data(vol, P.full_scheme.raw, mask)
+    np.testing.assert_array_equal(ae.y, ref.y)
