@@ -10,7 +10,7 @@ reference hands to ``model.fit(evaluation)``:
                         181x181 one-degree hash table with the semantics of
                         ``amico/directions/htable_ndirs=*.bin`` (nearest LUT
                         direction by |dot|; checked against the reference's own
-                        500-direction table in ``tests/test_synth.py``);
+                        500-direction table in ``tests/test_oracle_cpu.py``);
 * ``make_kernels``   -- the ``KERNELS`` dict of each model's ``resample``
                         (``amico/models.pyx:754-792, 1113-1144, 482-523, 1446-1486``);
 * ``make_voxels``    -- ``y`` (float32-valued, >= 0) and unit ``DIRs``.
@@ -436,13 +436,15 @@ class Problem:
     DIRs: np.ndarray = field(default=None)
 
 
-def make_problem(cfg, n_vox=None, ndirs=500, model=None, seed=None, snr=30.0):
+def make_problem(cfg, n_vox=None, ndirs=500, model=None, seed=None, snr=30.0, lut_dirs=None, htable=None):
+    """``lut_dirs`` / ``htable``: use this direction set and hash table (e.g. the reference's own ``directions/*.bin``)
+    instead of the synthetic half-sphere set."""
     model = model or CONFIGS[cfg][0]
     scheme = make_scheme(cfg)
     if model == "SANDI":
         scheme = directional_average_scheme(scheme)
-    lut = lut_directions(ndirs)
-    ht = build_htable(lut)
+    lut = lut_directions(ndirs) if lut_dirs is None else np.ascontiguousarray(lut_dirs, dtype=np.float64)
+    ht = build_htable(lut) if htable is None else np.ascontiguousarray(htable, dtype=np.int16)
     K, p = make_kernels(model, scheme, lut)
     if n_vox is None:
         n_vox = int(np.prod(CONFIGS[cfg][1]))

@@ -43,9 +43,30 @@ def input_digest(P):
     return h.hexdigest()
 
 
+def reference_tables(ndirs=500):
+    """The reference's own LUT direction set and hash table (amico/directions/*.bin), read the way amico/lut.pyx:50-91 does."""
+    d = os.path.join("/root/reference", "amico", "directions")
+    dirs = np.fromfile(os.path.join(d, "ndirs=%d.bin" % ndirs), dtype=np.float64).reshape(ndirs, 3)
+    ht = np.fromfile(os.path.join(d, "htable_ndirs=%d.bin" % ndirs), dtype=np.int16)
+    return dirs, ht
+
+
+def refdirs_case():
+    """NODDI cfg2 on the reference's REAL 500-direction set + hash table: the fixture carries both tables, test directions
+    that include every degree-grid edge case, and the reference fit's maps."""
+    dirs, ht = reference_tables(500)
+    P = synth.make_problem(2, n_vox=384, seed=77, lut_dirs=dirs, htable=ht)
+    res = ref_runner.fit_problem(P, nthreads=2, rmse=True)
+    out = {k: np.asarray(v) for k, v in res.items()}
+    out.update(lut_dirs=dirs, htable=ht, input_sha256=np.array(input_digest(P)))
+    np.savez_compressed(os.path.join(HERE, "noddi_refdirs500.npz"), **out)
+    print("noddi_refdirs500", {k: v.shape for k, v in out.items()})
+
+
 def main():
     if not ref_runner.available():
         raise SystemExit("oracle/_ref is not built: run python oracle/build_ref.py first")
+    refdirs_case()
     for name, cfg, model, n_vox, seed, flags in CASES:
         P = synth.make_problem(cfg, n_vox=n_vox, model=model, seed=seed)
         # NB the reference sizes its y_est scratch by the CHUNK's voxel count (models.pyx:588, 875, 1210, 1548:

@@ -167,6 +167,16 @@ def test_golden_reference_glue(name, cfg, model, n_vox, seed):
                 assert np.array_equal(got[k], g[k]), k
 
 
+def test_golden_on_reference_direction_set():
+    """NODDI on the reference's own 500-direction set + hash table (amico/directions/*.bin, carried by the fixture)."""
+    g = np.load(os.path.join(GOLDEN, "noddi_refdirs500.npz"))
+    P = synth.make_problem(2, n_vox=384, seed=77, lut_dirs=g["lut_dirs"], htable=g["htable"])
+    got = gpu_fit(P, rmse=True, debug=True)
+    assert np.array_equal(got["lut"], synth.lut_index_numpy(np.array(P.DIRs), g["htable"]))
+    assert pass_fraction(got["estimates"], g["estimates"]) >= 0.995
+    assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
+
+
 # ----------------------------------------------------------------------------------------------- edge cases
 def test_empty_and_tiny_inputs():
     P = synth.make_problem(1, n_vox=3)

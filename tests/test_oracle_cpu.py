@@ -145,3 +145,36 @@ def test_chunking_is_invisible():
     a = orc.fit_problem(P, nthreads=1)["estimates"]
     b = orc.fit_problem(P, nthreads=7)["estimates"]
     assert np.array_equal(a, b)
+
+
+# ----------------------------------------------------------------------------------------------- the reference's own LUT tables
+def _refdirs_problem():
+    g = np.load(os.path.join(GOLDEN, "noddi_refdirs500.npz"))
+    return g, synth.make_problem(2, n_vox=384, seed=77, lut_dirs=g["lut_dirs"], htable=g["htable"])
+
+
+def test_reference_hash_table_semantics():
+    """amico/directions/htable_ndirs=500.bin (fixture): entry [theta_deg * 181 + phi_deg] is the LUT direction nearest (max |dot|)
+    to that whole-degree direction -- exactly what synth.build_htable computes, so synthetic tables have the real semantics."""
+    g = np.load(os.path.join(GOLDEN, "noddi_refdirs500.npz"))
+    dirs, ht = g["lut_dirs"], g["htable"]
+    assert dirs.shape == (500, 3) and ht.shape == (181 * 181,) and ht.dtype == np.int16
+    np.testing.assert_allclose(np.linalg.norm(dirs, axis=1), 1.0, atol=1e-12)
+    assert (dirs[:, 1] >= 0).all()                      # half sphere y >= 0: why dir_to_lut_idx flips (amico/lut.pyx:335-338)
+    assert np.array_equal(synth.build_htable(dirs), ht)
+
+
+def test_oracle_reproduces_golden_on_reference_direction_set():
+    """NODDI on the reference's REAL 500-direction set and hash table: outputs of the reference's Cython fit."""
+    import hashlib
+    g, P = _refdirs_problem()
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(P.y).tobytes())
+    h.update(np.ascontiguousarray(P.DIRs).tobytes())
+    for k in sorted(P.KERNELS):
+        if k != "model":
+            h.update(np.ascontiguousarray(P.KERNELS[k]).tobytes())
+    if h.hexdigest() != str(g["input_sha256"]):
+        pytest.skip("synthetic generator is not bit-reproducible on this host (libm differences): fixture inputs differ")
+    res = orc.fit_problem(P, rmse=True, nthreads=2)
+    assert np.array_equal(res["estimates"], g["estimates"]) and np.array_equal(res["rmse"], g["rmse"])
