@@ -456,49 +456,48 @@ __device__ __forceinline__ void principal_evec(double a00, double a01, double a1
     out[0] = x / nrm; out[1] = y / nrm; out[2] = z / nrm;
 }
 
+// W (6 x m, fp64) sits in shared memory; one THREAD per voxel reads its row straight from global memory in 16-byte pieces
+// (a warp touches 32 different 128-byte lines per request and consumes each line completely over the next requests, so
+// L1 turns the strided pattern into full-line DRAM reads; no staging pass, 32 resident warps per SM for the fp64 log chains).
 template <typename T>
-__device__ __forceinline__ void stage_plain(T *rows, const T *__restrict__ src, int count, int m, int stride, int lane)
-{
-    int v = 0, j = lane;
-    while (j >= m) { j -= m; ++v; }
-    for (int e = lane; e < count; e += 32) {
-        rows[v * stride + j] = __ldcs(src + e);
-        j += 32;
-        while (j >= m) { j -= m; ++v; }
-    }
-}
-
-// W (6 x m, fp64) sits at the start of shared memory; one warp per chunk of 32 voxels
-template <typename T>
-__global__ void __launch_bounds__(128) k_dti(const T *__restrict__ y, long long n_vox, int m, int stride, const double *__restrict__ W,
-                                             double min_signal, double *dirs, long long n_chunks)
+__global__ void __launch_bounds__(256) k_dti(const T *__restrict__ y, long long n_vox, int m, const double *__restrict__ W,
+                                             double min_signal, double *dirs)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *sW = reinterpret_cast<double *>(smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     for (int i = threadIdx.x; i < 6 * m; i += blockDim.x) sW[i] = W[i];
     __syncthreads();
-    T *rows = reinterpret_cast<T *>(sW + 6 * m) + (size_t)warp * CH * stride;
-    for (long long c = (long long)blockIdx.x * wpb + warp; c < n_chunks; c += (long long)gridDim.x * wpb) {
-        const long long v0 = c * CH;
-        const int nvox = (int)min((long long)CH, n_vox - v0);
-        stage_plain<T>(rows, y + v0 * m, nvox * m, m, stride, lane);
-        __syncwarp();
-        if (lane < nvox) {
-            const T *r = rows + lane * stride;
-            double d[6] = {0, 0, 0, 0, 0, 0};
+    constexpr int VEC = 16 / sizeof(T);  // elements per 16-byte load
+    const bool vec_ok = (m % VEC) == 0 && ((uintptr_t)y & 15) == 0;
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vox; v += (long long)gridDim.x * blockDim.x) {
+        const T *r = y + v * m;
+        double d[6] = {0, 0, 0, 0, 0, 0};
+        if (vec_ok) {
+#pragma unroll 1
+            for (int j = 0; j < m; j += VEC) {
+                T x[VEC];
+                *reinterpret_cast<int4 *>(x) = __ldg(reinterpret_cast<const int4 *>(r + j));
+                double ls[VEC];
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) ls[t] = log(fmax((double)x[t], min_signal));  // independent chains
+#pragma unroll
+                for (int t = 0; t < VEC; ++t) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) d[k] = fma(sW[k * m + j + t], ls[t], d[k]);
+                }
+            }
+        } else {
 #pragma unroll 2
             for (int j = 0; j < m; ++j) {
                 const double ls = log(fmax((double)r[j], min_signal));
 #pragma unroll
                 for (int k = 0; k < 6; ++k) d[k] = fma(sW[k * m + j], ls, d[k]);
             }
-            double e[3];
-            principal_evec(d[0], d[1], d[2], d[3], d[4], d[5], e);
-            double *o = dirs + (v0 + lane) * 3;
-            o[0] = e[0]; o[1] = e[1]; o[2] = e[2];
         }
-        __syncwarp();
+        double e[3];
+        principal_evec(d[0], d[1], d[2], d[3], d[4], d[5], e);
+        double *o = dirs + v * 3;
+        o[0] = e[0]; o[1] = e[1]; o[2] = e[2];
     }
 }
 
@@ -836,20 +835,15 @@ int amx_dti_directions(int device, int space, const void *y, int y_dtype, int64_
         AMX_CK(tmp.alloc((void **)&d_d, (size_t)n_vox * 3 * sizeof(double)));
         src = d_y; dst = d_d;
     }
-    const int stride = m | 1;
-    const size_t fixed = (size_t)6 * m * sizeof(double), per_warp = (size_t)CH * stride * esz;
-    const int warps = warps_for(fixed, per_warp, max_smem);
-    if (warps <= 0) return amx::set_error(AMX_E_INVALID, "m=%d too large for the shared-memory staging", m);
-    const size_t smem = fixed + (size_t)warps * per_warp;
-    const long long n_chunks = (n_vox + CH - 1) / CH;
-    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)max_smem / smem));
-    const int grid = (int)std::max<long long>(1, std::min<long long>((n_chunks + warps - 1) / warps, (long long)sm * ctas_per_sm));
+    const size_t smem = (size_t)6 * m * sizeof(double);
+    if (smem > (size_t)max_smem) return amx::set_error(AMX_E_INVALID, "m=%d too large for the shared-memory weight table", m);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_vox + 255) / 256, (long long)sm * 8));
     if (y_dtype == AMX_F64) {
         AMX_CK(cudaFuncSetAttribute(k_dti<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dti<double><<<grid, warps * 32, smem, s>>>((const double *)src, n_vox, m, stride, d_W, min_signal, dst, n_chunks);
+        k_dti<double><<<grid, 256, smem, s>>>((const double *)src, n_vox, m, d_W, min_signal, dst);
     } else {
         AMX_CK(cudaFuncSetAttribute(k_dti<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_dti<float><<<grid, warps * 32, smem, s>>>((const float *)src, n_vox, m, stride, d_W, min_signal, dst, n_chunks);
+        k_dti<float><<<grid, 256, smem, s>>>((const float *)src, n_vox, m, d_W, min_signal, dst);
     }
     AMX_CK(cudaGetLastError());
     if (host) {
