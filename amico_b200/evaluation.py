@@ -85,9 +85,11 @@ class Evaluation:
         return self.CONFIG.get(key)
 
     # ------------------------------------------------------------------ load_data (core.py:107-283)
-    def load_data(self, dwi, scheme, mask=None, b0_thr=0, b0_min_signal=0, replace_bad_voxels=None):
-        """``dwi``: (X, Y, Z, nS) array (numpy, or a CUDA float32 torch tensor); ``scheme``: a ``Scheme`` or an Nx4 / Nx7
-        table; ``mask``: (X, Y, Z) array or None.  Same pre-processing, same float32 arithmetic as the reference."""
+    def load_data(self, dwi, scheme, mask=None, b0_thr=0, b0_min_signal=0, replace_bad_voxels=None, shard=None):
+        """``dwi``: file name, (X, Y, Z, nS) array (numpy, or a CUDA float32 torch tensor); ``scheme``: file name, a ``Scheme``
+        or an Nx4 / Nx7 table; ``mask``: file name, (X, Y, Z) array or None.  Same pre-processing, same float32 arithmetic as
+        the reference.  ``shard=(rank, world)``: this process takes one contiguous slab of the flat voxel list (multi-GPU: one
+        process per GPU, every rank sees the same inputs; ``fit`` gathers the volumes on rank 0)."""
         import torch
         lib = L.load()
         if self.get_config("doDebiasSignal"):
@@ -154,6 +156,13 @@ class Evaluation:
             n_total = int(np.prod(self._dim))
         self.set_config("dim", self._dim)
         order = "F" if self._forder else "C"
+        self._n_total_full = n_total
+        self._shard = None
+        if shard is not None and int(shard[1]) > 1:
+            from .parallel import shard_bounds
+            self._shard = (int(shard[0]), int(shard[1]))
+            i0, i1 = shard_bounds(n_total, self._shard[1], self._shard[0])
+            self._slab = (i0, i1)
         if mask is not None:
             mask_img = np.asarray(mask).astype(np.uint8)  # core.py:181
             if mask_img.ndim != 3:
@@ -184,9 +193,18 @@ class Evaluation:
             mb = torch.empty(n_total, dtype=torch.float32, device=dev)
             L.check(lib.amx_mean_b0(L.SPACE_DEVICE, self.device, vol.data_ptr(), n_total, sch.nS, b0_idx.ctypes.data, len(b0_idx),
                                     mb.data_ptr(), stream))
-            nf = mb.cpu().numpy()
+            nf = mb.cpu().numpy().reshape(self._dim, order=order)  # numpy's float32 mean depends on the C-order scan
             with np.errstate(all="ignore"):
                 thr = float(np.float32(b0_min_signal * nf[nf > 0].mean()))
+        if self._shard is not None:  # from here on only this rank's slab of the flat voxel list
+            i0, i1 = self._slab
+            vol = vol.reshape(-1, sch.nS)[i0:i1].clone()  # own allocation: the kernels want a 16-byte aligned base
+            n_total = i1 - i0
+            if d_mask is not None:
+                d_mask = d_mask[i0:i1].contiguous()
+                n_kept = int(np.count_nonzero(mask_img.reshape(-1, order=order)[i0:i1] == 1))
+            else:
+                n_kept = n_total
         shells = sorted(sch.shells, key=lambda s: s["b"])  # np.argsort(bvals) order (core.py:245)
         sh_idx = _i32(np.concatenate([s["idx"] for s in shells])) if shells else _i32([])
         sh_off = _i32(np.concatenate([[0], np.cumsum([len(s["idx"]) for s in shells])])) if shells else _i32([0])
@@ -213,7 +231,7 @@ class Evaluation:
         self._y = y[:n_kept]
         self._vox_idx = vox_idx[:n_kept]
         self._mean_b0s_dev = mean_b0s
-        self.mean_b0s = None if mean_b0s is None else mean_b0s.cpu().numpy().reshape(self._dim, order=order)
+        self.mean_b0s = None if (mean_b0s is None or self._shard is not None) else mean_b0s.cpu().numpy().reshape(self._dim, order=order)
         self._dirs = None
         self._fit_scheme = sch
         if flags & L.PRE_DIR_AVG:
@@ -329,7 +347,7 @@ class Evaluation:
         torch.cuda.synchronize(dev)
         self.set_config("fit_time", time.time() - t)
         # ---- store results (core.py:469-498)
-        n_total = int(np.prod(self._dim))
+        n_total = int(np.prod(self._dim)) if self._shard is None else self._slab[1] - self._slab[0]
         stream = torch.cuda.current_stream(dev).cuda_stream
         n_vox = self._y.shape[0]
 
@@ -361,6 +379,13 @@ class Evaluation:
                 raise NotImplementedError("doKeepb0Intact without doNormalizeSignal reads mean_b0s the reference never sets")
             out["DWI_corrected"] = scatter(yc.contiguous(), yc.shape[1])
         torch.cuda.synchronize(dev)
+        if self._shard is not None:  # one gather per volume: rank 0 ends up with the whole thing, in rank (= voxel) order
+            from .parallel import gather_maps
+            out = {k: gather_maps(v, self._shard[0], self._shard[1]) for k, v in sorted(out.items())}
+            if self._shard[0] != 0:
+                self.RESULTS = None
+                self._last_fit = res
+                return None
         self.RESULTS = {}
         for k, v in out.items():
             a = v.cpu().numpy()

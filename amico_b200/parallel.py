@@ -85,6 +85,10 @@ def gather_maps(est, rank, world, dst=0):
         return est
     import torch
     dist = _dist()
+    on_cuda = est.is_cuda
+    if on_cuda and dist.get_backend() == "gloo":  # gloo cannot gather CUDA tensors (CPU tests, two ranks on one GPU)
+        out = gather_maps(est.cpu(), rank, world, dst)
+        return None if out is None else out.to(est.device)
     sizes = [None] * world
     dist.all_gather_object(sizes, int(est.shape[0]))
     if len(set(sizes)) == 1:

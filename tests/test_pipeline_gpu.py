@@ -319,3 +319,54 @@ def test_file_based_flow_int16_scaled(tmp_path):
     ref = Evaluation()
     ref.load_data(vol, P.full_scheme.raw, mask)
     np.testing.assert_array_equal(ae.y, ref.y)
+
+
+SHARD_WORKER = """
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+from amico_b200 import synth
+from amico_b200.evaluation import Evaluation
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+P, dwi, mask = synth.make_raw_volume(1, (9, 7, 5), seed=13)
+ae = Evaluation(device=0)                       # both ranks share GPU 0 in this test; one GPU per rank in production
+ae.set_config("doComputeRMSE", True)
+ae.load_data(dwi, P.full_scheme, mask, b0_min_signal=0.01, shard=(rank, world))
+ae.set_model("FreeWater")
+ae.load_kernels(P.KERNELS, P.htable)
+res = ae.fit()
+if rank == 0:
+    one = Evaluation(device=0)
+    one.set_config("doComputeRMSE", True)
+    one.load_data(dwi, P.full_scheme, mask, b0_min_signal=0.01)
+    one.set_model("FreeWater")
+    one.load_kernels(P.KERNELS, P.htable)
+    want = one.fit()
+    for k in ("MAPs", "DIRs", "RMSE"):
+        assert res[k].shape == want[k].shape and np.array_equal(res[k], want[k]), k
+else:
+    assert res is None
+dist.barrier()
+dist.destroy_process_group()
+print("worker", rank, "ok")
+"""
+
+
+def test_sharded_evaluation_world2(tmp_path):
+    """Two ranks (gloo, sharing the one test GPU) each run the flow on their voxel slab; rank 0 gathers the full volumes,
+    identical to the single-process result."""
+    import os
+    import socket
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(SHARD_WORKER % root)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert r.stdout.count("ok") == 2
