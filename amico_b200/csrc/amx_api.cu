@@ -2,7 +2,6 @@
 #include "../../include/amico_b200.h"
 #include "amx_kernels.cuh"
 #include "amx_slow.cuh"
-#include "amx_w32.cuh"
 #include "amx_err.h"
 
 #include <algorithm>
@@ -84,8 +83,6 @@ struct amx_plan {
     unsigned slab_bytes = 0;  // bytes to stage per direction
     void *d_slab = nullptr;
     double *d_T1 = nullptr, *d_T2 = nullptr, *d_diag0 = nullptr;
-    double *d_T1p = nullptr, *d_T2p = nullptr;  // packed symmetric copies for the NODDI group kernels (amx_w32.cuh)
-    size_t T1p_stride = 0, T2p_stride = 0;
     double ridge_baked = -1.0;  // ridge currently added to the diagonal of d_T2 (< 0: none)
     int ldT1 = 0, ldT2 = 0, K2 = 0;
     size_t T1_stride = 0, T2_stride = 0;
@@ -235,7 +232,7 @@ int amx_plan_destroy(amx_plan *pl)
 {
     if (!pl) return AMX_OK;
     cudaSetDevice(pl->device);
-    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_T1p, pl->d_T2p, pl->d_diag0, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
+    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_diag0, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &wk : pl->work) {
@@ -449,26 +446,6 @@ int launch_noddi_split(const FitParams &p, int grid, int block, size_t smem, cud
     return launch_noddi_split_t<NPL, 512>(p, grid, block, smem, st);
 }
 
-// group kernels (amx_w32.cuh): per-stage warp count in nw[], dynamic shared memory = header + Gram table + warp states
-template <int NPL>
-int launch_noddi_w32(const FitParams &p, int grid, const int *nw, cudaStream_t st)
-{
-    constexpr int MAXT = 384;
-    auto k1 = k_noddi_w32<1, NPL, MAXT>;
-    auto k2 = k_noddi_w32<2, NPL, MAXT>;
-    auto k3 = k_noddi_w32<3, NPL, MAXT>;
-    size_t sm[3];
-    for (int k = 0; k < 3; ++k) sm[k] = 128 + (size_t)p.w32_T_bytes[k] + (size_t)nw[k] * p.w32_state[k];
-    CK(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm[0]));
-    CK(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm[1]));
-    CK(cudaFuncSetAttribute(k3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm[2]));
-    k1<<<grid, nw[0] * 32, sm[0], st>>>(p);
-    k2<<<grid, nw[1] * 32, sm[1], st>>>(p);
-    k3<<<grid, nw[2] * 32, sm[2], st>>>(p);
-    CK(cudaGetLastError());
-    return AMX_OK;
-}
-
 template <int MODEL, int NPL, typename TS>
 int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
@@ -520,7 +497,6 @@ int prepare_tables(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *la
                 k_save_diag<<<pl->ndirs, 128, 0, st>>>(pl->d_T2, pl->K2, pl->ldT2, pl->T2_stride, pl->d_diag0);
             }
             k_set_ridge<<<pl->ndirs, 128, 0, st>>>(pl->d_T2, pl->K2, pl->ldT2, pl->T2_stride, pl->d_diag0, ridge);
-            if (pl->d_T2p) k_pack_sym<<<pl->ndirs, 256, 0, st>>>(pl->d_T2, pl->K2, pl->ldT2, pl->T2_stride, pl->d_T2p, pl->T2p_stride);
             CK(cudaGetLastError());
             pl->ridge_baked = ridge;
             *launches += 1;
@@ -545,36 +521,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
 {
     const long long n_vox = a->n_vox;
     const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
-    // NODDI group kernels: whole Gram table of a direction in shared memory, groups of 16/32 voxels per warp.  Optional
-    // per-voxel outputs that need the full coefficient vector (fit errors, coefficients) stay on the warp-per-voxel kernels.
-    int w32_nw[3] = {0, 0, 0};
-    unsigned w32_T[3] = {0, 0, 0}, w32_st[3] = {0, 0, 0};
-    // (experimental, off by default: measured slower than the warp-per-voxel stage kernels)
-    bool w32 = batched && pl->npl == 5 && pl->n <= 255 && env_int("AMX_NODDI_SPLIT", 1) && env_int("AMX_NODDI_W32", 0) &&
-               !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE)) && !a->coeff_out;
-    if (w32 && !pl->d_T1p) {  // packed symmetric copies of the Gram tables, built on first use (T2 already carries the ridge)
-        pl->T1p_stride = w32_packed_stride(pl->n);
-        pl->T2p_stride = w32_packed_stride(pl->K2);
-        CK(cudaMalloc((void **)&pl->d_T1p, (size_t)pl->ndirs * pl->T1p_stride * sizeof(double)));
-        CK(cudaMalloc((void **)&pl->d_T2p, (size_t)pl->ndirs * pl->T2p_stride * sizeof(double)));
-        CK(cudaMemsetAsync(pl->d_T1p, 0, (size_t)pl->ndirs * pl->T1p_stride * sizeof(double), st));
-        CK(cudaMemsetAsync(pl->d_T2p, 0, (size_t)pl->ndirs * pl->T2p_stride * sizeof(double), st));
-        k_pack_sym<<<pl->ndirs, 256, 0, st>>>(pl->d_T1, pl->n, pl->ldT1, pl->T1_stride, pl->d_T1p, pl->T1p_stride);
-        k_pack_sym<<<pl->ndirs, 256, 0, st>>>(pl->d_T2, pl->K2, pl->ldT2, pl->T2_stride, pl->d_T2p, pl->T2p_stride);
-        CK(cudaGetLastError());
-    }
-    if (w32) {
-        static const char *wenv[3] = {"AMX_W32_WARPS1", "AMX_W32_WARPS2", "AMX_W32_WARPS3"};
-        for (int k = 0; k < 3; ++k) {
-            w32_T[k] = (unsigned)((k == 1 ? pl->T2p_stride : pl->T1p_stride) * sizeof(double));
-            w32_st[k] = w32_state_bytes(k + 1, pl->npl);
-            const long long room = (long long)pl->max_smem - 128 - (long long)w32_T[k];
-            const int fit = room > 0 ? (int)(room / w32_st[k]) : 0;
-            w32_nw[k] = std::min(std::min(12, fit), std::max(1, env_int(wenv[k], 12)));
-            if (w32_nw[k] < 4 || (w32_T[k] & 15u)) w32 = false;
-        }
-    }
-    const int tile_v = w32 ? std::max(32, env_int("AMX_W32_TILE", 512)) : batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
+    const int tile_v = batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
     const bool rotated = pl->model != AMX_MODEL_SANDI;
     const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
     CK(wk.tiles.reserve((size_t)max_tiles * sizeof(int4)));
@@ -597,7 +544,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         k_lut<<<G, B, 0, st>>>(a->dirs, n_vox, pl->d_htable, pl->ndirs, lut, hist, status, vox_offset);
         k_scan_bins<<<1, 1024, 0, st>>>(hist, pl->ndirs, tile_v, offs, cursor, tile_offs, totals);
         k_scatter<<<G, B, 0, st>>>(lut, n_vox, cursor, (int *)wk.order.p);
-        k_tiles<<<(pl->ndirs + 127) / 128, 128, 0, st>>>(hist, offs, tile_offs, pl->ndirs, tile_v, (int4 *)wk.tiles.p, w32 ? 1 : 0);
+        k_tiles<<<(pl->ndirs + 127) / 128, 128, 0, st>>>(hist, offs, tile_offs, pl->ndirs, tile_v, (int4 *)wk.tiles.p, 0);
         CK(cudaGetLastError());
         *launches += 4;
     } else {
@@ -663,13 +610,8 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
     int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count * ctas_per_sm));
 
-    if (w32) {
-        for (int k = 0; k < 3; ++k) { p.w32_T_bytes[k] = w32_T[k]; p.w32_state[k] = w32_st[k]; }
-        p.T1p = pl->d_T1p; p.T2p = pl->d_T2p; p.T1p_stride = pl->T1p_stride; p.T2p_stride = pl->T2p_stride;
-        grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count));
-    }
     if (p.batched) {
-        CK(wk.scratch.reserve((size_t)grid * 32 * std::max(2 * BV, w32 ? 32 : 0) * p.NA * sizeof(double)));
+        CK(wk.scratch.reserve((size_t)grid * 32 * 2 * BV * p.NA * sizeof(double)));
         p.scratch = (double *)wk.scratch.p;
         CK(wk.xiso.reserve((size_t)n_vox * 2 * sizeof(double)));
         CK(wk.supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
@@ -682,8 +624,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     int rc;
     switch (pl->model) {
     case AMX_MODEL_NODDI:
-        if (w32) rc = launch_noddi_w32<5>(p, grid, w32_nw, st);
-        else rc = dispatch_npl<MODEL_NODDI, float>(pl->npl, p, grid, nwarps * 32, smem, st);
+        rc = dispatch_npl<MODEL_NODDI, float>(pl->npl, p, grid, nwarps * 32, smem, st);
         break;
     case AMX_MODEL_FREEWATER: rc = dispatch_npl<MODEL_FREEWATER, float>(pl->npl, p, grid, nwarps * 32, smem, st); break;
     case AMX_MODEL_CZB: rc = dispatch_npl<MODEL_CZB, float>(pl->npl, p, grid, nwarps * 32, smem, st); break;
@@ -704,8 +645,8 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     }
     if (record_events) CK(cudaEventRecord(pl->ev[2], st));
     pl->last_cnt[1] = n_tiles_bound;  // upper bound; the exact count stays on the device
-    pl->last_cnt[3] = w32 ? (int64_t)(128 + w32_T[0] + (size_t)w32_nw[0] * w32_st[0]) : (int64_t)smem;
-    pl->last_cnt[4] = w32 ? w32_nw[0] : nwarps;
+    pl->last_cnt[3] = (int64_t)smem;
+    pl->last_cnt[4] = nwarps;
     pl->last_cnt[5] = staged ? 1 : 0;
     pl->last_cnt[7] = grid;
     return AMX_OK;

@@ -233,8 +233,6 @@ struct FitParams {
     int *ovf_list;       // voxels whose active set outgrew a warp: re-fitted by the scalar slow path (amx_slow.cuh)
     long long ovf_cap;
     unsigned *supmask;   // split NODDI path: [n_vox][NPL] stage-2 support, word s bit l <-> atom l + 32 s
-    unsigned w32_T_bytes[3], w32_state[3];
-    const double *T1p, *T2p; size_t T1p_stride, T2p_stride;  // packed symmetric copies of T1 / T2 (k_pack_sym)  // group kernels (amx_w32.cuh): bytes of the staged Gram table / per-warp state, per stage
 };
 
 struct WarpWS {

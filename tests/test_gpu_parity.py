@@ -334,10 +334,10 @@ def test_default_geometric_host_schedule_matches_single_shot(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"AMX_NODDI_SPLIT": "0"}, {"AMX_NODDI_BATCHED": "0"}, {"AMX_NODDI_BATCHED": "0", "AMX_NO_TMA": "1"},
-                                 {"AMX_WARPS": "8"}, {"AMX_NODDI_W32": "1"}, {"AMX_NODDI_W32": "1", "AMX_W32_TILE": "64"}])
+                                 {"AMX_WARPS": "8"}, {"AMX_COMPACT3": "0"}, {"AMX_STAGE1_WARPS": "24"}])
 def test_noddi_kernel_variants_agree(monkeypatch, env):
     """Fused / per-voxel / non-TMA / voxel-group variants of the NODDI path are kept for A/B measurements: same maps within
-    tolerance (the group kernels of amx_w32.cuh also return the modulated maps)."""
+    tolerance."""
     P = synth.make_problem(2, n_vox=6000, seed=8)
     base = gpu_fit(P, extra=True)
     for k, v in env.items():
