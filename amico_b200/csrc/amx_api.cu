@@ -433,8 +433,25 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     } else {
         k1<<<grid, block, s1, st>>>(p);
     }
-    k2<<<grid, block, s2, st>>>(p);
-    k3<<<grid, block, s3, st>>>(p);
+    // Stages 2 and 3: more resident warps hide more of the L2 latency of the Gram rows as long as registers (64K / threads)
+    // and shared memory (workspace x warps <= 227 KB) allow; the builds for 896 / 1024 threads spill ~150 bytes.
+    const int w2 = env_int("AMX_STAGE2_WARPS", 32), w3 = env_int("AMX_STAGE3_WARPS", 24);
+    auto launch_wide = [&](auto kern, int warps, unsigned ws_doubles) -> int {
+        const size_t sw = fixed + (size_t)ws_doubles * 8 * warps;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+        kern<<<grid, warps * 32, sw, st>>>(p);
+        return AMX_OK;
+    };
+    const bool wide_ok = MAXT == 768 && block == 768;
+    auto fits = [&](int warps, unsigned ws_doubles) { return fixed + (size_t)ws_doubles * 8 * warps <= (size_t)227 * 1024; };
+    int rc = AMX_OK;
+    if (wide_ok && w2 == 32 && fits(32, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 1024>, 32, p.ws_doubles_stage[1]);
+    else if (wide_ok && w2 == 28 && fits(28, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 896>, 28, p.ws_doubles_stage[1]);
+    else k2<<<grid, block, s2, st>>>(p);
+    if (rc) return rc;
+    if (wide_ok && w3 == 28 && fits(28, p.ws_doubles_stage[2])) rc = launch_wide(k_noddi_stage<3, NPL, float, 896>, 28, p.ws_doubles_stage[2]);
+    else k3<<<grid, block, s3, st>>>(p);
+    if (rc) return rc;
     CK(cudaGetLastError());
     return AMX_OK;
 }

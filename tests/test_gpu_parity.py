@@ -334,7 +334,7 @@ def test_default_geometric_host_schedule_matches_single_shot(monkeypatch):
 
 
 @pytest.mark.parametrize("env", [{"AMX_NODDI_SPLIT": "0"}, {"AMX_NODDI_BATCHED": "0"}, {"AMX_NODDI_BATCHED": "0", "AMX_NO_TMA": "1"},
-                                 {"AMX_WARPS": "8"}, {"AMX_COMPACT3": "0"}, {"AMX_STAGE1_WARPS": "24"}])
+                                 {"AMX_WARPS": "8"}, {"AMX_COMPACT3": "0"}, {"AMX_STAGE1_WARPS": "24", "AMX_STAGE2_WARPS": "24"}, {"AMX_STAGE2_WARPS": "28", "AMX_STAGE3_WARPS": "28"}])
 def test_noddi_kernel_variants_agree(monkeypatch, env):
     """Fused / per-voxel / non-TMA / voxel-group variants of the NODDI path are kept for A/B measurements: same maps within
     tolerance."""
