@@ -1,15 +1,16 @@
 // The callers either side of the per-voxel fit, on the GPU (include/amico_b200.h, second part):
-//   amx_preprocess      amico/core.py:151-156, 209-278 (load_data: NaN policy, b0 normalisation, b0 merge, directional
-//                       average) + :451-452 (mask compaction, y < 0 -> 0)
-//   amx_mean_b0         amico/core.py:212
-//   amx_dti_directions  amico/core.py:430-436, 456-458 (dipy TensorModel OLS -> principal eigenvector)
-//   amx_scatter_maps    amico/core.py:472-498
+//   amx_volume_to_voxel_major  nibabel get_fdata().astype(float32) + voxel-major layout, amico/core.py:135-136
+//   amx_preprocess             amico/core.py:151-156, 209-278 (load_data: NaN policy, b0 normalisation, b0 merge, directional
+//                              average) + :451-452 (mask compaction, y < 0 -> 0)
+//   amx_mean_b0                amico/core.py:212
+//   amx_dti_directions         amico/core.py:430-436, 456-458 (dipy TensorModel OLS -> principal eigenvector)
+//   amx_scatter_maps           amico/core.py:472-498
+//   amx_resample_kernels       amico/lut.pyx:274-311 (+ the [:, merge_idx] of every <Model>.resample)
 //
-// All three are streaming, HBM-bound passes (a few flops per byte).  Shape of every kernel: a warp takes a CHUNK of 32
-// consecutive voxels -- one contiguous block of 32 * nS floats in the voxel-major volume -- pulls it into shared memory
-// with 128-bit coalesced loads (row stride padded to an odd word count), lets lane v do voxel v's short sequential
-// arithmetic conflict-free, and writes the result rows back fully coalesced.  Grids are sized to the SM count and
-// walk the chunks with a stride (persistent warps).
+// All are streaming passes over voxel-major data (a few flops per byte, fp64 log chains for the DTI fit).  k_preprocess: a warp
+// takes a CHUNK of 32 consecutive voxels -- one contiguous block of 32 * nS floats -- as ONE TMA bulk copy into shared memory
+// (double buffered), lane v does voxel v's short sequential arithmetic, and the rows stream back out as float4.  Grids are
+// sized to the SM count and walk the chunks with a stride (persistent warps).
 #include "../../include/amico_b200.h"
 #include "amx_err.h"
 
@@ -25,7 +26,7 @@ constexpr int CH = 32;           // voxels per chunk (one per lane)
 constexpr int PRE_BLOCK_VOX = 1024;  // voxels per mask-count block
 
 struct PreParams {
-    const float *dwi; long long n_total; int nS, stride;  // stride = nS | 1 (words per shared-memory row)
+    const float *dwi; long long n_total; int nS;
     const unsigned char *mask;
     const int *b0_idx; int b0_count;
     const int *dwi_idx; int dwi_count;
@@ -684,7 +685,7 @@ int amx_preprocess(const amx_pre_args *a, int64_t *n_kept, int *m_out_p)
     if (!host && a->space != AMX_SPACE_DEVICE) return amx::set_error(AMX_E_INVALID, "bad space");
 
     PreParams p{};
-    p.n_total = a->n_total; p.nS = a->nS; p.stride = a->nS | 1;
+    p.n_total = a->n_total; p.nS = a->nS;
     p.b0_count = a->b0_count; p.dwi_count = a->dwi_count; p.n_shells = (a->flags & AMX_PRE_DIR_AVG) ? a->n_shells : 0;
     p.flags = a->flags; p.thr = a->b0_threshold; p.repl = a->replace_bad; p.m_out = m_out; p.y_cap = a->y_capacity;
 
