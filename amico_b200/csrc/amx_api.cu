@@ -596,6 +596,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.batched = batched ? (env_int("AMX_NODDI_SPLIT", 1) ? 2 : 1) : 0;
     p.fast_lars = env_int("AMX_FAST_LARS", 1);
     p.compact3 = env_int("AMX_COMPACT3", 1);
+    p.aspace = env_int("AMX_ASPACE", 1);
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);

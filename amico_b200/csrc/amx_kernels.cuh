@@ -225,6 +225,7 @@ struct FitParams {
     int cap_stage[3]; unsigned ws_doubles_stage[3];  // stage kernels: per-stage active-set capacity and workspace size
     int m_pad, dc_pad;
     int fast_lars;    // NODDI stage 2: throughput-oriented LARS (same path, fused arithmetic)
+    int aspace;       // NODDI NNLS stages: A-space re-evaluation of near-dependent candidate columns
     int compact3;     // NODDI stage 3: NNLS on the compact support system (one atom per lane) when the support fits a warp
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
@@ -890,8 +891,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
+                const ASpace asp{(const float *)S, n_pad, m, p.y, p.y_f64, (long long)p.order[pos]};
+                const ASpace *as = (p.aspace && sizeof(TS) == 4) ? &asp : nullptr;
                 if (STAGE == 1) {  // isotropic fraction (amico/models.pyx:911)
-                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr, cap);
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr, cap, nullptr, as);
                     if (lane == 0) {
                         p.xiso[2 * pos] = ws.x[n - 1];
                         p.xiso[2 * pos + 1] = p.exvivo ? ws.x[n - 2] : 0.0;
@@ -926,7 +929,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                         ws.c1[lane] = cq;  // c of the compact system, in place (every lane has read its entry)
                         __syncwarp();
                         ov = warp_nnls<1, true>(T1, p.ldT1, support, m, 3 * support, ws.c1, ws.x, lane < support ? 1u : 0u, ws.mat, ws.rd,
-                                                ws.P, lane, nullptr, cap, map);
+                                                ws.P, lane, nullptr, cap, map, as);
                         const double xq = lane < support ? ws.x[lane] : 0.0;
                         __syncwarp();
 #pragma unroll
@@ -936,7 +939,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
                         __syncwarp();
                         xf = ws.c1;
                     } else {
-                        ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr, cap);
+                        ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr, cap, nullptr, as);
                     }
                     noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
                                     (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, xf, lane);

@@ -7,6 +7,8 @@
 #include <string.h>
 
 #define CAP 64
+double gm_thr = 1e-6;   /* A-space re-evaluation threshold on d2 / H_jj (set from Python) */
+double gm_floor = 0.0;  /* refined candidates with d2 <= gm_floor * H_jj count as dependent */
 
 /* ---- NNLS, Lawson-Hanson pivoting in Gram space; Cholesky factor L of H_PP (row-major, CAP ld),
  * appended row-wise on entry, rebuilt from H_PP after removals.  z = L^-1 c_P kept incrementally.
@@ -61,10 +63,25 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
             for (a = 0; a < np_; ++a) { vv += v[a] * v[a]; vz += v[a] * z[a]; }
             d2 = H[(size_t)j * ld + j] - vv;
             if (stats) { double rel = d2 / H[(size_t)j * ld + j]; stats[3]++; if (rel < 1e-6) stats[4]++; if (rel < 1e-8) stats[5]++; if (rel < 1e-10) stats[6]++; if (rel<1e-12) stats[7]++; }
+            double znum = c[j] - vz;
+            if ((mode & 8) && np_ > 0 && d2 < gm_thr * H[(size_t)j * ld + j]) {
+                /* A-space re-evaluation of a near-dependent candidate: r = a_j - A_P beta, beta = L^-T v;
+                 * d2 = |r|^2 and the numerator r.y come without the cancellation of H_jj - v.v */
+                double beta[CAP], rr, acc2 = 0, accy = 0;
+                back_subst(L, np_, v, beta);
+                for (i = 0; i < m; ++i) {
+                    rr = A[(size_t)j * m + i];
+                    for (a = 0; a < np_; ++a) rr -= A[(size_t)P[a] * m + i] * beta[a];
+                    acc2 += rr * rr; accy += rr * y[i];
+                }
+                d2 = acc2; znum = accy;
+                if (d2 <= gm_floor * H[(size_t)j * ld + j]) d2 = 0;
+                if (stats) stats[9]++;
+            }
             if (d2 > 0) {
                 double unorm = sqrt(vv), t = unorm + sqrt(d2) * 0.01;
                 if (t - unorm > 0) {
-                    znew = (c[j] - vz) / sqrt(d2);
+                    znew = znum / sqrt(d2);
                     if (znew > 0) break;   /* ztest = znew / sqrt(d2) */
                 }
             }
