@@ -430,6 +430,12 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
         CK(cudaFuncSetAttribute(k1w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1w));
         CK(cudaFuncSetAttribute(k1w, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1w * 100 + 233471) / 233472 + 1)));
         k1w<<<grid, 1024, s1w, st>>>(p);
+    } else if (MAXT == 768 && block == 768 && w1 == 28) {
+        auto k1w = k_noddi_stage<1, NPL, float, 896>;
+        const size_t s1m = fixed + (size_t)p.ws_doubles_stage[0] * 8 * 28;
+        CK(cudaFuncSetAttribute(k1w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1m));
+        CK(cudaFuncSetAttribute(k1w, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1m * 100 + 233471) / 233472 + 1)));
+        k1w<<<grid, 896, s1m, st>>>(p);
     } else {
         k1<<<grid, block, s1, st>>>(p);
     }
