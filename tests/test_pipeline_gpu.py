@@ -370,3 +370,30 @@ def test_sharded_evaluation_world2(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="1"))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_evaluation_flow_noddi_merged_b0():
+    """doMergeB0: [mean b0 | dwi] volume (core.py:224-227), DTI on the merged gradient table (core.py:432-433), NODDI on the
+    merged KERNELS (m == 1 + dwi_count -> rows 1..m-1 are the DWI rows, amico/models.pyx:916-918)."""
+    from oracle import oracle as orc
+    P, dwi, mask = synth.make_raw_volume(2, (10, 9, 8), seed=17)
+    sch = P.full_scheme
+    merge_idx = np.hstack((sch.b0_idx[0], sch.dwi_idx))
+    K = dict(P.KERNELS)
+    K["wm"] = np.ascontiguousarray(P.KERNELS["wm"][:, :, merge_idx])
+    K["iso"] = np.ascontiguousarray(P.KERNELS["iso"][merge_idx])
+    r = opl().preprocess(dwi, sch, mask, doMergeB0=True)
+    dirs = opl().dti_directions(r["y"], sch, doMergeB0=True)
+    l1, l2 = orc.DEFAULT_LAMBDAS["NODDI"]
+    ref = orc.fit("NODDI", r["y"], dirs.copy(), P.htable, K, P.params, l1, l2, dwi_idx=sch.dwi_idx)
+    maps_ref = opl().scatter_maps(ref["estimates"], r["vox_idx"], mask.size).reshape(mask.shape + (-1,))
+    ae = Evaluation()
+    ae.set_config("doMergeB0", True)
+    ae.load_data(dwi, sch, mask)
+    ae.set_model("NODDI")
+    ae.load_kernels(K, P.htable)
+    res = ae.fit()
+    np.testing.assert_array_equal(ae.y, r["y"])
+    assert ae.y.shape[1] == 1 + sch.dwi_count
+    rel = np.abs(res["MAPs"] - maps_ref) / np.maximum(np.abs(maps_ref), 1e-3)
+    assert float((rel[mask == 1] <= 1e-4).all(axis=1).mean()) >= 0.995
