@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libamico_b200.so")
+LIB_PATH = os.environ.get("AMICO_B200_LIB") or os.path.join(_HERE, "libamico_b200.so")  # override: A/B builds of the same library
 
 AMX_OK, AMX_E_INVALID, AMX_E_CUDA, AMX_E_LUT_RANGE, AMX_E_CAPACITY, AMX_E_NONFINITE = 0, -1, -2, -3, -4, -5
 PRE_NORMALIZE, PRE_MERGE_B0, PRE_DIR_AVG, PRE_REPLACE_BAD = 1, 2, 4, 8

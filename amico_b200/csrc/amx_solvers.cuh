@@ -11,6 +11,9 @@
 //              Cholesky factor of H_PP instead of a Householder QR of A_P.
 #pragma once
 #include "amx_warp.cuh"
+#ifndef AMX_GD
+#define AMX_GD 2  // Gram rows fetched per batch (measured at 64-80 registers: 1 -> 39.6 ms, 2 -> 37.7, 3 -> 39.1, 4 -> 38.9) in the NODDI solvers' O(n |P|) passes (NPL > 2)
+#endif
 #include <math.h>
 
 namespace amx {
@@ -88,7 +91,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             wl[s] = ok ? c[j] : 0.0;
         }
         {   // rows of T are L2-resident (~300 cycles): fetch GD rows at a time
-            constexpr int GD = (NPL <= 2) ? 4 : 3;
+            constexpr int GD = (NPL <= 2) ? 4 : AMX_GD;
 #pragma unroll 1
             for (int k0 = 0; k0 < np; k0 += GD) {
                 double gq[GD][NPL];
@@ -638,7 +641,7 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         double sl[NPL];
 #pragma unroll
         for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
-        constexpr int GD = (NPL <= 2) ? 4 : 3;
+        constexpr int GD = (NPL <= 2) ? 4 : AMX_GD;
 #pragma unroll 1
         for (int j0 = 0; j0 <= i; j0 += GD) {
             double gq[GD][NPL];
