@@ -327,6 +327,8 @@ def main():
                     "tma_staged": counters["tma_staged"], "grid": counters["grid"], "overflow_voxels": counters["overflow_voxels"]},
             "maps_checksum": checksum,
         }
+        if mid == "NODDI":  # the three stage kernels run at their own widths (defaults of amx_api.cu; the counters above describe stage 3)
+            line["fit"]["noddi_stage_warps"] = [int(os.environ.get(f"AMX_STAGE{k}_WARPS", d)) for k, d in ((1, 32), (2, 32), (3, 24))]
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu:
