@@ -84,3 +84,49 @@ def resample_kernels(KRlm, nS, idx_out, Ylm_out, merge_idx=None, device=0):
     L.check(lib.amx_resample_kernels(int(device), L.SPACE_HOST, K.ctypes.data, n_rows, n_coef, Y.ctypes.data, io.ctypes.data,
                                      len(io), mi.ctypes.data, len(mi), int(nS), out.ctypes.data, None))
     return out
+
+
+# --------------------------------------------------------------------------- kernel generation: rotation in SH space
+def precompute_rotation_matrices(lmax, directions):
+    """``AUX`` of ``amico/lut.pyx:94-141`` for the LUT direction set ``directions`` (ndirs, 3): ``Ylm_rot`` (the SH basis at every
+    LUT direction), ``const`` = sqrt(4 pi / (2l+1)) and ``idx_m0`` (position of the m = 0 function of each order) per basis
+    function.  (The reference also stores ``fit``, the least-squares SH fit on its 500-direction grid; the zonal atoms of
+    ``amico_b200.signals`` come with their Legendre coefficients, so no fit is needed -- see ``rotate_kernel``.)"""
+    directions = np.asarray(directions, dtype=np.float64)
+    _, theta, phi = cart2sphere(directions[:, 0], directions[:, 1], directions[:, 2])
+    Y, m, l = real_sh_descoteaux(lmax, theta, phi)
+    return {"lmax": lmax, "ndirs": len(directions), "Ylm_rot": Y, "const": np.sqrt(4.0 * np.pi / (2.0 * l + 1.0)),
+            "idx_m0": ((l * l + l + 2) // 2 - 1).astype(np.int32), "l": l}
+
+
+def aux_structures_generate(scheme, lmax=12):
+    """``amico/lut.pyx:162-183``: sample indices of each shell in the 500-direction high-resolution scheme and SH indices."""
+    n_sh = (lmax + 1) * (lmax + 2) // 2
+    idx_in = [range(500 * s, 500 * (s + 1)) for s in range(len(scheme.shells))]
+    idx_out = [range(n_sh * s, n_sh * (s + 1)) for s in range(len(scheme.shells))]
+    return idx_in, idx_out
+
+
+def rotate_kernel(atom, aux, idx_out, ndirs):
+    """``rotate_kernel`` of ``amico/lut.pyx:227-271`` for a zonal atom given by its per-shell Legendre coefficients a_l.
+
+    The reference projects the signal on the SH basis (``K_lm``), keeps the m = 0 coefficient of every order and writes
+    ``KRlm[i, (l, m)] = sqrt(4 pi/(2l+1)) K_l0 Y_lm(dir_i)``.  For f(t) = sum_l a_l P_l(t) the m = 0 coefficient is
+    ``K_l0 = a_l sqrt(4 pi/(2l+1))`` exactly, so ``KRlm[i, (l, m)] = a_l 4 pi/(2l+1) Y_lm(dir_i)``.  Isotropic atoms: the SH
+    coefficients themselves (only l = 0: value * sqrt(4 pi)).  Returns float32 (ndirs, n_sh * n_shells) or (n_sh * n_shells,).
+    """
+    n_sh = aux["Ylm_rot"].shape[1]
+    n = n_sh * len(atom.per_shell)
+    if atom.isotropic:
+        out = np.zeros(n, dtype=np.float32)
+        for s, v in enumerate(atom.per_shell):
+            out[idx_out[s][0]] = np.float32(v * np.sqrt(4.0 * np.pi))
+        return out
+    if aux["ndirs"] != ndirs:
+        raise ValueError("AUX was computed for another number of directions")
+    order = (aux["l"] // 2).astype(int)  # index of the order l of each basis function in a_l (l = 0, 2, ...)
+    out = np.zeros((ndirs, n), dtype=np.float32)
+    for s, f in enumerate(atom.per_shell):
+        k_l0 = f.coeffs * np.sqrt(4.0 * np.pi / (2.0 * np.arange(0, aux["lmax"] + 1, 2) + 1.0))
+        out[:, list(idx_out[s])] = (aux["const"] * k_l0[order])[None, :] * aux["Ylm_rot"]
+    return out

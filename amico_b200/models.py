@@ -10,9 +10,10 @@ They can be injected into the reference without editing it through its own plugi
 (``$AMICO_WIP_MODELS`` -> ``from amicowipmodels import *``, ``amico/models.pyx:20-26``; lookup by name in
 ``amico/core.py:290-291``) -- see INTEGRATION.md.
 
-``resample`` reads the ``A_###.npy`` files the reference's ``generate`` wrote and builds the same
-``KERNELS`` dict as the reference, with the SH -> signal-space projection on the GPU (``amx_resample_kernels``).
-``generate`` (kernel synthesis: offline, once per protocol) is not provided here.
+``generate`` writes the rotated SH-space atoms ``A_###.npy`` in the reference's on-disk layout (signal models:
+``amico_b200.signals``, checked against the reference's ``synthesis.py``); ``resample`` reads such
+files -- the reference's or ours -- and builds the same ``KERNELS`` dict as the reference, with the SH -> signal-space
+projection on the GPU (``amx_resample_kernels``).
 """
 from __future__ import annotations
 
@@ -21,6 +22,7 @@ import os
 import numpy as np
 
 from . import lut as _lut
+from . import signals as _sig
 from .plan import Plan
 
 __all__ = ["NODDI", "FreeWater", "CylinderZeppelinBall", "SANDI", "BaseModel"]
@@ -43,8 +45,15 @@ class BaseModel:
     def set_solver(self):
         self.solver_params = {}
 
+    def _atoms(self):
+        """The model's atoms (``amico_b200.signals``) in the order the reference's ``generate`` writes them."""
+        raise NotImplementedError
+
     def generate(self, out_path, aux, idx_in, idx_out, ndirs):
-        raise NotImplementedError("kernel generation is outside the accelerated hot path (use the reference's generate)")
+        """``<Model>.generate`` (``amico/models.pyx:428-480, 725-752, 1088-1111, 1409-1444``): write the rotated SH-space atoms
+        ``A_###.npy`` to ``out_path``.  ``aux`` = ``amico_b200.lut.precompute_rotation_matrices(lmax, lut_directions)``."""
+        for i, atom in enumerate(self._atoms()):
+            np.save(os.path.join(out_path, f"A_{i + 1:03d}.npy"), _lut.rotate_kernel(atom, aux, idx_out, ndirs))
 
     def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
         raise NotImplementedError
@@ -150,6 +159,13 @@ class NODDI(BaseModel):
     def _model_params(self):
         return {"isExvivo": bool(self.isExvivo)}
 
+    def _atoms(self):
+        for od in self.IC_ODs:  # amico/models.pyx:736-745: kappa outer, v_ic inner, isotropic last
+            kappa = 1.0 / np.tan(od * np.pi / 2.0)
+            for vf in self.IC_VFs:
+                yield _sig.atom_noddi(self.scheme, self.dPar, kappa, vf)
+        yield _sig.atom_ball(self.scheme, self.dIso)
+
     def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
         """``amico/models.pyx:754-792``."""
         n_wm = len(self.IC_ODs) * len(self.IC_VFs)
@@ -202,6 +218,12 @@ class FreeWater(BaseModel):
     def _model_params(self):
         return {"type": self.type}
 
+    def _atoms(self):
+        for d in self.d_perps:
+            yield _sig.atom_zeppelin(self.scheme, self.d_par, d)
+        for d in self.d_isos:
+            yield _sig.atom_ball(self.scheme, d)
+
     def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
         """``amico/models.pyx:1113-1144``."""
         nS, merge_idx = self._merge_idx(doMergeB0)
@@ -241,6 +263,14 @@ class CylinderZeppelinBall(BaseModel):
 
     def _model_params(self):
         return {"Rs": np.asarray(self.Rs, dtype=np.float64)}
+
+    def _atoms(self):
+        for R in self.Rs:
+            yield _sig.atom_cylinder(self.scheme, self.d_par, R)
+        for d in self.d_perps:
+            yield _sig.atom_zeppelin(self.scheme, self.d_par, d)
+        for d in self.d_isos:
+            yield _sig.atom_ball(self.scheme, d)
 
     def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
         """``amico/models.pyx:482-523``."""
@@ -282,6 +312,14 @@ class SANDI(BaseModel):
     def _model_params(self):
         return {"Rs": np.asarray(self.Rs, dtype=np.float64), "d_in": np.asarray(self.d_in, dtype=np.float64),
                 "d_isos": np.asarray(self.d_isos, dtype=np.float64)}
+
+    def _atoms(self):
+        for R in self.Rs:
+            yield _sig.atom_sphere(self.scheme, self.d_is, R)
+        for d in self.d_in:
+            yield _sig.atom_astrosticks(self.scheme, d)
+        for d in self.d_isos:
+            yield _sig.atom_ball(self.scheme, d)
 
     def resample(self, in_path, idx_out, Ylm_out, doMergeB0, ndirs):
         """``amico/models.pyx:1446-1486``: every atom is isotropic; columns are L2-normalised."""

@@ -63,10 +63,44 @@ def refdirs_case():
     print("noddi_refdirs500", {k: v.shape for k, v in out.items()})
 
 
+def synthesis_case():
+    """Signals of the reference's own compartment models (amico/synthesis.py, imported from oracle/_ref) for a fibre along z on
+    its 500-direction high-resolution scheme (amico/lut.pyx:359-384, gradient table lut.pyx:390-891), one entry per atom type."""
+    import importlib
+    ref_runner._models()  # puts oracle/_ref on sys.path
+    syn = importlib.import_module("amico.synthesis")
+    lut = importlib.import_module("amico.lut")
+    rsch = importlib.import_module("amico.scheme")
+    out = {"grad": np.asarray(lut.grad, dtype=np.float64)}
+    sch2 = synth.make_scheme(2)
+    hi2 = lut.create_high_resolution_scheme(rsch.Scheme(sch2.raw.copy(), 0))
+    ic, ec, iso = syn.NODDIIntraCellular(hi2), syn.NODDIExtraCellular(hi2), syn.NODDIIsotropic(hi2)
+    cases = []
+    for od, vf in ((0.03, 0.1), (0.3, 0.5), (0.84, 0.99)):
+        kappa = 1.0 / np.tan(od * np.pi / 2.0)
+        cases.append(vf * ic.get_signal(1.7e-3, kappa) + (1 - vf) * ec.get_signal(1.7e-3, kappa, vf))
+    out["noddi_od_vf"] = np.array([(0.03, 0.1), (0.3, 0.5), (0.84, 0.99)])
+    out["noddi"] = np.array(cases)
+    out["noddi_iso"] = iso.get_signal(3.0e-3)
+    sch5 = synth.make_scheme(5)
+    hi5 = lut.create_high_resolution_scheme(rsch.Scheme(sch5.raw.copy(), 0))
+    out["cylinder_R"] = np.array([0.01e-6, 2.0e-6, 8.0e-6])
+    out["cylinder"] = np.array([syn.CylinderGPD(hi5).get_signal(0.6e-3, R) for R in out["cylinder_R"]])
+    out["zeppelin"] = syn.Zeppelin(hi5).get_signal(0.6e-3, 0.51e-3)
+    out["stick"] = syn.Stick(hi5).get_signal(1.7e-3)
+    out["ball"] = syn.Ball(hi5).get_signal(2.0e-3)
+    out["sphere_R"] = np.array([1.0e-6, 6.5e-6, 12.0e-6])
+    out["sphere"] = np.array([syn.SphereGPD(hi5).get_signal(3.0e-3, R) for R in out["sphere_R"]])
+    out["astrosticks"] = syn.Astrosticks(hi5).get_signal(1.5e-3)
+    np.savez_compressed(os.path.join(HERE, "synthesis_ref.npz"), **out)
+    print("synthesis_ref", {k: np.asarray(v).shape for k, v in out.items()})
+
+
 def main():
     if not ref_runner.available():
         raise SystemExit("oracle/_ref is not built: run python oracle/build_ref.py first")
     refdirs_case()
+    synthesis_case()
     for name, cfg, model, n_vox, seed, flags in CASES:
         P = synth.make_problem(cfg, n_vox=n_vox, model=model, seed=seed)
         # NB the reference sizes its y_est scratch by the CHUNK's voxel count (models.pyx:588, 875, 1210, 1548:

@@ -39,10 +39,7 @@ def test_default_grids():
     assert len(s.Rs) == 5 and len(s.d_in) == 5 and len(s.d_isos) == 5 and s.d_is == 3e-3
 
 
-def test_generate_is_out_of_scope_and_resample_needs_the_gpu(tmp_path):
-    m = models.NODDI()
-    with pytest.raises(NotImplementedError):
-        m.generate(None, None, None, None, 500)
+def test_resample_needs_the_gpu(tmp_path):
     # resample is provided (GPU projection): without a device it must fail loudly, never fall back to the CPU
     from amico_b200 import lut, synth
     sch = synth.make_scheme(1)

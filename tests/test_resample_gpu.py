@@ -99,3 +99,25 @@ def test_resample_outdated_lut_error(tmp_path):
     _write_atoms(str(tmp_path), [(7, Ylm_out.shape[1])] * 10 + [(Ylm_out.shape[1],)], 0)
     with pytest.raises(RuntimeError, match="Outdated LUT"):
         mdl.resample(str(tmp_path), idx_out, Ylm_out, False, 9)
+
+
+def test_generate_resample_fit_chain(tmp_path):
+    """The whole offline chain without the reference: generate (rotated SH atoms on disk) -> resample on the GPU -> the same
+    KERNELS as sampling the models directly (1 float32 ulp) -> identical FreeWater maps."""
+    from amico_b200.plan import Plan
+    P = synth.make_problem(1, n_vox=256)
+    sch = P.scheme
+    mdl = models.FreeWater()
+    mdl.scheme = sch
+    aux = lut.precompute_rotation_matrices(12, P.lut_dirs)
+    idx_in, idx_out_gen = lut.aux_structures_generate(sch, 12)
+    mdl.generate(str(tmp_path), aux, idx_in, idx_out_gen, len(P.lut_dirs))
+    idx_out, Ylm_out = lut.aux_structures_resample(sch, 12)
+    K = mdl.resample(str(tmp_path), idx_out, Ylm_out, False, len(P.lut_dirs))
+    for k in ("D", "CSF"):
+        np.testing.assert_allclose(K[k], P.KERNELS[k], rtol=0, atol=2e-7, err_msg=k)
+    with Plan("FreeWater", K, P.htable, P.params, dwi_idx=sch.dwi_idx) as plan:
+        a = plan.fit(P.y, np.array(P.DIRs), 0.0, 1e-3)["estimates"]
+    with Plan("FreeWater", P.KERNELS, P.htable, P.params, dwi_idx=sch.dwi_idx) as plan:
+        b = plan.fit(P.y, np.array(P.DIRs), 0.0, 1e-3)["estimates"]
+    assert np.abs(a - b).max() < 1e-4
