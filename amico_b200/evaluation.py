@@ -260,14 +260,54 @@ class Evaluation:
             raise RuntimeError('Model not set; call "set_model()" method first')
         self.model.set_solver(**params)
 
-    def load_kernels(self, KERNELS, htable=None):
-        """Hand over the dictionary ``<Model>.resample`` built (``core.py:368-404``) and the direction hash table
-        (``amico/lut.pyx:71-91``)."""
+    def set_lut(self, directions, htable):
+        """The LUT direction set and its 181x181 hash table -- what the reference reads from its package data
+        (``amico/directions/ndirs=*.bin``, ``htable_ndirs=*.bin``; ``lut.pyx:50-91``).  Needed by ``generate_kernels`` /
+        ``load_kernels()`` without arguments."""
+        self._lut_dirs = np.ascontiguousarray(directions, dtype=np.float64)
+        self.htable = np.ascontiguousarray(htable, dtype=np.int16)
+        self.set_config("ndirs", len(self._lut_dirs))
+
+    def generate_kernels(self, regenerate=False, lmax=12):
+        """``core.py:328-365``: write the model's rotated SH-space atoms to ``<study>/kernels/<model id>/A_###.npy`` (skipped when
+        they are already there and ``regenerate`` is False)."""
         if self.model is None:
             raise RuntimeError('Model not set; call "set_model()" method first')
-        self.KERNELS = KERNELS
-        self.htable = htable
+        if self.scheme is None:
+            raise RuntimeError('Scheme not loaded; call "load_data()" first')
+        if getattr(self, "_lut_dirs", None) is None:
+            raise RuntimeError('LUT directions not set; call "set_lut()" first')
+        from . import lut as _lut
+        path = os.path.join(self.get_config("study_path"), "kernels", self.model.id)
+        self.set_config("ATOMS_path", path)
+        self.set_config("lmax", lmax)
+        if os.path.isdir(path) and glob.glob(os.path.join(path, "A_*.npy")) and not regenerate:
+            return path
+        os.makedirs(path, exist_ok=True)
+        for f in glob.glob(os.path.join(path, "*")):
+            os.remove(f)
         self.model.scheme = self._fit_scheme if not self.get_config("doDirectionalAverage") else self.scheme
+        aux = _lut.precompute_rotation_matrices(lmax, self._lut_dirs)
+        idx_in, idx_out = _lut.aux_structures_generate(self.model.scheme, lmax)
+        self.model.generate(path, aux, idx_in, idx_out, len(self._lut_dirs))
+        return path
+
+    def load_kernels(self, KERNELS=None, htable=None):
+        """``core.py:368-404``.  With ``KERNELS``: hand over a dictionary some ``<Model>.resample`` built (and the hash table).
+        Without: resample the atoms of ``generate_kernels`` to the subject's scheme on the GPU."""
+        if self.model is None:
+            raise RuntimeError('Model not set; call "set_model()" method first')
+        self.model.scheme = self._fit_scheme if not self.get_config("doDirectionalAverage") else self.scheme
+        if KERNELS is None:
+            if self.get_config("ATOMS_path") is None:
+                raise RuntimeError('Response functions not generated; call "generate_kernels()" first')
+            from . import lut as _lut
+            idx_out, Ylm_out = _lut.aux_structures_resample(self.model.scheme, self.get_config("lmax") or 12)
+            KERNELS = self.model.resample(self.get_config("ATOMS_path"), idx_out, Ylm_out, self.get_config("doMergeB0"),
+                                          self.get_config("ndirs"))
+        self.KERNELS = KERNELS
+        if htable is not None:
+            self.htable = htable
 
     # ------------------------------------------------------------------ fit (core.py:407-498)
     @property

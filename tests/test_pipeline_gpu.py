@@ -397,3 +397,33 @@ def test_evaluation_flow_noddi_merged_b0():
     assert ae.y.shape[1] == 1 + sch.dwi_count
     rel = np.abs(res["MAPs"] - maps_ref) / np.maximum(np.abs(maps_ref), 1e-3)
     assert float((rel[mask == 1] <= 1e-4).all(axis=1).mean()) >= 0.995
+
+
+def test_reference_style_script_end_to_end(tmp_path):
+    """The reference's usage pattern, start to finish, without the reference: files in a study folder -> load_data ->
+    set_model -> generate_kernels -> load_kernels -> fit -> save_results; maps equal to the flow fed with the directly
+    sampled dictionary."""
+    import os
+    from amico_b200 import nifti
+    P, dwi, mask = synth.make_raw_volume(1, (6, 6, 6), seed=31)
+    subj = tmp_path / "study" / "s01"
+    os.makedirs(subj)
+    nifti.save(subj / "DWI.nii.gz", dwi)
+    nifti.save(subj / "mask.nii.gz", mask.astype(np.float32))
+    np.savetxt(subj / "DWI.scheme", P.full_scheme.raw, fmt="%.8f", header="VERSION: BVECTOR", comments="")
+    ae = Evaluation(str(tmp_path / "study"), "s01")
+    ae.load_data("DWI.nii.gz", "DWI.scheme", "mask.nii.gz", b0_thr=0)
+    ae.set_model("FreeWater")
+    ae.set_lut(P.lut_dirs, P.htable)
+    path = ae.generate_kernels(regenerate=True)
+    assert len(os.listdir(path)) == 11 and ae.generate_kernels() == path          # second call: kernels are reused
+    ae.load_kernels()
+    res = ae.fit()
+    ae.save_results()
+    ref = Evaluation()
+    ref.load_data(dwi, P.full_scheme.raw, mask)
+    ref.set_model("FreeWater")
+    ref.load_kernels(P.KERNELS, P.htable)
+    want = ref.fit()
+    assert np.abs(res["MAPs"] - want["MAPs"]).max() < 1e-4
+    assert os.path.isfile(subj / "AMICO" / "FreeWater" / "fit_FW.nii.gz")
