@@ -29,8 +29,6 @@ import math
 from dataclasses import dataclass, field
 
 import numpy as np
-from numpy.polynomial import legendre as npleg
-from scipy import optimize, special
 
 
 CONFIGS = {
