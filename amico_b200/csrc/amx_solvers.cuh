@@ -572,7 +572,7 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         cur = bi;
     }
     int newAtom = 1, iter = 0, na = 0;
-    double coef_l = 0.0;
+    double coef_l = 0.0, rs_l = 0.0;  // coefficient / row sum of (G_SS)^-1 of this lane's active position
     int ind_l = -1;
     unsigned act = 0;
     const int length_path = 4 * L;
@@ -593,14 +593,23 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
             __syncwarp();
             if (i == 0) {
                 if (lane == 0) Mi[0] = 1.0 / g;
+                rs_l = (lane == 0) ? 1.0 / g : 0.0;
             } else {
                 double ur = 0.0;
                 if (lane < i) {
                     ur = sym_row_dot(Mi, lane, i, gs);
                     u[lane] = ur;
                 }
-                const double dot = warp_sum(lane < i ? ur * g : 0.0);
+                double dot = lane < i ? ur * g : 0.0, usum = lane < i ? ur : 0.0;  // two interleaved butterfly sums
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dot += __shfl_xor_sync(FULL, dot, o);
+                    usum += __shfl_xor_sync(FULL, usum, o);
+                }
                 const double schur = 1.0 / (shfl(g, i) - dot);
+                // row sums of the inverse after the Schur update: old rows += schur u_r (sum(u) - 1), new row = schur (1 - sum(u))
+                if (lane < i) rs_l = fma(schur * ur, usum - 1.0, rs_l);
+                if (lane == i) rs_l = schur * (1.0 - usum);
                 __syncwarp();
                 if (lane < i) {
                     const double su = schur * ur;
@@ -621,8 +630,16 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
             gs[lane] = sg;
         }
         __syncwarp();
+        // With the positivity constraint every active correlation is positive (never observed otherwise: 0 of 150,000 model voxels),
+        // so u = (G_SS)^-1 1 is the vector of row sums of the inverse, which is carried along in O(1) per lane and step; the
+        // general form stays as the fallback.
         double ul = 0.0;
-        if (lane <= i) {
+        if (!__any_sync(FULL, lane <= i && !(dl > 0.0))) {
+            if (lane <= i) {
+                ul = rs_l;
+                u[lane] = ul;
+            }
+        } else if (lane <= i) {
             ul = sym_row_dot(Mi, lane, i + 1, gs);
             u[lane] = ul;
         }
@@ -708,8 +725,11 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
             if (lane < i) u[lane] = uk;
             double cn = __shfl_down_sync(FULL, coef_l, 1);
             int in_ = __shfl_down_sync(FULL, ind_l, 1);
-            if (lane >= z && lane < i) { coef_l = cn; ind_l = in_; }
-            if (lane == i) { coef_l = 0.0; ind_l = -1; }
+            const double rn = __shfl_down_sync(FULL, rs_l, 1);
+            const double ksum = warp_sum(lane < i ? uk : 0.0);
+            if (lane >= z && lane < i) { coef_l = cn; ind_l = in_; rs_l = rn; }
+            if (lane == i) { coef_l = 0.0; ind_l = -1; rs_l = 0.0; }
+            if (lane < i) rs_l = rs_l - uk - uk * ksum / schur_r;  // row sums: without column z, then the rank-1 downdate
             if ((az & 31) == lane) act &= ~(1u << (az >> 5));
 #pragma unroll 1
             for (int j = z; j < i; ++j) {

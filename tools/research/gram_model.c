@@ -8,7 +8,9 @@
 
 #define CAP 64
 double gm_thr = 1e-6;   /* A-space re-evaluation threshold on d2 / H_jj (set from Python) */
-double gm_floor = 0.0;  /* refined candidates with d2 <= gm_floor * H_jj count as dependent */
+double gm_floor = 0.0;
+int gm_lars_incr = 0;     /* LARS: path direction u = invGs 1 updated in O(|S|) per step instead of recomputed in O(|S|^2) */
+long gm_lars_signflips = 0;  /* steps where an active correlation was not positive (the incremental form assumes +1) */  /* refined candidates with d2 <= gm_floor * H_jj count as dependent */
 
 /* ---- NNLS, Lawson-Hanson pivoting in Gram space; Cholesky factor L of H_PP (row-major, CAP ld),
  * appended row-wise on entry, rebuilt from H_PP after removals.  z = L^-1 c_P kept incrementally.
@@ -149,6 +151,7 @@ int gm_lars(const double *G, int ld, double ridge_in, const double *DtR_in, doub
     double DtR[512], Gs[CAP * CAP], invGs[CAP * CAP], u[512], work[3 * 512], coeffs[CAP];
     const double *Ga[CAP];
     int ind[CAP];
+    double rs[CAP];  /* incremental row sums of invGs */
     if (L > K) L = K;
     if (L > CAP) L = CAP;
     LL = L; length_path = 4 * L;
@@ -174,10 +177,17 @@ int gm_lars(const double *G, int ld, double ridge_in, const double *DtR_in, doub
                 invGs[i * LL + i] = schur;
                 for (j = 0; j < i; ++j) invGs[i * LL + j] = -schur * u[j];
                 for (k = 0; k < i; ++k) for (j = 0; j <= k; ++j) invGs[k * LL + j] += schur * u[j] * u[k];
+                { double U = 0; for (j = 0; j < i; ++j) U += u[j];
+                  for (j = 0; j < i; ++j) rs[j] += schur * u[j] * (U - 1.0);
+                  rs[i] = schur * (1.0 - U); }
             }
+            if (i == 0) rs[0] = invGs[0];
         }
         for (j = 0; j <= i; ++j) work[j] = DtR[ind[j]] > 0 ? 1.0 : -1.0;
         for (int r = 0; r <= i; ++r) { double s = 0; for (int c = 0; c <= i; ++c) s += (r <= c ? invGs[c * LL + r] : invGs[r * LL + c]) * work[c]; u[r] = s; }
+        { int allpos = 1; for (j = 0; j <= i; ++j) if (work[j] < 0) allpos = 0;
+          if (!allpos) gm_lars_signflips++;
+          if (gm_lars_incr && allpos) for (j = 0; j <= i; ++j) u[j] = rs[j]; }
         step_max = INFINITY; first_zero = -1;
         for (j = 0; j <= i; ++j) { double ratio = -coeffs[j] / u[j]; if (ratio > 0 && ratio <= step_max) { step_max = ratio; first_zero = j; } }
         cc = fabs(DtR[ind[0]]);
@@ -215,6 +225,10 @@ int gm_lars(const double *G, int ld, double ridge_in, const double *DtR_in, doub
                 for (k = z; k < i; ++k) invGs[j * LL + k] = invGs[(j + 1) * LL + k + 1];
             }
             for (k = 0; k < i; ++k) for (j = 0; j <= k; ++j) invGs[k * LL + j] -= u[j] * u[k] / schur;
+            { /* row sums: drop row/column z, then the rank-1 downdate */
+              double S = 0; for (k = 0; k < i; ++k) S += u[k];
+              for (k = z; k < i; ++k) rs[k] = rs[k + 1];
+              for (k = 0; k < i; ++k) rs[k] = rs[k] - u[k] - u[k] * S / schur; }
             newAtom = 0; i -= 2;
         } else newAtom = 1;
         if (iter >= length_path - 1 || fabs(step) < 1e-15 || step == step_max2 || normX < 1e-15 || i == L - 1) break;

@@ -12,8 +12,13 @@ def maps_noddi(x, K, n_wm):
     f2 = ((1.0-icvf.astype(np.float64)).astype(np.float32).astype(np.float64)*x[:n_wm]/s/swm).sum()
     k1 = (kap.astype(np.float64)*x[:n_wm]/s/swm).sum()
     return np.array([f1/(f1+f2+1e-16), 2/np.pi*np.arctan2(1.0,k1), x[-1]/s])
+import os
 n_vox = int(sys.argv[1]); mode = int(sys.argv[2]); cfg = int(sys.argv[3]) if len(sys.argv)>3 else 2
-P = synth.make_problem(cfg, n_vox=n_vox); K = P.KERNELS
+snr = float(sys.argv[4]) if len(sys.argv) > 4 else 30.0
+C.c_double.in_dll(lib, 'gm_thr').value = float(os.environ.get('GM_THR', '1e-10'))
+C.c_double.in_dll(lib, 'gm_floor').value = float(os.environ.get('GM_FLOOR', '1e-24'))
+C.c_int.in_dll(lib, 'gm_lars_incr').value = int(os.environ.get('GM_LARS_INCR', '0'))
+P = synth.make_problem(cfg, n_vox=n_vox, snr=snr, seed=104); K = P.KERNELS
 ref = orc.fit_problem(P, return_debug=True, nthreads=8)
 lut = ref['lut']
 n_wm = K['wm'].shape[0]; n = n_wm+1; m = P.y.shape[1]
@@ -38,4 +43,4 @@ r = ref['estimates']
 rel = np.abs(est-r)/np.maximum(np.abs(r),1e-3)
 ok = (rel<=1e-4).all(1)
 print('mode',mode,'n',n_vox,'pass frac',ok.mean(),'fails',(~ok).sum(),'support eq',(sup==ref['support']).mean(),'p50',np.median(rel),'p99',np.percentile(rel,99),'max',rel.max(), 'time',time.time()-t0)
-print('failing idx', np.nonzero(~ok)[0][:20])
+print('failing idx', np.nonzero(~ok)[0][:20], 'lars sign flips', C.c_long.in_dll(lib, 'gm_lars_signflips').value)
