@@ -48,6 +48,24 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
     int i, j, k, a;
     for (j = 0; j < n; ++j) { x[j] = 0; inP[j] = 0; }
     while (np_ < n && np_ < mcap && np_ < CAP) {
+        int aspace_dual = 0;
+        if ((mode & 16) && np_ > 0) {
+            /* exact-fit regime: once the residual has collapsed, c - Hx is rounding noise at 1e-16 |c|; the reference's dual
+             * A'(y - Ax) is not.  Residual in A-space (cheap: m x np), switch when |r|^2 < 1e-12 |y|^2. */
+            double r2 = 0, y2 = 0;
+            static __thread double rr[1024];
+            for (i = 0; i < m; ++i) { double t = y[i]; for (k = 0; k < np_; ++k) t -= A[(size_t)P[k] * m + i] * x[P[k]]; rr[i] = t; r2 += t * t; y2 += y[i] * y[i]; }
+            if (r2 < 1e-12 * y2) {
+                aspace_dual = 1;
+                for (j = 0; j < n; ++j) {
+                    if (inP[j]) { w[j] = 0; continue; }
+                    double acc = 0; for (i = 0; i < m; ++i) acc += A[(size_t)j * m + i] * rr[i];
+                    w[j] = acc;
+                }
+                if (stats) stats[10]++;
+            }
+        }
+        if (!aspace_dual)
         for (j = 0; j < n; ++j) {
             if (inP[j]) { w[j] = 0; continue; }
             double acc = c[j];
