@@ -9,6 +9,7 @@
 #define CAP 64
 double gm_thr = 1e-6;   /* A-space re-evaluation threshold on d2 / H_jj (set from Python) */
 double gm_floor = 0.0;
+long gm_ill_solves = 0, gm_ill_nnls = 0, gm_nnls_calls = 0;  /* refined passive solves / NNLS calls that took a near-dependent atom / all */
 int gm_lars_incr = 0;     /* LARS: path direction u = invGs 1 updated in O(|S|) per step instead of recomputed in O(|S|^2) */
 long gm_lars_signflips = 0;  /* steps where an active correlation was not positive (the incremental form assumes +1) */  /* refined candidates with d2 <= gm_floor * H_jj count as dependent */
 
@@ -42,7 +43,7 @@ static void fwd_subst(double L[CAP][CAP], int np_, const double *g, double *v)
 int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x,
             const double *A, const double *y, int m, int mode, int *stats)
 {
-    int P[CAP], inP[512], np_ = 0, iter = 0, itmax = 3 * n, outer = 0, nrem = 0;
+    int P[CAP], inP[512], np_ = 0, iter = 0, itmax = 3 * n, outer = 0, nrem = 0, ill = 0;  /* ill: a near-dependent atom was accepted */
     static __thread double L[CAP][CAP];
     double w[512], s[CAP], g[CAP], v[CAP], z[CAP];
     int i, j, k, a;
@@ -83,7 +84,7 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
             for (a = 0; a < np_; ++a) { vv += v[a] * v[a]; vz += v[a] * z[a]; }
             d2 = H[(size_t)j * ld + j] - vv;
             if (stats) { double rel = d2 / H[(size_t)j * ld + j]; stats[3]++; if (rel < 1e-6) stats[4]++; if (rel < 1e-8) stats[5]++; if (rel < 1e-10) stats[6]++; if (rel<1e-12) stats[7]++; }
-            double znum = c[j] - vz;
+            double znum = c[j] - vz; int ill_cand = 0;
             if ((mode & 8) && np_ > 0 && d2 < gm_thr * H[(size_t)j * ld + j]) {
                 /* A-space re-evaluation of a near-dependent candidate: r = a_j - A_P beta, beta = L^-T v;
                  * d2 = |r|^2 and the numerator r.y come without the cancellation of H_jj - v.v */
@@ -94,7 +95,7 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
                     for (a = 0; a < np_; ++a) rr -= A[(size_t)P[a] * m + i] * beta[a];
                     acc2 += rr * rr; accy += rr * y[i];
                 }
-                d2 = acc2; znum = accy;
+                d2 = acc2; znum = accy; ill_cand = 1;
                 if (d2 <= gm_floor * H[(size_t)j * ld + j]) d2 = 0;
                 if (stats) stats[9]++;
             }
@@ -102,7 +103,7 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
                 double unorm = sqrt(vv), t = unorm + sqrt(d2) * 0.01;
                 if (t - unorm > 0) {
                     znew = znum / sqrt(d2);
-                    if (znew > 0) break;   /* ztest = znew / sqrt(d2) */
+                    if (znew > 0) { if (ill_cand) ill = 1; break; }   /* ztest = znew / sqrt(d2) */
                 }
             }
             w[j] = 0;
@@ -114,7 +115,8 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
         for (;;) {
             if (++iter > itmax) goto done;
             back_subst(L, np_, z, s);
-            if (mode & 1) {
+            if ((mode & 32) && ill) gm_ill_solves++;
+            if ((mode & 1) || ((mode & 32) && ill)) {
                 double r[1024], q[CAP], dz[CAP], ds[CAP];
                 for (i = 0; i < m; ++i) { double t = y[i]; for (a = 0; a < np_; ++a) t -= A[(size_t)P[a] * m + i] * s[a]; r[i] = t; }
                 for (a = 0; a < np_; ++a) { double t = 0; for (i = 0; i < m; ++i) t += A[(size_t)P[a] * m + i] * r[i]; q[a] = t; }
@@ -155,6 +157,7 @@ int gm_nnls(const double *H, int ld, const double *c, int n, int mcap, double *x
         for (a = 0; a < np_; ++a) x[P[a]] = s[a];
     }
 done:
+    gm_nnls_calls++; if (ill) gm_ill_nnls++;
     if (stats) { stats[0] += outer; stats[1] += iter; stats[2] += nrem; }
     return outer;
 }

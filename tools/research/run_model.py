@@ -43,4 +43,6 @@ r = ref['estimates']
 rel = np.abs(est-r)/np.maximum(np.abs(r),1e-3)
 ok = (rel<=1e-4).all(1)
 print('mode',mode,'n',n_vox,'pass frac',ok.mean(),'fails',(~ok).sum(),'support eq',(sup==ref['support']).mean(),'p50',np.median(rel),'p99',np.percentile(rel,99),'max',rel.max(), 'time',time.time()-t0)
-print('failing idx', np.nonzero(~ok)[0][:20], 'lars sign flips', C.c_long.in_dll(lib, 'gm_lars_signflips').value)
+print('failing idx', np.nonzero(~ok)[0][:20], 'lars sign flips', C.c_long.in_dll(lib, 'gm_lars_signflips').value,
+      'nnls calls', C.c_long.in_dll(lib, 'gm_nnls_calls').value, 'with a near-dependent atom', C.c_long.in_dll(lib, 'gm_ill_nnls').value,
+      'refined passive solves', C.c_long.in_dll(lib, 'gm_ill_solves').value)
