@@ -603,6 +603,8 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.fast_lars = env_int("AMX_FAST_LARS", 1);
     p.compact3 = env_int("AMX_COMPACT3", 1);
     p.aspace = env_int("AMX_ASPACE", 1);
+    p.refine = env_int("AMX_REFINE", 1);
+    p.cta_chunk = std::max(0, env_int("AMX_CTA_CHUNK", 0));
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);

@@ -226,6 +226,7 @@ struct FitParams {
     int m_pad, dc_pad;
     int fast_lars;    // NODDI stage 2: throughput-oriented LARS (same path, fused arithmetic)
     int aspace;       // NODDI NNLS stages: A-space re-evaluation of near-dependent candidate columns
+    int refine;       // ... and A-space refinement of the passive solves after such a column was accepted
     int compact3;     // NODDI stage 3: NNLS on the compact support system (one atom per lane) when the support fits a warp
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
@@ -234,6 +235,7 @@ struct FitParams {
     int *ovf_list;       // voxels whose active set outgrew a warp: re-fitted by the scalar slow path (amx_slow.cuh)
     long long ovf_cap;
     unsigned *supmask;   // split NODDI path: [n_vox][NPL] stage-2 support, word s bit l <-> atom l + 32 s
+    int cta_chunk;       // stage kernels: batches are handed out to a CTA in runs of this many consecutive ones (0: one global queue)
 };
 
 struct WarpWS {
@@ -809,6 +811,38 @@ __device__ __forceinline__ void queue_slow(const FitParams &p, long long vox, in
     }
 }
 
+// Batch hand-out of the stage kernels.  The batch list is sorted by LUT direction, so CONSECUTIVE batches share their Gram tables:
+// a CTA takes runs of `chunk` consecutive batches (one global atomic per run) and its warps take single batches out of the run
+// through a shared-memory ticket counter -- the warps of an SM then work on the same direction(s) and the Gram rows they re-read
+// hit L1 instead of L2.  No CTA barrier: the warp that draws the first ticket of a run fetches it and publishes its base in a ring
+// of four slots; a warp holds one ticket at a time, so at most two runs are ever live.
+// hdr: [0] ticket counter, [1..4] run base, [5..8] run id + 1 (ready flag); zeroed by the kernel prologue.
+__device__ __forceinline__ int next_batch(int *hdr, int *counter, int chunk, int lane)
+{
+    int b = 0;
+    if (lane == 0) {
+        if (chunk <= 0) {
+            b = atomicAdd(counter, 1);
+        } else {
+            const int t = atomicAdd(&hdr[0], 1);
+            const int run = t / chunk, slot = t - run * chunk, q = run & 3;
+            volatile int *vh = hdr;
+            if (slot == 0) {
+                const int base = atomicAdd(counter, chunk);
+                vh[1 + q] = base;
+                __threadfence_block();
+                vh[5 + q] = run + 1;
+                b = base;
+            } else {
+                while (vh[5 + q] != run + 1) { }
+                __threadfence_block();
+                b = vh[1 + q] + slot;
+            }
+        }
+    }
+    return __shfl_sync(FULL, b, 0);
+}
+
 // ------------------------------------------------------------------------------------------------
 // NODDI as three stage kernels over the same batch queue (STAGE 1: NNLS for the isotropic fraction, 2: LARS support
 // selection, 3: NNLS on the support + maps).  Same arithmetic as k_fit_noddi_batched; the split exists because the
@@ -833,10 +867,11 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
     for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
     int *counter = p.tile_counter + (STAGE - 1);
     const int n_tiles = *p.n_tiles_ptr;
+    int *hdr = (int *)smem;
+    if (threadIdx.x < 16) hdr[threadIdx.x] = 0;
+    __syncthreads();
     for (;;) {
-        int b = 0;
-        if (lane == 0) b = atomicAdd(counter, 1);
-        b = __shfl_sync(FULL, b, 0);
+        const int b = next_batch(hdr, counter, p.cta_chunk, lane);
         if (b >= n_tiles) break;
         const int4 tile = p.tiles[b];
         const int nb = tile.z;  // <= BV
@@ -891,7 +926,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
-                const ASpace asp{(const float *)S, n_pad, m, p.y, p.y_f64, (long long)p.order[pos]};
+                const ASpace asp{(const float *)S, n_pad, m, p.y, p.y_f64, (long long)p.order[pos], p.refine};
                 const ASpace *as = (p.aspace && sizeof(TS) == 4) ? &asp : nullptr;
                 if (STAGE == 1) {  // isotropic fraction (amico/models.pyx:911)
                     int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr, cap, nullptr, as);

@@ -54,7 +54,39 @@ struct NnlsStat {
 struct ASpace {
     const float *S; int n_pad, m;
     const void *y; int y_f64; long long vox;
+    int refine;  // A-space refinement of the passive solves once a near-dependent atom has been accepted
 };
+
+// One step of iterative refinement of a passive solve in A-space (the corrected semi-normal equations):
+//   r = y - A_P s,  s += (L L^T)^-1 A_P^T r.
+// Needed only once a near-dependent atom sits in the passive set: H_PP then has condition ~1e14 and the Cholesky solution is
+// inaccurate along the near-null direction (residual 1e-7 instead of the 1e-15 the reference's Householder QR reaches,
+// amico/models.pyx:911, 940), which is visible on exact-fit (noise-free) voxels.  Lane a holds s_a; rows of A go lane per row.
+template <bool MAPPED>
+__device__ __noinline__ double nnls_refine(const ASpace *as, const double *Lp, const double *rd, int np, const int *P, const int *map,
+                                           double s, int lane)
+{
+    double q = 0.0;  // lane a: (A_P^T r)_a
+    #pragma unroll 1
+    for (int i0 = 0; i0 < as->m; i0 += 32) {
+        const int i = i0 + lane;
+        const bool on = i < as->m;
+        const float *Si = as->S + (size_t)(on ? i : 0) * as->n_pad;
+        double r = 0.0;
+        if (on) r = as->y_f64 ? ((const double *)as->y)[as->vox * as->m + i] : (double)((const float *)as->y)[as->vox * as->m + i];
+        #pragma unroll 1
+        for (int a = 0; a < np; ++a) r = fma(-(double)Si[MAPPED ? map[P[a]] : P[a]], shfl(s, a), r);
+        if (!on) r = 0.0;
+        #pragma unroll 1
+        for (int a = 0; a < np; ++a) {
+            const double pa = warp_sum((double)Si[MAPPED ? map[P[a]] : P[a]] * r);
+            if (lane == a) q += pa;
+        }
+    }
+    const double dz = fwd_subst(Lp, rd, np, lane < np ? q : 0.0, lane);
+    const double ds = back_subst(Lp, rd, np, lane < np ? dz : 0.0, lane);
+    return lane < np ? s + ds : 0.0;
+}
 
 // min 1/2 x'Tx - c'x, x >= 0 over the atoms whose bit is set in `allowed` (bit s of lane l <-> atom
 // l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays.  mcap = number of rows of the
@@ -71,6 +103,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
     auto AT = [&](int q) { return MAPPED ? map[q] : q; };  // compact index -> atom (= Gram table row / column)
     const int mycol = MAPPED ? map[lane < n ? lane : 0] : 0;
     int np = 0, iter = 0, overflow = 0;
+    bool ill = false;  // a near-dependent atom was accepted: passive solves get one A-space refinement step from here on
     cap = min(cap, c_lc_cap);
     unsigned inP = 0;
     double xp = 0.0, zl = 0.0;
@@ -115,6 +148,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
         // candidate selection
         int j = -1;
         double v = 0.0, d2 = 0.0, znum = 0.0;
+        bool near_dep = false;
         for (;;) {
             double bv = 0.0;
             int bj = -1;
@@ -131,7 +165,9 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             const double hjj = T[(size_t)AT(j) * (ldT + 1)];
             d2 = hjj - vv;
             znum = c[j] - vz;
+            near_dep = false;
             if (as && np > 0 && d2 < 1e-10 * hjj) {
+                near_dep = true;
                 // Near-dependent candidate: H_jj - v.v has lost its digits (the Gram form squares the conditioning; below ~1e-13 H_jj
                 // it is rounding noise of either sign) and so has c_j - v.z -- yet the NODDI dictionary really holds atoms that are
                 // independent of the passive set only at the 1e-7 level (d2 ~ 1e-14 H_jj), and the reference's Householder QR
@@ -178,6 +214,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             }
         }
         if (j < 0) break;
+        ill |= near_dep;
         // move j to the passive set: append a row to the factor
         {
             const double ird = rsqrt(d2), dd = d2 * ird;
@@ -201,6 +238,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             if (++iter > itmax) goto done;
             if (st) ++st->inner;
             s = back_subst(Lp, rd, np, (lane < np) ? zl : 0.0, lane);
+            if (ill && as->refine) s = nnls_refine<MAPPED>(as, Lp, rd, np, P, map, s, lane);
             bool neg = (lane < np) && (s <= 0.0);
             if (!__any_sync(FULL, neg)) break;
             double tmin = INFINITY;

@@ -263,6 +263,85 @@ def make_voxels(model, K, htable, n_vox, seed, snr=30.0, iso_max=0.5):
     return y, dirs
 
 
+def lut_index_torch(dirs, htable_dev):
+    """``lut_index_numpy`` on a CUDA tensor (float64 (n, 3)); ``htable_dev``: the hash table as an int64 CUDA tensor."""
+    import torch
+    d = torch.where(dirs[:, 1:2] < 0, -dirs, dirs)
+    two_pi = 2.0 * math.pi
+    i2 = torch.fmod(torch.atan2(d[:, 1], d[:, 0]), two_pi)
+    i2 = torch.where(i2 < 0, torch.fmod(i2 + two_pi, two_pi), i2)
+    big = i2 > math.pi
+    rxy = torch.sqrt(d[:, 0] ** 2 + d[:, 1] ** 2)
+    i1 = torch.where(big, torch.atan2(rxy, -d[:, 2]), torch.atan2(rxy, d[:, 2]))
+    i2 = torch.where(big, torch.fmod(torch.atan2(-d[:, 1], -d[:, 0]), two_pi), i2)
+    c_round = lambda x: torch.sign(x) * torch.floor(torch.abs(x) + 0.5)
+    ii1 = c_round(i1 / math.pi * 180.0).long()
+    ii2 = c_round(i2 / math.pi * 180.0).long()
+    return htable_dev[ii1 * 181 + ii2]
+
+
+def make_voxels_torch(model, K, htable, n_vox, seed, device, snr=30.0, iso_max=0.5, chunk=1 << 20):
+    """``make_voxels`` generated ON the GPU in chunks (same recipe: 1-2 atoms + isotropic fraction, Rician noise; torch's
+    generator, so not the numpy stream) -- for the volumes of BASELINE cfg3 / cfg5 whose float64 intermediates (10.5 M x 288) do
+    not belong on the host.  Returns CUDA tensors ``y`` (n_vox, m) float32 and ``dirs`` (n_vox, 3) float64."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    if model == "NODDI":
+        rot, iso = K["wm"], K["iso"][None, :]
+    elif model in ("FreeWater", "FreeWaterMouse"):
+        rot, iso = K["D"], K["CSF"]
+    elif model == "CylinderZeppelinBall":
+        rot, iso = np.concatenate([K["wmr"], K["wmh"]]), K["iso"]
+    else:
+        raise ValueError(model)
+    rot_d = torch.from_numpy(np.ascontiguousarray(rot, dtype=np.float32)).to(device)
+    iso_d = torch.from_numpy(np.ascontiguousarray(iso, dtype=np.float32)).to(device)
+    ht = torch.from_numpy(np.asarray(htable).astype(np.int64)).to(device)
+    n_rot, _, m = rot_d.shape
+    y = torch.empty((n_vox, m), dtype=torch.float32, device=device)
+    dirs = torch.empty((n_vox, 3), dtype=torch.float64, device=device)
+    sigma = 1.0 / snr
+    for o in range(0, n_vox, chunk):
+        c = min(chunk, n_vox - o)
+        v = torch.randn((c, 3), generator=g, device=device, dtype=torch.float64)
+        d = v / v.norm(dim=1, keepdim=True)
+        k = lut_index_torch(d, ht)
+        u = torch.rand((c, 3), generator=g, device=device, dtype=torch.float32)
+        f_iso = (u[:, 0] * iso_max)[:, None]
+        w1 = torch.where(u[:, 1] < 0.5, 0.3 + 0.4 * u[:, 2], torch.ones_like(u[:, 2]))[:, None]
+        j1 = torch.randint(0, n_rot, (c,), generator=g, device=device)
+        j2 = torch.randint(0, n_rot, (c,), generator=g, device=device)
+        ji = torch.randint(0, iso_d.shape[0], (c,), generator=g, device=device)
+        sig = (1 - f_iso) * (w1 * rot_d[j1, k] + (1 - w1) * rot_d[j2, k]) + f_iso * iso_d[ji]
+        re = sig + sigma * torch.randn((c, m), generator=g, device=device, dtype=torch.float32)
+        im = sigma * torch.randn((c, m), generator=g, device=device, dtype=torch.float32)
+        y[o:o + c] = torch.sqrt(re * re + im * im)
+        dirs[o:o + c] = d
+    return y, dirs
+
+
+def make_sandi_raw_torch(scheme_full, n_vox, seed, device, snr=30.0, chunk=1 << 19):
+    """Raw (un-normalised, un-averaged) SANDI volume (n_vox, nS) float32 on the GPU: the isotropic bi-exponential signal of
+    ``make_raw_volume`` times S0 ~ U(400, 1600), Rician noise."""
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    b = torch.from_numpy(np.asarray(scheme_full.b, dtype=np.float32) * 1e-3).to(device)[None, :]
+    nS = b.shape[1]
+    out = torch.empty((n_vox, nS), dtype=torch.float32, device=device)
+    sigma = 1.0 / snr
+    for o in range(0, n_vox, chunk):
+        c = min(chunk, n_vox - o)
+        u = torch.rand((c, 3), generator=g, device=device, dtype=torch.float32)
+        d, f, s0 = 0.3 + 2.2 * u[:, 0:1], 0.2 + 0.6 * u[:, 1:2], 400.0 + 1200.0 * u[:, 2:3]
+        sig = f * torch.exp(-b * d) + (1 - f) * torch.exp(-b * 0.2 * d)
+        re = sig + sigma * torch.randn((c, nS), generator=g, device=device, dtype=torch.float32)
+        im = sigma * torch.randn((c, nS), generator=g, device=device, dtype=torch.float32)
+        out[o:o + c] = torch.sqrt(re * re + im * im) * s0
+    return out
+
+
 @dataclass
 class Problem:
     """Everything ``model.fit(evaluation)`` reads, for one synthetic config."""

@@ -4,16 +4,17 @@ land in the git-ignored ``oracle/_ref/``).
 
 TEST INFRASTRUCTURE ONLY (see ``amico_oracle.c``).  What this gives:
 
-* ``amico.models`` / ``amico.lut`` of daducci/AMICO cythonized UNMODIFIED (``util``, ``scheme``,
-  ``synthesis`` byte-compiled): every line of chunking, dictionary assembly, NODDI stage logic, clamps, map formulas
+* ``amico.models`` / ``amico.lut`` of daducci/AMICO cythonized UNMODIFIED, and the three pure-Python modules they import
+  (``util``, ``scheme``, ``synthesis``) cythonized the same way -- binaries only, so that everything travels to the GPU
+  box like any other built ``.so`` (a sourceless ``.pyc`` may be dropped by a snapshot filter): every line of chunking, dictionary assembly, NODDI stage logic, clamps, map formulas
   and fit errors is the reference's;
 * the two solver entry points it cimports from the absent third-party ``spams-cython``
   (``cyspams.interfaces.nnls`` / ``.lasso``, amico/models.pyx:18) are bound to the restated
   solvers of ``amico_oracle.c`` through a shim ``cyspams`` package -- so this arm validates the
   oracle's *glue* bit-for-bit and serves as the "reference glue + restated solvers" CPU baseline,
   it does NOT pin the solvers themselves;
-* ``dicelib.ui.ProgressBar`` and the three dipy symbols ``amico.lut`` imports are stubbed (they
-  are only exercised by kernel generation, which is outside the hot path).
+* ``dicelib.ui.ProgressBar`` and the three dipy symbols ``amico.lut`` imports are stubbed at import time by
+  ``ref_runner._install_stubs`` (they are only exercised by kernel generation, which is outside the hot path).
 
 Run:  python oracle/build_ref.py        (needs /root/reference, Cython, g++)
 """
@@ -51,29 +52,9 @@ STUBS = {
             orc_lasso(A, y, m, n, p, x, l1, l2);
         }
         """),
-    "dicelib/__init__.py": "",
-    "dicelib/ui.py": textwrap.dedent("""\
-        class ProgressBar:
-            \"\"\"No-op stand-in for dicelib.ui.ProgressBar (call shapes: models.pyx:304-310, 802; core.py:457).\"\"\"
-            def __init__(self, total=None, multithread_progress=None, disable=False, **kw):
-                pass
-            def __enter__(self):
-                return self
-            def __exit__(self, *a):
-                return False
-            def update(self, *a, **kw):
-                pass
-        """),
-    "dipy/__init__.py": "",
-    "dipy/data/__init__.py": "",
-    "dipy/data/fetcher.py": "import os\ndipy_home = os.path.join(os.path.expanduser('~'), '.dipy')\n",
-    "dipy/core/__init__.py": "",
-    "dipy/core/geometry.py": "def cart2sphere(*a, **k):\n    raise NotImplementedError('dipy stub (oracle/_ref)')\n",
-    "dipy/reconst/__init__.py": "",
-    "dipy/reconst/shm.py": "def real_sh_descoteaux(*a, **k):\n    raise NotImplementedError('dipy stub (oracle/_ref)')\n",
 }
 
-PY_MODULES = ["util.py", "synthesis.py", "scheme.py"]  # byte-compiled (sourceless .pyc) into _ref
+PY_MODULES = ["util.py", "synthesis.py", "scheme.py"]  # pure Python in the reference: cythonized to extension modules too
 MODULES = ["lut.pyx", "models.pyx"]
 
 
@@ -96,14 +77,23 @@ def build():
     ext = sysconfig.get_config_var("EXT_SUFFIX")
     obj = os.path.join(bdir, "amico_oracle.o")
     run(["gcc", "-O2", "-fPIC", "-std=c99", "-c", os.path.join(HERE, "amico_oracle.c"), "-o", obj])
-    import py_compile
-    for mod in PY_MODULES:
-        py_compile.compile(os.path.join(REF, "amico", mod), cfile=os.path.join(OUT, "amico", mod + "c"), doraise=True)
-    for mod in MODULES:
+    for stale in os.listdir(os.path.join(OUT, "amico")):
+        if stale.endswith(".pyc"):
+            os.remove(os.path.join(OUT, "amico", stale))
+    for mod in PY_MODULES + MODULES:
         name = mod.split(".")[0]
         cpp = os.path.join(bdir, name + ".cpp")
-        run([sys.executable, "-m", "cython", "--cplus", "-3", "-I", OUT, "-I", REF,
-             os.path.join(REF, "amico", mod), "-o", cpp])
+        src = os.path.join(REF, "amico", mod)
+        if mod.endswith(".py"):
+            # CPython accepts the reference's util.py (tabs in some functions, spaces in others), Cython does not: compile a
+            # scratch copy with the tabs expanded (whitespace only; lives in the build directory that is removed below)
+            with open(src) as f:
+                text = f.read().expandtabs(4)
+            src = os.path.join(bdir, mod)
+            with open(src, "w") as f:
+                f.write(text)
+        # --module-name: the .py files would otherwise be compiled as top-level modules
+        run([sys.executable, "-m", "cython", "--cplus", "-3", "-I", OUT, "-I", REF, "--module-name", "amico." + name, src, "-o", cpp])
         so = os.path.join(OUT, "amico", name + ext)
         # the reference builds with -std=c++14 -Ofast (setup.py:40); -O3 keeps IEEE semantics so
         # that this arm is comparable bit-for-bit with the plain-C oracle

@@ -15,11 +15,72 @@ _REF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 
 
 def available():
-    return os.path.isdir(os.path.join(_REF, "amico")) and any(
-        f.startswith("models.") and f.endswith(".so") for f in os.listdir(os.path.join(_REF, "amico")))
+    d = os.path.join(_REF, "amico")
+    need = ("models.", "lut.", "util.", "scheme.", "synthesis.")
+    return os.path.isdir(d) and all(any(f.startswith(n) and f.endswith(".so") for f in os.listdir(d)) for n in need)
+
+
+class _ProgressBar:
+    """No-op stand-in for dicelib.ui.ProgressBar (call shapes: amico/models.pyx:304-310, 802; core.py:457)."""
+
+    def __init__(self, total=None, multithread_progress=None, disable=False, **kw):
+        pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def update(self, *a, **kw):
+        pass
+
+
+def _stub(*a, **k):
+    raise NotImplementedError("dipy stub (oracle/_ref): only kernel generation calls this, which is outside the hot path")
+
+
+def _install_stubs():
+    """The compiled reference modules import dicelib.ui.ProgressBar and three dipy symbols at import time; neither package is
+    installed here.  The stand-ins are created in sys.modules (not as files), so that oracle/_ref needs nothing but its
+    extension modules to be usable on a box that received only the built binaries."""
+    import types
+
+    def mod(name, **attrs):
+        if name in sys.modules:
+            return sys.modules[name]
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        if "." in name:
+            setattr(sys.modules[name.rsplit(".", 1)[0]], name.rsplit(".", 1)[1], m)
+        sys.modules[name] = m
+        return m
+
+    try:
+        import dicelib.ui  # noqa: F401
+    except Exception:
+        mod("dicelib", __path__=[])
+        mod("dicelib.ui", ProgressBar=_ProgressBar)
+    try:
+        import dipy.reconst.shm  # noqa: F401
+        import dipy.core.geometry  # noqa: F401
+        import dipy.data.fetcher  # noqa: F401
+    except Exception:
+        for k in [k for k in sys.modules if k == "dipy" or k.startswith("dipy.")]:
+            del sys.modules[k]
+        mod("dipy", __path__=[])
+        mod("dipy.data", __path__=[])
+        mod("dipy.data.fetcher", dipy_home=os.path.join(os.path.expanduser("~"), ".dipy"))
+        mod("dipy.core", __path__=[])
+        mod("dipy.core.geometry", cart2sphere=_stub)
+        mod("dipy.reconst", __path__=[])
+        mod("dipy.reconst.shm", real_sh_descoteaux=_stub)
+    if "amico" not in sys.modules and not os.path.exists(os.path.join(_REF, "amico", "__init__.py")):
+        mod("amico", __path__=[os.path.join(_REF, "amico")])
 
 
 def _models():
+    _install_stubs()
     if _REF not in sys.path:
         sys.path.insert(0, _REF)
     util = importlib.import_module("amico.util")

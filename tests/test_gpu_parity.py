@@ -130,7 +130,7 @@ def test_noddi_vs_oracle_across_noise_levels(snr, seed):
     frac = pass_fraction(got["estimates"], ref["estimates"])
     sup = float((got["support"] == ref["support"]).mean())
     print(f"SNR {snr}: pass fraction {frac:.5f}, support equality {sup:.5f}")
-    assert frac >= 0.9995 and sup >= 0.9995
+    assert frac >= 0.9999 and sup >= 0.9999
 
 
 def test_noddi_exvivo_vs_oracle():
@@ -139,7 +139,7 @@ def test_noddi_exvivo_vs_oracle():
     ref = orc().fit_problem(P, nthreads=os.cpu_count())
     got = gpu_fit(P)
     assert got["estimates"].shape == (4000, 4)
-    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.9999
 
 
 def test_noddi_known_answers():
@@ -156,15 +156,22 @@ def test_noddi_known_answers():
     P.y = y  # float64 input path
     got = gpu_fit(P)
     ref = orc().fit_problem(P)
-    # Exact-fit voxels are the one regime where Gram space and A space part ways: once the true atoms are in, the dual is pure
-    # rounding noise -- 1e-14 |c| for c - Hx, 1e-17 for A^T(y - Ax) -- and the remaining pivots are decided by it.  The oracle
-    # recovers the truth to 1e-8; the GPU stays within 2e-3 of it, and within 1e-4 of the oracle on >= 98 % of such voxels.
-    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.98
+    # Exact-fit voxels: once the true atoms are in, the passive system holds near-dependent columns (cond(H_PP) ~ 1e14) and the
+    # plain Cholesky solve is off along the near-null direction; the A-space refinement step of warp_nnls (nnls_refine) brings the
+    # passive solves back to the accuracy of the reference's Householder QR.  Bars: >= 99.9 % of the voxels within 1e-4 of the
+    # oracle, and the generating grid values recovered to 1e-6 relative (SURVEY section 4's known-answer case).
+    frac = pass_fraction(got["estimates"], ref["estimates"])
     e = got["estimates"]
     assert np.allclose(e[0], [0.0, 1.0, 0.0])
     vf, od = P.params["IC_VFs"][j % 12], P.params["IC_ODs"][j // 12]
-    good = (np.abs(e[1:, 0] - vf[1:]) < 0.02) & (np.abs(e[1:, 1] - od[1:]) < 0.02) & (np.abs(e[1:, 2] - f[1:]) < 0.01)
-    assert good.mean() > 0.9
+    truth = np.stack([vf, od, f], axis=1)[1:]
+    rel = np.abs(e[1:] - truth) / np.maximum(np.abs(truth), 1e-3)
+    rel_o = np.abs(ref["estimates"][1:] - truth) / np.maximum(np.abs(truth), 1e-3)
+    good = (rel <= 1e-6).all(axis=1)
+    print(f"known answers: within 1e-4 of the oracle {frac:.5f}; truth recovered to 1e-6: GPU {good.mean():.5f}, oracle {(rel_o <= 1e-6).all(axis=1).mean():.5f}; "
+          f"max rel GPU {rel.max():.2e}, oracle {rel_o.max():.2e}")
+    assert frac >= 0.999
+    assert good.mean() >= 0.999
 
 
 # ----------------------------------------------------------------------------------------------- golden fixtures
@@ -176,7 +183,7 @@ def test_golden_reference_glue(name, cfg, model, n_vox, seed):
     P = synth.make_problem(cfg, n_vox=n_vox, model=model, seed=seed)
     got = gpu_fit(P, rmse=True, nrmse=True, extra=model in ("NODDI", "FreeWater", "FreeWaterMouse"))
     if model == "NODDI":
-        assert pass_fraction(got["estimates"], g["estimates"]) >= 0.995
+        assert pass_fraction(got["estimates"], g["estimates"]) == 1.0
         assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
     else:
         for k in ("estimates", "rmse", "nrmse", "y_corrected"):
@@ -190,7 +197,7 @@ def test_golden_on_reference_direction_set():
     P = synth.make_problem(2, n_vox=384, seed=77, lut_dirs=g["lut_dirs"], htable=g["htable"])
     got = gpu_fit(P, rmse=True, debug=True)
     assert np.array_equal(got["lut"], synth.lut_index_numpy(np.array(P.DIRs), g["htable"]))
-    assert pass_fraction(got["estimates"], g["estimates"]) >= 0.995
+    assert pass_fraction(got["estimates"], g["estimates"]) == 1.0
     assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
 
 
@@ -227,7 +234,7 @@ def test_single_b0_scheme_rows():
     P = synth.Problem(0, "NODDI", scheme, lut, ht, K, p, y, dirs)
     ref = orc().fit_problem(P, nthreads=os.cpu_count())
     got = gpu_fit(P)
-    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.9999
 
 
 def test_device_tensor_path_matches_host_path():
@@ -270,7 +277,7 @@ def test_model_plugin_surface_end_to_end():
     ref = orc().fit_problem(P, rmse=True, extra=True, return_debug=True)
     assert set(res) == {"estimates", "rmse", "estimates_mod"}
     assert res["estimates"].dtype == np.float64 and res["estimates"].shape == (2000, 3)
-    assert pass_fraction(res["estimates"], ref["estimates"]) >= 0.998
+    assert pass_fraction(res["estimates"], ref["estimates"]) >= 0.9999
     # contiguous float64 DIRs are flipped in place, exactly like the reference (SURVEY 8a quirk i)
     assert np.array_equal(ev.DIRs, ref["dirs"]) and not np.array_equal(ev.DIRs, before)
 
@@ -310,7 +317,7 @@ def test_full_size_properties():
         idx = np.arange(0, n, n // 20000)[:20000]
         Q = synth.Problem(P.cfg, P.model, P.scheme, P.lut_dirs, P.htable, P.KERNELS, P.params, P.y[idx], P.DIRs[idx])
         ref = orc().fit_problem(Q, nthreads=os.cpu_count())
-        assert pass_fraction(a.cpu().numpy()[idx], ref["estimates"]) >= 0.999
+        assert pass_fraction(a.cpu().numpy()[idx], ref["estimates"]) >= 0.9999
 
 
 # ----------------------------------------------------------------------------------------------- host pipeline / variants
@@ -371,8 +378,23 @@ def test_noddi_whole_brain_protocol_m288():
     ref = orc().fit_problem(P, nthreads=os.cpu_count(), return_debug=True)
     got = gpu_fit(P, debug=True)
     assert got["_counters"]["overflow_voxels"] == 0
-    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.998
-    assert float((got["support"] == ref["support"]).mean()) >= 0.998
+    assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.9999
+    assert float((got["support"] == ref["support"]).mean()) >= 0.9999
+
+
+@pytest.mark.parametrize("cfg,n_vox", [(2, 262144), (3, 65536)])
+def test_noddi_parity_at_scale(cfg, n_vox):
+    """The measurement tools/parity_at_scale.py records (profiles/parity_r0N.json) as a test: a quarter of the cfg2 volume /
+    65,536 voxels of the cfg3 protocol against the oracle; at most 1 voxel in 10,000 may leave the 1e-4 band."""
+    P = synth.make_problem(cfg, n_vox=n_vox, seed=4242)
+    ref = orc().fit_problem(P, return_debug=True, nthreads=os.cpu_count())
+    got = gpu_fit(P, debug=True)
+    rel = rel_err(got["estimates"], ref["estimates"])
+    frac = float((rel <= TOL).all(axis=1).mean())
+    sup = float((got["support"] == ref["support"]).mean())
+    print(f"cfg{cfg} at scale: {n_vox} voxels, pass fraction {frac:.6f}, support equality {sup:.6f}, p99 {np.percentile(rel, 99):.2e}, max {rel.max():.2e}")
+    assert np.array_equal(got["lut"], ref["lut"])
+    assert frac >= 0.9999 and sup >= 0.9999
 
 
 def test_large_active_sets_take_the_slow_path(monkeypatch):

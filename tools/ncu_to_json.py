@@ -29,6 +29,15 @@ for vals in rows[2:]:
     st = {h.replace("smsp__average_warps_issue_stalled_", "").replace("_per_issue_active.ratio", ""): round(float(v), 2)
           for h, v in d.items() if h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio") and float(v) >= 0.1}
     k["stalls_warp_cycles_per_issue"] = dict(sorted(st.items(), key=lambda kv: -kv[1]))
+    # scalar FP64 flop of the launch: thread-level DADD + DMUL + 2 DFMA (per-cycle sums over the sub-partitions x elapsed cycles);
+    # the DMMA tensor flop are counted analytically by bench.py (2 m x padded atoms per voxel and A^T Y product)
+    try:
+        cyc = float(d["smsp__cycles_elapsed.avg"])
+        per = {op: float(d[f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"]) for op in ("dadd", "dmul", "dfma")}
+        k["fp64_flop_scalar"] = (per["dadd"] + per["dmul"] + 2.0 * per["dfma"]) * cyc
+        k["smsp__cycles_elapsed.avg"] = cyc
+    except (KeyError, ValueError):
+        pass
     if len(sys.argv) > 3:
         k["n_vox"] = int(sys.argv[3])
     k["command"] = sys.argv[2] if len(sys.argv) > 2 else ""
