@@ -2,6 +2,7 @@
 #include "../../include/amico_b200.h"
 #include "amx_kernels.cuh"
 #include "amx_slow.cuh"
+#include "amx_exact.cuh"
 #include "amx_err.h"
 
 #include <algorithm>
@@ -96,14 +97,14 @@ struct amx_plan {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
     // per-launch workspace; two sets so that consecutive voxel chunks can be in flight on two compute streams
-    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws; } work[2];
+    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws, exact_list, exact_a; } work[2];
     cudaStream_t cs[2] = {nullptr, nullptr};          // [0] == stream
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
     int max_smem = 0, sm_count = 0;
     // last-call records
     double last_ms[8] = {0};
-    int64_t last_cnt[8] = {0};
+    int64_t last_cnt[16] = {0};
     bool timing_valid = false;
 };
 
@@ -236,7 +237,8 @@ int amx_plan_destroy(amx_plan *pl)
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &wk : pl->work) {
-        DevBuf *bufs[] = {&wk.lut, &wk.order, &wk.bins, &wk.tiles, &wk.status, &wk.scratch, &wk.xiso, &wk.supmask, &wk.ovf_list, &wk.slow_ws};
+        DevBuf *bufs[] = {&wk.lut, &wk.order, &wk.bins, &wk.tiles, &wk.status, &wk.scratch, &wk.xiso, &wk.supmask, &wk.ovf_list, &wk.slow_ws,
+                          &wk.exact_list, &wk.exact_a};
         for (DevBuf *b : bufs) b->release();
     }
     if (pl->cs[1]) cudaStreamDestroy(pl->cs[1]);
@@ -469,6 +471,16 @@ int launch_noddi_split(const FitParams &p, int grid, int block, size_t smem, cud
     return launch_noddi_split_t<NPL, 512>(p, grid, block, smem, st);
 }
 
+template <int NPL>
+int launch_noddi_exact(const FitParams &p, int grid, size_t smem, long long *status, double *scratch_a, cudaStream_t st)
+{
+    auto kern = k_noddi_exact<NPL, float>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, 32 * NPL, smem, st>>>(p, p.exact_list, status, scratch_a);
+    CK(cudaGetLastError());
+    return AMX_OK;
+}
+
 template <int MODEL, int NPL, typename TS>
 int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
@@ -603,8 +615,6 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.fast_lars = env_int("AMX_FAST_LARS", 1);
     p.compact3 = env_int("AMX_COMPACT3", 1);
     p.aspace = env_int("AMX_ASPACE", 1);
-    p.refine = env_int("AMX_REFINE", 1);
-    p.cta_chunk = std::max(0, env_int("AMX_CTA_CHUNK", 0));
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);
@@ -643,9 +653,20 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         CK(wk.supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
         p.xiso = (double *)wk.xiso.p;
         p.supmask = (unsigned *)wk.supmask.p;
-        p.ovf_cap = 3 * n_vox;
+        p.ovf_cap = 4 * n_vox;
         CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
         p.ovf_list = (int *)wk.ovf_list.p;
+        // per-chunk queue counters (the consumers add them to the call totals in status[6], status[7])
+        CK(cudaMemsetAsync(status + 2, 0, sizeof(long long), st));
+        CK(cudaMemsetAsync(status + 4, 0, sizeof(long long), st));
+        p.exact_tol = 0.0;
+        if (p.batched == 2) {
+            const char *tol = getenv("AMX_EXACT_TOL");
+            p.exact_tol = (tol && *tol) ? atof(tol) : 1e-6;
+            p.exact_cap = n_vox;
+            CK(wk.exact_list.reserve((size_t)n_vox * sizeof(int)));
+            p.exact_list = (int *)wk.exact_list.p;
+        }
     }
     int rc;
     switch (pl->model) {
@@ -658,6 +679,24 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     }
     if (rc) return rc;
     *launches += (p.batched == 2) ? 3 : 1;
+    if (p.batched == 2 && p.exact_tol > 0.0) {
+        // exact-fit voxels queued by stage 1 are re-fitted from scratch by the reference's own algorithm (A-space Lawson-Hanson
+        // with Householder QR, amx_exact.cuh); unconditional launch, returns at once when the queue is empty
+        const int m_pad = (pl->m + 1) & ~1, dc_pad = (pl->dc + 1) & ~1;
+        const size_t smem_x = (size_t)(ws_doubles_for(p.NA, m_pad, dc_pad, 0, LC) + exact_extra_doubles(pl->m, p.NA)) * sizeof(double);
+        if (smem_x <= (size_t)pl->max_smem) {
+            const int grid_x = (int)std::max<long long>(1, std::min<long long>(n_vox, (long long)pl->sm_count * 6));
+            CK(wk.exact_a.reserve((size_t)grid_x * pl->m * pl->n * sizeof(double)));
+            switch (pl->npl) {
+            case 1: rc = launch_noddi_exact<1>(p, grid_x, smem_x, status, (double *)wk.exact_a.p, st); break;
+            case 2: rc = launch_noddi_exact<2>(p, grid_x, smem_x, status, (double *)wk.exact_a.p, st); break;
+            case 3: case 4: rc = launch_noddi_exact<4>(p, grid_x, smem_x, status, (double *)wk.exact_a.p, st); break;
+            default: rc = launch_noddi_exact<5>(p, grid_x, smem_x, status, (double *)wk.exact_a.p, st); break;
+            }
+            if (rc) return rc;
+            *launches += 1;
+        }
+    }
     if (p.batched == 2) {
         // voxels whose active set outgrew a warp (possible with a small lambda1) are re-fitted by the scalar slow path;
         // the launch is unconditional and returns at once when the queue is empty
@@ -762,7 +801,7 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     cudaStream_t s_in = (host && nset > 1) ? pl->s_in : st, s_out = (host && nset > 1) ? pl->s_out : st;
     CK(cudaEventRecord(pl->ev[3], st));
     {
-        long long init[4] = {0, (long long)1 << 62, 0, 0};
+        long long init[8] = {0, (long long)1 << 62, 0, 0, 0, 0, 0, 0};
         for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(pl->work[b].status.p, init, sizeof init, cudaMemcpyHostToDevice, st));
     }
     {
@@ -847,7 +886,7 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
         }
     }
     CK(cudaEventRecord(pl->ev[4], st));
-    long long h_status[2][4] = {{0, (long long)1 << 62, 0, 0}, {0, (long long)1 << 62, 0, 0}};
+    long long h_status[2][8] = {{0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}, {0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}};
     for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(h_status[b], pl->work[b].status.p, sizeof h_status[b], cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f;
@@ -861,7 +900,8 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     pl->last_cnt[0] = launches;
     const long long bad = h_status[0][0] | h_status[1][0], bad_vox = std::min(h_status[0][1], h_status[1][1]);
     pl->last_cnt[2] = h_status[0][3] + h_status[1][3];
-    pl->last_cnt[6] = h_status[0][2] + h_status[1][2];
+    pl->last_cnt[6] = h_status[0][6] + h_status[1][6] + ((pl->model == AMX_MODEL_NODDI) ? 0 : h_status[0][2] + h_status[1][2]);
+    pl->last_cnt[8] = h_status[0][7] + h_status[1][7];
     if (bad) {
         if (err_voxel) *err_voxel = bad_vox;
         return fail(AMX_E_LUT_RANGE, "\"amico.lut.dir_to_lut_idx\" index out of bounds (voxel %lld)", bad_vox);
@@ -914,7 +954,7 @@ int amx_plan_last_timing(amx_plan *pl, double *out_ms, int n)
 int amx_plan_last_counters(amx_plan *pl, int64_t *out, int n)
 {
     if (!pl || !out) return fail(AMX_E_INVALID, "bad argument");
-    for (int i = 0; i < n && i < 8; ++i) out[i] = pl->last_cnt[i];
+    for (int i = 0; i < n && i < 16; ++i) out[i] = pl->last_cnt[i];
     return AMX_OK;
 }
 

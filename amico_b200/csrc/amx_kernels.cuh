@@ -31,7 +31,7 @@ __device__ __forceinline__ int dir_to_lut_idx(double *d, const int16_t *__restri
 }
 
 // status words: [0] error flag, [1] first offending voxel, [2] voxels queued for the scalar slow path,
-// [3] voxels a kernel WITHOUT slow path could not finish (-> AMX_E_CAPACITY)
+// [3] voxels a kernel WITHOUT slow path could not finish (-> AMX_E_CAPACITY), [4] voxels queued for the exact path
 __global__ void k_lut(double *dirs, long long n, const int16_t *__restrict__ htable, int ndirs, int *lut, int *hist,
                       long long *status, long long vox_offset)
 {
@@ -226,7 +226,6 @@ struct FitParams {
     int m_pad, dc_pad;
     int fast_lars;    // NODDI stage 2: throughput-oriented LARS (same path, fused arithmetic)
     int aspace;       // NODDI NNLS stages: A-space re-evaluation of near-dependent candidate columns
-    int refine;       // ... and A-space refinement of the passive solves after such a column was accepted
     int compact3;     // NODDI stage 3: NNLS on the compact support system (one atom per lane) when the support fits a warp
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
@@ -235,7 +234,9 @@ struct FitParams {
     int *ovf_list;       // voxels whose active set outgrew a warp: re-fitted by the scalar slow path (amx_slow.cuh)
     long long ovf_cap;
     unsigned *supmask;   // split NODDI path: [n_vox][NPL] stage-2 support, word s bit l <-> atom l + 32 s
-    int cta_chunk;       // stage kernels: batches are handed out to a CTA in runs of this many consecutive ones (0: one global queue)
+    int *exact_list;     // NODDI: exact-fit voxels queued by stage 1 for the A-space QR path (amx_exact.cuh); status[4] counts them
+    long long exact_cap;
+    double exact_tol;    // ... when ||y - Ax||^2 < exact_tol ||y||^2
 };
 
 struct WarpWS {
@@ -347,9 +348,10 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 }
 
 // c1[v][k] = sum_r y_v[r] A[r][k] for the batch's voxels -> out[v * NA + k]   (NODDI stage 1 / stage 3 right-hand side)
+// normy (optional): ||y_v||^2 of the batch's voxels -> normy[v]
 template <int NT, int TP, typename TS>
 __device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *y, int y_f64, long long myvox, bool vvalid,
-                                     double *out, int NA, int lane)
+                                     double *out, int NA, int lane, double *normy = nullptr)
 {
     const int kk = lane & 3, g = lane >> 2;
     const float *yf = (const float *)y + myvox * m;
@@ -359,15 +361,22 @@ __device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *
         double acc[TP][2];
 #pragma unroll
         for (int t = 0; t < TP; ++t) acc[t][0] = acc[t][1] = 0.0;
+        double ny = 0.0;
 #pragma unroll 1
         for (int r0 = 0; r0 < m; r0 += 4) {
             const int r = r0 + kk;
             const bool rv = r < m;
             double a = 0.0;
             if (rv && vvalid) a = y_f64 ? ld_stream(yd + r) : (double)ld_stream(yf + r);
+            ny = fma(a, a, ny);
             const TS *row = S + (size_t)(rv ? r : m - 1) * n_pad + g + 8 * t0;
 #pragma unroll
             for (int t = 0; t < TP; ++t) dmma(acc[t][0], acc[t][1], a, (double)ld_stream(row + 8 * t));
+        }
+        if (normy && t0 == 0) {
+            ny += __shfl_xor_sync(FULL, ny, 1);
+            ny += __shfl_xor_sync(FULL, ny, 2);
+            if (kk == 0) normy[g] = ny;
         }
         double *o = out + (size_t)g * NA + 2 * kk + 8 * t0;
         if (vvalid) {
@@ -811,38 +820,6 @@ __device__ __forceinline__ void queue_slow(const FitParams &p, long long vox, in
     }
 }
 
-// Batch hand-out of the stage kernels.  The batch list is sorted by LUT direction, so CONSECUTIVE batches share their Gram tables:
-// a CTA takes runs of `chunk` consecutive batches (one global atomic per run) and its warps take single batches out of the run
-// through a shared-memory ticket counter -- the warps of an SM then work on the same direction(s) and the Gram rows they re-read
-// hit L1 instead of L2.  No CTA barrier: the warp that draws the first ticket of a run fetches it and publishes its base in a ring
-// of four slots; a warp holds one ticket at a time, so at most two runs are ever live.
-// hdr: [0] ticket counter, [1..4] run base, [5..8] run id + 1 (ready flag); zeroed by the kernel prologue.
-__device__ __forceinline__ int next_batch(int *hdr, int *counter, int chunk, int lane)
-{
-    int b = 0;
-    if (lane == 0) {
-        if (chunk <= 0) {
-            b = atomicAdd(counter, 1);
-        } else {
-            const int t = atomicAdd(&hdr[0], 1);
-            const int run = t / chunk, slot = t - run * chunk, q = run & 3;
-            volatile int *vh = hdr;
-            if (slot == 0) {
-                const int base = atomicAdd(counter, chunk);
-                vh[1 + q] = base;
-                __threadfence_block();
-                vh[5 + q] = run + 1;
-                b = base;
-            } else {
-                while (vh[5 + q] != run + 1) { }
-                __threadfence_block();
-                b = vh[1 + q] + slot;
-            }
-        }
-    }
-    return __shfl_sync(FULL, b, 0);
-}
-
 // ------------------------------------------------------------------------------------------------
 // NODDI as three stage kernels over the same batch queue (STAGE 1: NNLS for the isotropic fraction, 2: LARS support
 // selection, 3: NNLS on the support + maps).  Same arithmetic as k_fit_noddi_batched; the split exists because the
@@ -867,11 +844,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
     for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
     int *counter = p.tile_counter + (STAGE - 1);
     const int n_tiles = *p.n_tiles_ptr;
-    int *hdr = (int *)smem;
-    if (threadIdx.x < 16) hdr[threadIdx.x] = 0;
-    __syncthreads();
     for (;;) {
-        const int b = next_batch(hdr, counter, p.cta_chunk, lane);
+        int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1);
+        b = __shfl_sync(FULL, b, 0);
         if (b >= n_tiles) break;
         const int4 tile = p.tiles[b];
         const int nb = tile.z;  // <= BV
@@ -919,20 +895,28 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
             }
         } else {
             const double *T1 = p.T1 + (size_t)tile.x * p.T1_stride;
-            gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane);
+            gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane, STAGE == 1 ? ws.bx : nullptr);
             #pragma unroll 1
             for (int v = 0; v < nb; ++v) {
                 const long long pos = tile.y + v;
 #pragma unroll
                 for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
-                const ASpace asp{(const float *)S, n_pad, m, p.y, p.y_f64, (long long)p.order[pos], p.refine};
+                const ASpace asp{(const float *)S, n_pad, m, p.y, p.y_f64, (long long)p.order[pos]};
                 const ASpace *as = (p.aspace && sizeof(TS) == 4) ? &asp : nullptr;
                 if (STAGE == 1) {  // isotropic fraction (amico/models.pyx:911)
-                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr, cap, nullptr, as);
+                    double zz = 0.0;
+                    int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr, cap, nullptr, as, &zz);
                     if (lane == 0) {
                         p.xiso[2 * pos] = ws.x[n - 1];
                         p.xiso[2 * pos + 1] = p.exvivo ? ws.x[n - 2] : 0.0;
+                        // exact-fit voxel (residual below exact_tol ||y||^2): the Gram-space pivots are decided by rounding noise there --
+                        // queue it for the A-space QR path, which re-fits it from scratch after stage 3
+                        const double yy = ws.bx[v];
+                        if (yy > 0.0 && yy - zz < p.exact_tol * yy) {
+                            const unsigned long long idx = atomicAdd((unsigned long long *)&p.status[4], 1ull);
+                            if ((long long)idx < p.exact_cap) p.exact_list[idx] = (int)p.order[pos];
+                        }
                     }
                     if (ov) queue_slow(p, (long long)p.order[pos], lane);
                 } else {  // debias on the support (:929-942), maps

@@ -238,10 +238,11 @@ __device__ inline void slow_lars(const double *__restrict__ T, int ld, double *D
 
 // NODDI, whole pipeline for the queued voxels (amico/models.pyx:901-981)
 template <typename TS>
-__global__ void k_slow_noddi(const FitParams p, const int *__restrict__ list, const long long *__restrict__ status, unsigned char *wsbase,
+__global__ void k_slow_noddi(const FitParams p, const int *__restrict__ list, long long *status, unsigned char *wsbase,
                              size_t ws_bytes, int cap)
 {
-    const long long count = status[2];
+    const long long count = min(status[2], p.ovf_cap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) status[6] += count;  // call total (status[2] is per voxel chunk)
     const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, dc = p.dc;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
     SlowWS W = slow_carve(wsbase + (size_t)tid * ws_bytes, cap, p.NA);

@@ -54,39 +54,7 @@ struct NnlsStat {
 struct ASpace {
     const float *S; int n_pad, m;
     const void *y; int y_f64; long long vox;
-    int refine;  // A-space refinement of the passive solves once a near-dependent atom has been accepted
 };
-
-// One step of iterative refinement of a passive solve in A-space (the corrected semi-normal equations):
-//   r = y - A_P s,  s += (L L^T)^-1 A_P^T r.
-// Needed only once a near-dependent atom sits in the passive set: H_PP then has condition ~1e14 and the Cholesky solution is
-// inaccurate along the near-null direction (residual 1e-7 instead of the 1e-15 the reference's Householder QR reaches,
-// amico/models.pyx:911, 940), which is visible on exact-fit (noise-free) voxels.  Lane a holds s_a; rows of A go lane per row.
-template <bool MAPPED>
-__device__ __noinline__ double nnls_refine(const ASpace *as, const double *Lp, const double *rd, int np, const int *P, const int *map,
-                                           double s, int lane)
-{
-    double q = 0.0;  // lane a: (A_P^T r)_a
-    #pragma unroll 1
-    for (int i0 = 0; i0 < as->m; i0 += 32) {
-        const int i = i0 + lane;
-        const bool on = i < as->m;
-        const float *Si = as->S + (size_t)(on ? i : 0) * as->n_pad;
-        double r = 0.0;
-        if (on) r = as->y_f64 ? ((const double *)as->y)[as->vox * as->m + i] : (double)((const float *)as->y)[as->vox * as->m + i];
-        #pragma unroll 1
-        for (int a = 0; a < np; ++a) r = fma(-(double)Si[MAPPED ? map[P[a]] : P[a]], shfl(s, a), r);
-        if (!on) r = 0.0;
-        #pragma unroll 1
-        for (int a = 0; a < np; ++a) {
-            const double pa = warp_sum((double)Si[MAPPED ? map[P[a]] : P[a]] * r);
-            if (lane == a) q += pa;
-        }
-    }
-    const double dz = fwd_subst(Lp, rd, np, lane < np ? q : 0.0, lane);
-    const double ds = back_subst(Lp, rd, np, lane < np ? dz : 0.0, lane);
-    return lane < np ? s + ds : 0.0;
-}
 
 // min 1/2 x'Tx - c'x, x >= 0 over the atoms whose bit is set in `allowed` (bit s of lane l <-> atom
 // l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays.  mcap = number of rows of the
@@ -97,13 +65,12 @@ __device__ __noinline__ double nnls_refine(const ASpace *as, const double *Lp, c
 template <int NPL, bool MAPPED = false>
 __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
                          unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st, int cap = LC,
-                         const int *map = nullptr, const ASpace *as = nullptr)
+                         const int *map = nullptr, const ASpace *as = nullptr, double *zz_out = nullptr)
 {
     static_assert(!MAPPED || NPL == 1, "the mapped variant keeps one atom per lane");
     auto AT = [&](int q) { return MAPPED ? map[q] : q; };  // compact index -> atom (= Gram table row / column)
     const int mycol = MAPPED ? map[lane < n ? lane : 0] : 0;
     int np = 0, iter = 0, overflow = 0;
-    bool ill = false;  // a near-dependent atom was accepted: passive solves get one A-space refinement step from here on
     cap = min(cap, c_lc_cap);
     unsigned inP = 0;
     double xp = 0.0, zl = 0.0;
@@ -148,7 +115,6 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
         // candidate selection
         int j = -1;
         double v = 0.0, d2 = 0.0, znum = 0.0;
-        bool near_dep = false;
         for (;;) {
             double bv = 0.0;
             int bj = -1;
@@ -158,16 +124,14 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             warp_argmax(bv, bj);
             if (bj < 0 || !(bv > 0.0)) { j = -1; break; }
             j = bj;
-            double t = (lane < np) ? T[(size_t)AT(P[lane]) * ldT + AT(j)] : 0.0;
+            double t = (lane < np) ? T[(size_t)AT(j) * ldT + AT(P[lane])] : 0.0;  // = T[P[lane]][j] (the table is exactly symmetric): one row, not np
             v = fwd_subst(Lp, rd, np, t, lane);
             double vv = warp_sum(lane < np ? v * v : 0.0);
             double vz = warp_sum(lane < np ? v * zl : 0.0);
             const double hjj = T[(size_t)AT(j) * (ldT + 1)];
             d2 = hjj - vv;
             znum = c[j] - vz;
-            near_dep = false;
             if (as && np > 0 && d2 < 1e-10 * hjj) {
-                near_dep = true;
                 // Near-dependent candidate: H_jj - v.v has lost its digits (the Gram form squares the conditioning; below ~1e-13 H_jj
                 // it is rounding noise of either sign) and so has c_j - v.z -- yet the NODDI dictionary really holds atoms that are
                 // independent of the passive set only at the 1e-7 level (d2 ~ 1e-14 H_jj), and the reference's Householder QR
@@ -214,7 +178,6 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             }
         }
         if (j < 0) break;
-        ill |= near_dep;
         // move j to the passive set: append a row to the factor
         {
             const double ird = rsqrt(d2), dd = d2 * ird;
@@ -238,7 +201,6 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             if (++iter > itmax) goto done;
             if (st) ++st->inner;
             s = back_subst(Lp, rd, np, (lane < np) ? zl : 0.0, lane);
-            if (ill && as->refine) s = nnls_refine<MAPPED>(as, Lp, rd, np, P, map, s, lane);
             bool neg = (lane < np) && (s <= 0.0);
             if (!__any_sync(FULL, neg)) break;
             double tmin = INFINITY;
@@ -330,6 +292,8 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
     }
 done:
     if (lane < np) x[P[lane]] = xp;
+    // ||A x||^2 = ||z||^2 of the final passive system (z = L^-1 c_P): with ||y||^2 it gives the fit residual without touching A
+    if (zz_out) *zz_out = warp_sum(lane < np ? zl * zl : 0.0);
     __syncwarp();
     return overflow;
 }

@@ -212,7 +212,7 @@ class Plan:
         return {"binning_ms": out[0], "fit_kernel_ms": out[1], "total_ms": out[2]}
 
     def last_counters(self):
-        out = (C.c_int64 * 8)()
-        L.check(L.load().amx_plan_last_counters(self._h, out, 8))
+        out = (C.c_int64 * 16)()
+        L.check(L.load().amx_plan_last_counters(self._h, out, 16))
         return {"launches": out[0], "tiles": out[1], "overflow_voxels": out[2], "smem_bytes": out[3], "warps_per_cta": out[4],
-                "tma_staged": bool(out[5]), "slow_path_voxels": out[6], "grid": out[7]}
+                "tma_staged": bool(out[5]), "slow_path_voxels": out[6], "grid": out[7], "exact_path_voxels": out[8]}

@@ -156,10 +156,12 @@ def test_noddi_known_answers():
     P.y = y  # float64 input path
     got = gpu_fit(P)
     ref = orc().fit_problem(P)
-    # Exact-fit voxels: once the true atoms are in, the passive system holds near-dependent columns (cond(H_PP) ~ 1e14) and the
-    # plain Cholesky solve is off along the near-null direction; the A-space refinement step of warp_nnls (nnls_refine) brings the
-    # passive solves back to the accuracy of the reference's Householder QR.  Bars: >= 99.9 % of the voxels within 1e-4 of the
+    # Exact-fit voxels: once the true atoms are in, the passive Gram system holds near-dependent columns (cond(H_PP) ~ 1e14) and the
+    # dual c - Hx is rounding noise, so the Gram-space stage kernels cannot follow the reference's pivots.  Stage 1 detects the
+    # regime (||y - Ax||^2 < 1e-6 ||y||^2) and queues the voxel for the exact path (amx_exact.cuh): the reference's own A-space
+    # Lawson-Hanson / Householder algorithm, bit-identical to the oracle.  Bars: >= 99.9 % of the voxels within 1e-4 of the
     # oracle, and the generating grid values recovered to 1e-6 relative (SURVEY section 4's known-answer case).
+    assert got["_counters"]["exact_path_voxels"] >= 590
     frac = pass_fraction(got["estimates"], ref["estimates"])
     e = got["estimates"]
     assert np.allclose(e[0], [0.0, 1.0, 0.0])
