@@ -518,6 +518,94 @@ __device__ __noinline__ void fit_errors(const TS *S, int n_pad, int n, int m, do
     }
 }
 
+// Maps of the single-fit models from the elastic-net coefficients x (amico/models.pyx:1241-1255 FreeWater, :618-636
+// CylinderZeppelinBall, :1570-1611 SANDI -- x is un-normalised in place there); all lanes compute, lane 0 stores.  Returns the
+// support size.
+template <int MODEL, int NPL>
+__device__ __forceinline__ int lasso_maps(const FitParams &p, double *x, long long vox, int lane)
+{
+    const int n = p.n;
+    int support = 0;
+    for_each_positive<NPL>(x, n, lane, [&](int, double) { ++support; });
+    if (MODEL == MODEL_FREEWATER) {
+        double xs = 0.0, xp = 0.0;
+        for_each_positive<NPL>(x, n, lane, [&](int j, double xj) { xs += xj; if (j < p.n_perp) xp += xj; });
+        xs += 1e-16;
+        const double vv = xp / xs;
+        if (lane == 0) {
+            double *e = p.est + vox * p.n_maps;
+            e[0] = vv; e[1] = 1.0 - vv;
+            if (p.mouse) { e[2] = x[p.n_perp] / xs; e[3] = x[p.n_perp + 1] / xs; }
+        }
+    } else if (MODEL == MODEL_CZB) {
+        double f1 = 0.0, f2 = 0.0, aa = 0.0;
+        for_each_positive<NPL>(x, p.n_rs + p.n_perp, lane, [&](int j, double xj) { if (j < p.n_rs) f1 += xj; else f2 += xj; });
+        f2 += 1e-16;
+        const double vv = f1 / (f1 + f2 + 1e-16);
+        f1 += 1e-16;
+        for_each_positive<NPL>(x, p.n_rs, lane, [&](int j, double xj) { aa += p.Rs[j] * xj; });
+        aa = 1e6 * 2.0 * aa / f1;
+        const double dd = (4.0 * vv) / (3.14159265358979323846 * (aa * aa) + 1e-16);
+        if (lane == 0) {
+            double *e = p.est + vox * 3;
+            e[0] = vv; e[1] = aa; e[2] = dd;
+        }
+    } else {  // SANDI: un-normalise, then group sums
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int j = lane + 32 * s;
+            if (j < n) x[j] = x[j] * p.sandi_norms[j];
+        }
+        __syncwarp();
+        const int n_rs = p.n_rs, n_in = p.n_in;
+        double xs = 0, sph = 0, stk = 0, iso = 0, Rsoma = 0, Din = 0, De = 0;
+        for_each_positive<NPL>(x, n, lane, [&](int j, double xj) {
+            xs += xj;
+            if (j < n_rs) sph += xj;
+            else if (j < n_rs + n_in) stk += xj;
+            else iso += xj;
+        });
+        xs += 1e-16;
+        for_each_positive<NPL>(x, n, lane, [&](int j, double xj) {
+            if (j < n_rs) Rsoma += p.Rs[j] * xj;
+            else if (j < n_rs + n_in) Din += p.d_in[j - n_rs] * xj;
+            else De += p.d_isos[j - n_rs - n_in] * xj;
+        });
+        if (lane == 0) {
+            double *e = p.est + vox * 6;
+            e[0] = sph / xs; e[1] = stk / xs; e[2] = iso / xs;
+            sph += 1e-16; stk += 1e-16; iso += 1e-16;
+            e[3] = 1e6 * Rsoma / sph; e[4] = 1e3 * Din / stk; e[5] = 1e3 * De / iso;
+        }
+    }
+    return support;
+}
+
+// Optional outputs of the single-fit models: support / coefficients (debug), FreeWater corrected DWI (:1263-1274), fit errors
+// (:45-71).  yv: the voxel's signal as doubles in shared memory (destroyed by the error pass).
+template <int MODEL, int NPL, typename TS>
+__device__ __forceinline__ void lasso_outputs(const FitParams &p, const TS *S, double *yv, const double *x, long long vox, int support, int lane)
+{
+    const int m = p.m, n = p.n, n_pad = p.n_pad;
+    if (p.support_out && lane == 0) p.support_out[vox] = support;
+    if (p.coeff_out)
+        #pragma unroll 1
+        for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = x[j];
+    if (MODEL == MODEL_FREEWATER && (p.flags & FLAG_EXTRA)) {
+        #pragma unroll 1
+        for (int i = lane; i < m; i += 32) {
+            double fw = 0.0;
+            #pragma unroll 1
+            for (int k = n - p.n_iso; k < n; ++k) fw = madd(fw, (double)S[(size_t)i * n_pad + k], x[k]);
+            double cv = yv[i] - fw;
+            p.extra[vox * m + i] = cv < 0.0 ? 0.0 : cv;
+        }
+        __syncwarp();
+    }
+    if (p.flags & (FLAG_RMSE | FLAG_NRMSE))
+        fit_errors<NPL, TS>(S, n_pad, n, m, yv, x, p.flags, p.rmse ? p.rmse + vox : nullptr, p.nrmse ? p.nrmse + vox : nullptr, lane);
+}
+
 template <int MODEL, int NPL, typename TS>
 __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
 {
@@ -623,79 +711,20 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
                                          : at_y<NPL, TS, true, false>(S, n_pad, n, m, nullptr, ws.y, nullptr, 0, 0, ws.dtr, lane);
                 overflow |= warp_lars<NPL>(T2, p.ldT2, p.lambda2, n, m < n ? m : n, p.lambda1, ws.dtr, normX, ws.mat, ws.u,
                                            ws.gs, ws.P, ws.x, lane, nullptr);
-                for_each_positive<NPL>(ws.x, n, lane, [&](int, double) { ++support; });
-                if (MODEL == MODEL_FREEWATER) {
-                    double xs = 0.0, xp = 0.0;
-                    for_each_positive<NPL>(ws.x, n, lane, [&](int j, double xj) { xs += xj; if (j < p.n_perp) xp += xj; });
-                    xs += 1e-16;
-                    const double vv = xp / xs;
-                    if (lane == 0) {
-                        double *e = p.est + vox * p.n_maps;
-                        e[0] = vv; e[1] = 1.0 - vv;
-                        if (p.mouse) { e[2] = ws.x[p.n_perp] / xs; e[3] = ws.x[p.n_perp + 1] / xs; }
-                    }
-                } else if (MODEL == MODEL_CZB) {
-                    double f1 = 0.0, f2 = 0.0, aa = 0.0;
-                    for_each_positive<NPL>(ws.x, p.n_rs + p.n_perp, lane, [&](int j, double xj) { if (j < p.n_rs) f1 += xj; else f2 += xj; });
-                    f2 += 1e-16;
-                    const double vv = f1 / (f1 + f2 + 1e-16);
-                    f1 += 1e-16;
-                    for_each_positive<NPL>(ws.x, p.n_rs, lane, [&](int j, double xj) { aa += p.Rs[j] * xj; });
-                    aa = 1e6 * 2.0 * aa / f1;
-                    const double dd = (4.0 * vv) / (3.14159265358979323846 * (aa * aa) + 1e-16);
-                    if (lane == 0) {
-                        double *e = p.est + vox * 3;
-                        e[0] = vv; e[1] = aa; e[2] = dd;
-                    }
-                } else {  // SANDI (:1570-1611): un-normalise, then group sums
-#pragma unroll
-                    for (int s = 0; s < NPL; ++s) {
-                        int j = lane + 32 * s;
-                        if (j < n) ws.x[j] = ws.x[j] * p.sandi_norms[j];
-                    }
-                    __syncwarp();
-                    const int n_rs = p.n_rs, n_in = p.n_in;
-                    double xs = 0, sph = 0, stk = 0, iso = 0, Rsoma = 0, Din = 0, De = 0;
-                    for_each_positive<NPL>(ws.x, n, lane, [&](int j, double xj) {
-                        xs += xj;
-                        if (j < n_rs) sph += xj;
-                        else if (j < n_rs + n_in) stk += xj;
-                        else iso += xj;
-                    });
-                    xs += 1e-16;
-                    for_each_positive<NPL>(ws.x, n, lane, [&](int j, double xj) {
-                        if (j < n_rs) Rsoma += p.Rs[j] * xj;
-                        else if (j < n_rs + n_in) Din += p.d_in[j - n_rs] * xj;
-                        else De += p.d_isos[j - n_rs - n_in] * xj;
-                    });
-                    if (lane == 0) {
-                        double *e = p.est + vox * 6;
-                        e[0] = sph / xs; e[1] = stk / xs; e[2] = iso / xs;
-                        sph += 1e-16; stk += 1e-16; iso += 1e-16;
-                        e[3] = 1e6 * Rsoma / sph; e[4] = 1e3 * Din / stk; e[5] = 1e3 * De / iso;
-                    }
-                }
+                support = lasso_maps<MODEL, NPL>(p, ws.x, vox, lane);
             }
             __syncwarp();
-            if (p.support_out && lane == 0) p.support_out[vox] = support;
-            if (p.coeff_out)
-                #pragma unroll 1
-                for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
-            // FreeWater corrected DWI (:1263-1274) -- before fit_errors destroys ws.y? no: errors first use y.
-            if (MODEL == MODEL_FREEWATER && (p.flags & FLAG_EXTRA)) {
-                #pragma unroll 1
-                for (int i = lane; i < m; i += 32) {
-                    double fw = 0.0;
+            if (MODEL == MODEL_NODDI) {
+                if (p.support_out && lane == 0) p.support_out[vox] = support;
+                if (p.coeff_out)
                     #pragma unroll 1
-                    for (int k = n - p.n_iso; k < n; ++k) fw = madd(fw, (double)S[(size_t)i * n_pad + k], ws.x[k]);
-                    double cv = ws.y[i] - fw;
-                    p.extra[vox * m + i] = cv < 0.0 ? 0.0 : cv;
-                }
-                __syncwarp();
+                    for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
+                if (p.flags & (FLAG_RMSE | FLAG_NRMSE))
+                    fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
+                                        p.nrmse ? p.nrmse + vox : nullptr, lane);
+            } else {
+                lasso_outputs<MODEL, NPL, TS>(p, S, ws.y, ws.x, vox, support, lane);
             }
-            if (p.flags & (FLAG_RMSE | FLAG_NRMSE))
-                fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
-                                    p.nrmse ? p.nrmse + vox : nullptr, lane);
             if (overflow) ++n_overflow;
             __syncwarp();
             // next voxel of this tile

@@ -19,30 +19,31 @@
 namespace amx {
 
 // ------------------------------------------------------------------------------------------------
-// Triangular solves against the packed lower factor Lp (row-major packed, diagonal reciprocals rd).
-// Lane a holds element a of the right-hand side / the result (0 beyond np).
-__device__ __forceinline__ double fwd_subst(const double *Lp, const double *rd, int np, double t, int lane)
+// Triangular solves against the packed lower factor Lp (row-major packed).  Lane a holds element a of the right-hand
+// side / the result (0 beyond np) and rdl = 1 / L[a][a] of its own row, so the pivot of step k is formed on lane k before
+// the broadcast and no per-step select or reciprocal load is needed.
+__device__ __forceinline__ double fwd_subst(const double *Lp, double rdl, int np, double t, int lane)
 {
-    double v = 0.0;
+    const double *row = Lp + tri(lane, 0);
+    const bool act = lane < np;
     #pragma unroll 1
     for (int k = 0; k < np; ++k) {
-        double vk = shfl(t, k) * rd[k];
-        if (lane == k) v = vk;
-        if (lane > k && lane < np) t = fma(-Lp[tri(lane, k)], vk, t);
+        const double vk = shfl(t * rdl, k);  // lane k's t is final from step k - 1 on
+        if (act && lane > k) t = fma(-row[k], vk, t);
     }
-    return v;
+    return act ? t * rdl : 0.0;
 }
 
-__device__ __forceinline__ double back_subst(const double *Lp, const double *rd, int np, double t, int lane)
+__device__ __forceinline__ double back_subst(const double *Lp, double rdl, int np, double t, int lane)
 {
-    double s = 0.0;
+    const double *col = Lp + tri(np - 1, 0) + lane;  // element (k, lane) of row k, walking up
     #pragma unroll 1
     for (int k = np - 1; k >= 0; --k) {
-        double sk = shfl(t, k) * rd[k];
-        if (lane == k) s = sk;
-        if (lane < k) t = fma(-Lp[tri(k, lane)], sk, t);
+        const double sk = shfl(t * rdl, k);
+        if (lane < k) t = fma(-*col, sk, t);
+        col -= k;
     }
-    return s;
+    return lane < np ? t * rdl : 0.0;
 }
 
 struct NnlsStat {
@@ -56,15 +57,70 @@ struct ASpace {
     const void *y; int y_f64; long long vox;
 };
 
+// arg-max over strictly positive values (lanes with idx < 0 do not take part): the bit pattern of a positive double orders like
+// an unsigned integer, so no order-preserving key is needed; ties -> lowest index
+__device__ __forceinline__ void warp_argmax_pos(double &v, int &idx)
+{
+    const unsigned hi = idx >= 0 ? (unsigned)__double2hiint(v) : 0u, lo = idx >= 0 ? (unsigned)__double2loint(v) : 0u;
+    const unsigned hm = __reduce_max_sync(FULL, hi);
+    const unsigned lm = __reduce_max_sync(FULL, hi == hm ? lo : 0u);
+    const bool win = idx >= 0 && hi == hm && lo == lm;
+    const int widx = __reduce_min_sync(FULL, win ? idx : 0x7fffffff);
+    v = __hiloint2double((int)hm, (int)lm);
+    idx = (hm | lm) ? widx : -1;
+}
+
+// Cholesky downdate for the deletion of passive position q (of pn): rows q+1.. move up one slot and Givens rotations restore
+// the triangle; z = L^-1 c_P is rotated along (the reference updates its QR the same way).  Row i = lane streams its OLD row
+// i + 1 through the rotations: per step one load, one store, the rotated-out element carried in a register -- no separate
+// shift pass for the columns >= q.  rdl / zl: per-lane 1 / diagonal and z, updated in place.
+__device__ __forceinline__ void chol_delete(double *Lp, int q, int pn, double &rdl, double &zl, int lane)
+{
+    const bool mine = (lane >= q) && (lane < pn - 1);
+    const double *src = Lp + tri(lane + 1, 0);  // old row lane + 1 (only dereferenced when `mine`)
+    double *dst = Lp + tri(lane, 0);
+    #pragma unroll 1
+    for (int col = 0; col < q; ++col) {  // columns left of q: plain move (read everywhere before anyone overwrites)
+        double lv = 0.0;
+        if (mine) lv = src[col];
+        __syncwarp();
+        if (mine) dst[col] = lv;
+    }
+    double carry = 0.0;
+    if (mine) carry = src[q];
+    __syncwarp();
+    #pragma unroll 1
+    for (int r = q; r < pn - 1; ++r) {
+        const bool act = mine && lane >= r;
+        double u2 = 0.0;
+        if (act) u2 = src[r + 1];
+        const double a = shfl(carry, r), b = shfl(u2, r);
+        const double ir = rsqrt(fma(a, a, b * b));  // = 1 / (new diagonal element)
+        const double cs = a * ir, sn = b * ir;
+        __syncwarp();  // column r of row lane + 1 was read one step ago; its owner may overwrite it now
+        if (act) {
+            dst[r] = fma(cs, carry, sn * u2);
+            carry = fma(cs, u2, -sn * carry);
+            if (lane == r) rdl = ir;
+        }
+        const double zr = shfl(zl, r), zr1 = shfl(zl, r + 1);
+        if (lane == r) zl = fma(cs, zr, sn * zr1);
+        else if (lane == r + 1) zl = fma(cs, zr1, -sn * zr);
+    }
+    if (lane >= pn - 1) zl = 0.0;
+    __syncwarp();
+}
+
 // min 1/2 x'Tx - c'x, x >= 0 over the atoms whose bit is set in `allowed` (bit s of lane l <-> atom
-// l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays.  mcap = number of rows of the
+// l + 32 s).  T: n x n Gram (ld ldT), c/x: per-warp shared arrays (c readable up to 32 NPL entries).  mcap = number of rows of the
 // least-squares system (the reference stops growing the passive set at m).  Returns overflow flag.
 // MAPPED (NPL must be 1): the system is the sub-system of T on the atoms map[0..n) (n <= 32, one per lane): c, x, P
 // live in that compact numbering and T is addressed through map -- NODDI stage 3, where the support holds ~10 of 145
 // atoms, so the dual pass touches one Gram entry per lane and row instead of NPL.
+// zz_out (optional): ||z||^2 = ||A x||^2 of the final passive system.
 template <int NPL, bool MAPPED = false>
 __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
-                         unsigned allowed, double *Lp, double *rd, int *P, int lane, NnlsStat *st, int cap = LC,
+                         unsigned allowed, double *Lp, double *, int *P, int lane, NnlsStat *st, int cap = LC,
                          const int *map = nullptr, const ASpace *as = nullptr, double *zz_out = nullptr)
 {
     static_assert(!MAPPED || NPL == 1, "the mapped variant keeps one atom per lane");
@@ -72,24 +128,23 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
     const int mycol = MAPPED ? map[lane < n ? lane : 0] : 0;
     int np = 0, iter = 0, overflow = 0;
     cap = min(cap, c_lc_cap);
-    unsigned inP = 0;
-    double xp = 0.0, zl = 0.0;
+    unsigned inP = 0, avail = 0;
+    double xp = 0.0, zl = 0.0, rdl = 0.0;  // coefficient, z and 1 / diagonal of this lane's passive position
 #pragma unroll
-    for (int s = 0; s < NPL; ++s) x[lane + 32 * s] = 0.0;
+    for (int s = 0; s < NPL; ++s) {
+        x[lane + 32 * s] = 0.0;
+        avail |= (lane + 32 * s < n ? 1u : 0u) << s;
+    }
+    avail &= allowed;
     __syncwarp();
     for (;;) {
         if (np >= mcap) break;
         if (np >= cap) { overflow = 1; break; }
-        // dual w = c - T[:,P] x_P on the zero set
+        // dual w = c - T[:,P] x_P; slots outside `valid` carry finite values nobody looks at
         double wl[NPL];
-        unsigned valid = 0;
+        unsigned valid = avail & ~inP;
 #pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            int j = lane + 32 * s;
-            bool ok = (j < n) && ((allowed >> s) & 1u) && !((inP >> s) & 1u);
-            valid |= (ok ? 1u : 0u) << s;
-            wl[s] = ok ? c[j] : 0.0;
-        }
+        for (int s = 0; s < NPL; ++s) wl[s] = c[lane + 32 * s];
         {   // rows of T are L2-resident (~300 cycles): fetch GD rows at a time
             constexpr int GD = (NPL <= 2) ? 4 : AMX_GD;
 #pragma unroll 1
@@ -99,8 +154,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                 for (int q = 0; q < GD; ++q) {
                     const double *row = T + (size_t)AT(P[min(k0 + q, np - 1)]) * ldT;
 #pragma unroll
-                    for (int s = 0; s < NPL; ++s) gq[q][s] = row[MAPPED ? mycol : lane + 32 * s];  // slots that are not `valid` pick up
-                                                                                                // finite garbage nobody reads (table is padded)
+                    for (int s = 0; s < NPL; ++s) gq[q][s] = row[MAPPED ? mycol : lane + 32 * s];  // table is padded
                 }
 #pragma unroll
                 for (int q = 0; q < GD; ++q) {
@@ -121,13 +175,17 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
 #pragma unroll
             for (int s = 0; s < NPL; ++s)
                 if (((valid >> s) & 1u) && wl[s] > bv) { bv = wl[s]; bj = lane + 32 * s; }
-            warp_argmax(bv, bj);
-            if (bj < 0 || !(bv > 0.0)) { j = -1; break; }
+            warp_argmax_pos(bv, bj);
+            if (bj < 0) { j = -1; break; }
             j = bj;
             double t = (lane < np) ? T[(size_t)AT(j) * ldT + AT(P[lane])] : 0.0;  // = T[P[lane]][j] (the table is exactly symmetric): one row, not np
-            v = fwd_subst(Lp, rd, np, t, lane);
-            double vv = warp_sum(lane < np ? v * v : 0.0);
-            double vz = warp_sum(lane < np ? v * zl : 0.0);
+            v = fwd_subst(Lp, rdl, np, t, lane);
+            double vv = v * v, vz = v * zl;  // both 0 beyond np (v is); two interleaved butterfly sums
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                vv += __shfl_xor_sync(FULL, vv, o);
+                vz += __shfl_xor_sync(FULL, vz, o);
+            }
             const double hjj = T[(size_t)AT(j) * (ldT + 1)];
             d2 = hjj - vv;
             znum = c[j] - vz;
@@ -140,7 +198,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
                 // numerator is r.y.  Measured on the C model of this solver (tools/research): support mismatches against the
                 // oracle 68 -> 0 of 6000 voxels at SNR 300, 8 -> 0 at SNR 30, for any threshold between 1e-6 and 1e-13; 1e-10 sends
                 // ~0.3 candidates per voxel here.
-                const double beta = back_subst(Lp, rd, np, (lane < np) ? v : 0.0, lane);
+                const double beta = back_subst(Lp, rdl, np, v, lane);
                 const float *Sj = as->S + AT(j);
                 double a2 = 0.0, ay = 0.0;
                 #pragma unroll 1
@@ -171,11 +229,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             }
             if (d2 > 0.0 && d2 > 1.2325951644078309e-28 * vv && znum > 0.0) break;
             // reject: drop j from this round's candidates
-            if ((j & 31) == lane) {
-#pragma unroll
-                for (int s = 0; s < NPL; ++s)
-                    if (s == (j >> 5)) wl[s] = 0.0;
-            }
+            if ((j & 31) == lane) valid &= ~(1u << (j >> 5));
         }
         if (j < 0) break;
         // move j to the passive set: append a row to the factor
@@ -185,7 +239,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             if (lane < np) Lp[tri(np, lane)] = v;
             if (lane == np) {
                 Lp[tri(np, np)] = dd;
-                rd[np] = ird;
+                rdl = ird;
                 P[np] = j;
                 zl = znew;
                 xp = 0.0;
@@ -200,7 +254,7 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
         for (;;) {
             if (++iter > itmax) goto done;
             if (st) ++st->inner;
-            s = back_subst(Lp, rd, np, (lane < np) ? zl : 0.0, lane);
+            s = back_subst(Lp, rdl, np, (lane < np) ? zl : 0.0, lane);
             bool neg = (lane < np) && (s <= 0.0);
             if (!__any_sync(FULL, neg)) break;
             double tmin = INFINITY;
@@ -213,75 +267,34 @@ __device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int
             if (cand < 0) break;
             if (lane < np) xp = fma(tmin, s - xp, xp);
             if (lane == cand) xp = 0.0;
-            bool keep = (lane < np) && (xp > 0.0);
-            unsigned kmask = __ballot_sync(FULL, keep);
-            int myP = (lane < np) ? P[lane] : 0;
-            if (lane < np && !keep) x[myP] = 0.0;
-            int nnew = __popc(kmask);
+            const bool keep = (lane < np) && (xp > 0.0);
+            const unsigned kmask = __ballot_sync(FULL, keep);
             const int np_old = np;
+            unsigned rmask = ~kmask & (np_old >= 32 ? 0xffffffffu : ((1u << np_old) - 1u));  // removed positions
+            const int myP = (lane < np) ? P[lane] : 0;
+            if (lane < np && !keep) x[myP] = 0.0;
+            for (unsigned r2 = rmask; r2; r2 &= r2 - 1) {  // their atoms leave the passive bit set
+                const int a = __shfl_sync(FULL, myP, __ffs(r2) - 1);
+                if ((a & 31) == lane) inP &= ~(1u << (a >> 5));
+            }
+            const int nnew = __popc(kmask);
             if (st) st->removed += np - nnew;
-            unsigned src = __fns(kmask, 0, lane + 1);
-            bool has = lane < nnew;
-            int srcl = has ? (int)src : 0;
-            double xs = shfl(xp, srcl);
-            int ps = __shfl_sync(FULL, myP, srcl);
+            const unsigned src = __fns(kmask, 0, lane + 1);
+            const bool has = lane < nnew;
+            const int srcl = has ? (int)src : 0;
+            const double xs = shfl(xp, srcl);
+            const int ps = __shfl_sync(FULL, myP, srcl);
             __syncwarp();
             if (has) P[lane] = ps;
             xp = has ? xs : 0.0;
             np = nnew;
             __syncwarp();
-            inP = 0;
-            #pragma unroll 1
-            for (int k = 0; k < np; ++k) {
-                int a = P[k];
-                if ((a & 31) == lane) inP |= 1u << (a >> 5);
-            }
             if (np == 0) break;
-            // Cholesky downdate (column deletion) by Givens rotations, one removed position at a time, highest first;
-            // z = L^-1 c_P is rotated along (the reference updates its QR the same way)
-            {
-                unsigned rmask = ~kmask & (np_old >= 32 ? 0xffffffffu : ((1u << np_old) - 1u));
-                int pn = np_old;
-                while (rmask) {
-                    const int q = 31 - __clz(rmask);
-                    rmask &= ~(1u << q);
-                    // rows q+1.. move up one slot; the element beyond a row's packed capacity stays in register e
-                    double e = 0.0;
-                    const bool mine = (lane >= q) && (lane < pn - 1);
-#pragma unroll 1
-                    for (int col = 0; col < pn; ++col) {
-                        const bool act = mine && (col <= lane + 1);
-                        double lv = 0.0;
-                        if (act) lv = Lp[tri(lane + 1, col)];
-                        __syncwarp();
-                        if (act) {
-                            if (col <= lane) Lp[tri(lane, col)] = lv;
-                            else e = lv;
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll 1
-                    for (int r = q; r < pn - 1; ++r) {
-                        const double a = Lp[tri(r, r)];
-                        const double b = shfl(e, r);
-                        const double ir = rsqrt(fma(a, a, b * b));  // = 1 / (new diagonal element)
-                        const double cs = a * ir, sn = b * ir;
-                        if (lane >= r && lane < pn - 1) {
-                            const double u1 = (lane == r) ? a : Lp[tri(lane, r)];
-                            const double u2 = (lane == r) ? e : Lp[tri(lane, r + 1)];
-                            const double n1 = fma(cs, u1, sn * u2), n2 = fma(cs, u2, -sn * u1);
-                            Lp[tri(lane, r)] = n1;
-                            if (lane > r) Lp[tri(lane, r + 1)] = n2;
-                            else rd[r] = ir;
-                        }
-                        const double zr = shfl(zl, r), zr1 = shfl(zl, r + 1);
-                        if (lane == r) zl = fma(cs, zr, sn * zr1);
-                        else if (lane == r + 1) zl = fma(cs, zr1, -sn * zr);
-                        __syncwarp();
-                    }
-                    if (lane >= pn - 1) zl = 0.0;
-                    --pn;
-                }
+            // Cholesky downdate (column deletion), one removed position at a time, highest first
+            for (int pn = np_old; rmask; --pn) {
+                const int q = 31 - __clz(rmask);
+                rmask &= ~(1u << q);
+                chol_delete(Lp, q, pn, rdl, zl, lane);
             }
         }
         if (lane < np) {
