@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("AMICO_B200_LIB") or os.path.join(_HERE, "libamico_b20
 AMX_OK, AMX_E_INVALID, AMX_E_CUDA, AMX_E_LUT_RANGE, AMX_E_CAPACITY, AMX_E_NONFINITE = 0, -1, -2, -3, -4, -5
 PRE_NORMALIZE, PRE_MERGE_B0, PRE_DIR_AVG, PRE_REPLACE_BAD = 1, 2, 4, 8
 MODEL_NODDI, MODEL_FREEWATER, MODEL_CZB, MODEL_SANDI = 0, 1, 2, 3
-FLAG_RMSE, FLAG_NRMSE, FLAG_EXTRA = 1, 2, 4
+FLAG_RMSE, FLAG_NRMSE, FLAG_EXTRA, FLAG_EXACT = 1, 2, 4, 8
 F32, F64 = 0, 1
 SPACE_HOST, SPACE_DEVICE = 0, 1
 

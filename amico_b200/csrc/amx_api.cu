@@ -6,6 +6,8 @@
 #include "amx_err.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -74,6 +76,71 @@ int env_int(const char *name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
+// ---- host-side staging of the signal --------------------------------------------------------------------------------------
+// The reference hands a model `evaluation.y` as a PAGEABLE float64 array (amico/core.py:451-452) whose values are float32 (the
+// volume is float32, core.py:136).  A cudaMemcpyAsync from such memory is staged by the driver on one thread at a few GB/s.
+// Instead, host threads move each voxel chunk into pinned memory -- narrowing float64 to float32 on the way when every value
+// survives the round trip, which halves the PCIe bytes -- while the GPU is busy with the previous chunks.
+int host_threads()
+{
+    const int hw = (int)std::thread::hardware_concurrency();
+    return std::max(1, std::min(env_int("AMX_HOST_THREADS", std::min(hw > 0 ? hw : 1, 16)), 64));
+}
+
+template <typename F>
+void parallel_blocks(size_t n_blocks, int threads, F f)
+{
+    threads = (int)std::min<size_t>((size_t)threads, n_blocks);
+    if (threads <= 1) { for (size_t b = 0; b < n_blocks; ++b) f(b); return; }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> pool;
+    pool.reserve(threads - 1);
+    auto work = [&]() { for (size_t b = next.fetch_add(1); b < n_blocks; b = next.fetch_add(1)) f(b); };
+    for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto &t : pool) t.join();
+}
+
+// Copy `count` signal values into pinned `dst`.  float64 input: written as float32 when lossless (returns AMX_F32), else as is.
+int stage_signal(const void *src, int src_dtype, void *dst, size_t count, int threads)
+{
+    constexpr size_t BLK = 1 << 16;
+    const size_t nb = (count + BLK - 1) / BLK;
+    if (src_dtype == AMX_F64) {
+        std::atomic<int> lossy{0};
+        const double *s = (const double *)src;
+        float *d = (float *)dst;
+        parallel_blocks(nb, threads, [&](size_t b) {
+            const size_t i0 = b * BLK, i1 = std::min(count, i0 + BLK);
+            int bad = 0;
+            for (size_t i = i0; i < i1; ++i) {
+                const float f = (float)s[i];
+                bad |= ((double)f != s[i]);
+                d[i] = f;
+            }
+            if (bad) lossy.store(1, std::memory_order_relaxed);
+        });
+        if (!lossy.load()) return AMX_F32;
+        parallel_blocks(nb, threads, [&](size_t b) {
+            const size_t i0 = b * BLK, i1 = std::min(count, i0 + BLK);
+            memcpy((double *)dst + i0, s + i0, (i1 - i0) * sizeof(double));
+        });
+        return AMX_F64;
+    }
+    parallel_blocks(nb, threads, [&](size_t b) {
+        const size_t i0 = b * BLK, i1 = std::min(count, i0 + BLK);
+        memcpy((float *)dst + i0, (const float *)src + i0, (i1 - i0) * sizeof(float));
+    });
+    return AMX_F32;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
 }  // namespace
 
 struct amx_plan {
@@ -83,7 +150,8 @@ struct amx_plan {
     size_t slab_stride = 0;   // elements per direction
     unsigned slab_bytes = 0;  // bytes to stage per direction
     void *d_slab = nullptr;
-    double *d_T1 = nullptr, *d_T2 = nullptr, *d_diag0 = nullptr;
+    double *d_T1 = nullptr, *d_T2 = nullptr, *d_diag0 = nullptr, *d_W = nullptr;
+    int ldW = 0; size_t W_stride = 0;
     double ridge_baked = -1.0;  // ridge currently added to the diagonal of d_T2 (< 0: none)
     int ldT1 = 0, ldT2 = 0, K2 = 0;
     size_t T1_stride = 0, T2_stride = 0;
@@ -101,6 +169,8 @@ struct amx_plan {
     cudaStream_t cs[2] = {nullptr, nullptr};          // [0] == stream
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
+    void *hpin[2] = {nullptr, nullptr};  // pinned host staging of pageable / float64 signals (host path)
+    size_t hpin_cap[2] = {0, 0};
     int max_smem = 0, sm_count = 0;
     // last-call records
     double last_ms[8] = {0};
@@ -233,7 +303,7 @@ int amx_plan_destroy(amx_plan *pl)
 {
     if (!pl) return AMX_OK;
     cudaSetDevice(pl->device);
-    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_diag0, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
+    void *ptrs[] = {pl->d_slab, pl->d_T1, pl->d_T2, pl->d_diag0, pl->d_W, pl->d_htable, pl->d_dwi_rows, pl->d_norms, pl->d_icvf, pl->d_kappa,
                     pl->d_Rs, pl->d_sandi_norms, pl->d_d_in, pl->d_d_isos};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &wk : pl->work) {
@@ -241,6 +311,7 @@ int amx_plan_destroy(amx_plan *pl)
                           &wk.exact_list, &wk.exact_a};
         for (DevBuf *b : bufs) b->release();
     }
+    for (void *h : pl->hpin) if (h) cudaFreeHost(h);
     if (pl->cs[1]) cudaStreamDestroy(pl->cs[1]);
     if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
     for (auto &e : pl->ev_join) if (e) cudaEventDestroy(e);
@@ -398,16 +469,6 @@ int amx_plan_info(const amx_plan *pl, int *model, int *m, int *n_atoms, int *n_m
 
 namespace {
 
-template <int NPL>
-int launch_noddi_batched(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
-{
-    auto kern = k_fit_noddi_batched<NPL, float>;
-    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, block, smem, st>>>(p);
-    CK(cudaGetLastError());
-    return AMX_OK;
-}
-
 template <int NPL, int MAXT>
 int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
@@ -432,17 +493,11 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
         CK(cudaFuncSetAttribute(k1w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1w));
         CK(cudaFuncSetAttribute(k1w, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1w * 100 + 233471) / 233472 + 1)));
         k1w<<<grid, 1024, s1w, st>>>(p);
-    } else if (MAXT == 768 && block == 768 && w1 == 28) {
-        auto k1w = k_noddi_stage<1, NPL, float, 896>;
-        const size_t s1m = fixed + (size_t)p.ws_doubles_stage[0] * 8 * 28;
-        CK(cudaFuncSetAttribute(k1w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1m));
-        CK(cudaFuncSetAttribute(k1w, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1m * 100 + 233471) / 233472 + 1)));
-        k1w<<<grid, 896, s1m, st>>>(p);
     } else {
         k1<<<grid, block, s1, st>>>(p);
     }
     // Stages 2 and 3: more resident warps hide more of the L2 latency of the Gram rows as long as registers (64K / threads)
-    // and shared memory (workspace x warps <= 227 KB) allow; the builds for 896 / 1024 threads spill ~150 bytes.
+    // and shared memory (workspace x warps <= 227 KB) allow; the 1024-thread builds spill ~150 bytes.
     const int w2 = env_int("AMX_STAGE2_WARPS", 32), w3 = env_int("AMX_STAGE3_WARPS", 24);
     auto launch_wide = [&](auto kern, int warps, unsigned ws_doubles) -> int {
         const size_t sw = fixed + (size_t)ws_doubles * 8 * warps;
@@ -454,11 +509,10 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     auto fits = [&](int warps, unsigned ws_doubles) { return fixed + (size_t)ws_doubles * 8 * warps <= (size_t)227 * 1024; };
     int rc = AMX_OK;
     if (wide_ok && w2 == 32 && fits(32, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 1024>, 32, p.ws_doubles_stage[1]);
-    else if (wide_ok && w2 == 28 && fits(28, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 896>, 28, p.ws_doubles_stage[1]);
     else k2<<<grid, block, s2, st>>>(p);
     if (rc) return rc;
-    if (wide_ok && w3 == 28 && fits(28, p.ws_doubles_stage[2])) rc = launch_wide(k_noddi_stage<3, NPL, float, 896>, 28, p.ws_doubles_stage[2]);
-    else k3<<<grid, block, s3, st>>>(p);
+    (void)w3;
+    k3<<<grid, block, s3, st>>>(p);
     if (rc) return rc;
     CK(cudaGetLastError());
     return AMX_OK;
@@ -491,9 +545,27 @@ int launch_fit(const FitParams &p, int grid, int block, size_t smem, cudaStream_
     return AMX_OK;
 }
 
+template <int MODEL, int NPL, typename TS, int MAXT>
+int launch_lasso_batched(const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
+{
+    auto kern = k_lasso_batched<MODEL, NPL, TS, MAXT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(p);
+    CK(cudaGetLastError());
+    return AMX_OK;
+}
+
 template <int MODEL, typename TS>
 int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
+    if (MODEL != MODEL_NODDI && p.batched == 3) {
+        switch (npl) {
+        case 1: return block > 768 ? launch_lasso_batched<MODEL, 1, TS, 1024>(p, grid, block, smem, st)
+                                   : launch_lasso_batched<MODEL, 1, TS, 768>(p, grid, block, smem, st);
+        case 2: return launch_lasso_batched<MODEL, 2, TS, 768>(p, grid, block, smem, st);
+        case 3: case 4: return launch_lasso_batched<MODEL, 4, TS, 768>(p, grid, block, smem, st);
+        }
+    }
     if (MODEL == MODEL_NODDI && p.batched == 2) {
         switch (npl) {
         case 1: return launch_noddi_split<1>(p, grid, block, smem, st);
@@ -502,20 +574,17 @@ int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, 
         case 5: return launch_noddi_split<5>(p, grid, block, smem, st);
         }
     }
-    if (MODEL == MODEL_NODDI && p.batched) {
+    if constexpr (MODEL == MODEL_NODDI) {
+        // dictionaries of up to 160 atoms run as stage kernels; only larger ones (user grids, <= 254 atoms) take the per-voxel kernel
+        if (npl >= 6 && npl <= 8) return launch_fit<MODEL, 8, TS>(p, grid, block, smem, st);
+    } else {
         switch (npl) {
-        case 1: return launch_noddi_batched<1>(p, grid, block, smem, st);
-        case 2: return launch_noddi_batched<2>(p, grid, block, smem, st);
-        case 3: case 4: return launch_noddi_batched<4>(p, grid, block, smem, st);
-        case 5: return launch_noddi_batched<5>(p, grid, block, smem, st);
+        case 1: return launch_fit<MODEL, 1, TS>(p, grid, block, smem, st);
+        case 2: return launch_fit<MODEL, 2, TS>(p, grid, block, smem, st);
+        case 3: case 4: return launch_fit<MODEL, 4, TS>(p, grid, block, smem, st);
+        case 5: return launch_fit<MODEL, 5, TS>(p, grid, block, smem, st);
+        case 6: case 7: case 8: return launch_fit<MODEL, 8, TS>(p, grid, block, smem, st);
         }
-    }
-    switch (npl) {
-    case 1: return launch_fit<MODEL, 1, TS>(p, grid, block, smem, st);
-    case 2: return launch_fit<MODEL, 2, TS>(p, grid, block, smem, st);
-    case 3: case 4: return launch_fit<MODEL, 4, TS>(p, grid, block, smem, st);
-    case 5: return launch_fit<MODEL, 5, TS>(p, grid, block, smem, st);
-    case 6: case 7: case 8: return launch_fit<MODEL, 8, TS>(p, grid, block, smem, st);
     }
     return fail(AMX_E_INVALID, "unsupported atom count (npl=%d)", npl);
 }
@@ -535,6 +604,16 @@ int prepare_tables(amx_plan *pl, const amx_fit_args *a, cudaStream_t st, int *la
             CK(cudaGetLastError());
             pl->ridge_baked = ridge;
             *launches += 1;
+            if (pl->model == AMX_MODEL_CZB && pl->n <= 32) {  // inverse tables of the dense-start NNQP follow the ridge
+                if (!pl->d_W) {
+                    pl->ldW = pl->ldT2; pl->W_stride = pl->T2_stride;
+                    CK(cudaMalloc((void **)&pl->d_W, ((size_t)pl->ndirs * pl->W_stride + 256) * sizeof(double)));
+                    CK(cudaMemsetAsync(pl->d_W, 0, ((size_t)pl->ndirs * pl->W_stride + 256) * sizeof(double), st));
+                }
+                k_invert_spd<<<pl->ndirs, 32, 0, st>>>(pl->d_T2, pl->n, pl->ldT2, pl->T2_stride, pl->d_W, pl->ldW, pl->W_stride);
+                CK(cudaGetLastError());
+                *launches += 1;
+            }
         }
     }
     {
@@ -555,8 +634,10 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
                bool record_events, cudaEvent_t after_lut = nullptr)
 {
     const long long n_vox = a->n_vox;
-    const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5 && env_int("AMX_NODDI_BATCHED", 1);
-    const int tile_v = batched ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
+    const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5;  // larger dictionaries: the per-voxel kernel (k_fit)
+    // single-fit models: DMMA-batched throughput kernel unless the caller asks for the bit-reproducible one
+    const bool lasso_fast = pl->model != AMX_MODEL_NODDI && pl->npl <= 4 && !(a->flags & AMX_FLAG_EXACT) && env_int("AMX_LASSO_FAST", 1);
+    const int tile_v = (batched || lasso_fast) ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
     const bool rotated = pl->model != AMX_MODEL_SANDI;
     const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
     CK(wk.tiles.reserve((size_t)max_tiles * sizeof(int4)));
@@ -600,6 +681,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.slab = pl->d_slab; p.slab_stride = pl->slab_stride;
     p.T1 = pl->d_T1; p.ldT1 = pl->ldT1; p.T1_stride = pl->T1_stride;
     p.T2 = pl->d_T2; p.ldT2 = pl->ldT2; p.T2_stride = pl->T2_stride; p.K2 = pl->K2;
+    if (pl->d_W && a->lambda1 == 0.0 && pl->m >= pl->n && env_int("AMX_CZB_DENSE", 1)) { p.W = pl->d_W; p.ldW = pl->ldW; p.W_stride = pl->W_stride; }
     p.y = a->y; p.y_f64 = a->y_dtype == AMX_F64; p.n_vox = n_vox;
     p.order = rotated ? (const int *)wk.order.p : nullptr; p.tiles = (const int4 *)wk.tiles.p; p.n_tiles_ptr = totals;
     p.tile_counter = totals + 2;
@@ -611,15 +693,22 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.lut = lut;
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
-    p.batched = batched ? (env_int("AMX_NODDI_SPLIT", 1) ? 2 : 1) : 0;
+    p.batched = batched ? 2 : lasso_fast ? 3 : 0;
     p.fast_lars = env_int("AMX_FAST_LARS", 1);
     p.compact3 = env_int("AMX_COMPACT3", 1);
     p.aspace = env_int("AMX_ASPACE", 1);
     p.m_pad = (pl->m + 1) & ~1; p.dc_pad = p.batched ? 0 : (pl->dc + 1) & ~1;
     if (p.batched && !(a->flags & (AMX_FLAG_RMSE | AMX_FLAG_NRMSE))) p.m_pad = 0;
+    if (p.batched == 3 && (a->flags & AMX_FLAG_EXTRA)) p.m_pad = (pl->m + 1) & ~1;  // FreeWater corrected DWI reads the signal
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);
 
     // shared-memory budget: [header 128][slab (optional)][nwarps x workspace]
+    if (p.batched == 3) {
+        p.cap_stage[1] = std::max(4, std::min(LC, std::min(pl->n, std::min(pl->m, pl->n)) + 1));  // the path never holds more than min(m, n) atoms
+        if (p.W) p.cap_stage[1] = std::max(p.cap_stage[1], 18);  // the block-pivoting scratch (NNQP_KMAX x (NNQP_KMAX + 1)) lives in the same matrix area
+        p.ws_doubles_stage[1] = ws_doubles_for(p.NA, p.m_pad, 0, 1, p.cap_stage[1]);
+        p.ws_doubles = p.ws_doubles_stage[1];
+    }
     if (p.batched == 2) {
         // stage 1 (NNLS on the full dictionary) never holds more than ~8 passive atoms on NODDI dictionaries (rank ~11):
         // a 16-atom workspace leaves ~85 KB more L1 for its Gram rows; rarer larger sets go to the slow path
@@ -630,10 +719,10 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     }
     const size_t ws_bytes = (size_t)p.ws_doubles * sizeof(double);
     const size_t budget = (size_t)pl->max_smem;
-    const int max_warps = (batched && env_int("AMX_NODDI_SPLIT", 1)) ? 24 : 16;
+    const int max_warps = lasso_fast ? (pl->npl == 1 ? 32 : 24) : batched ? 24 : 16;
     const int want_warps = std::min(max_warps, std::max(1, env_int("AMX_WARPS", max_warps)));
     const int min_staged_warps = std::max(1, env_int("AMX_MIN_STAGED_WARPS", 8));
-    bool staged = !batched && env_int("AMX_NO_TMA", 0) == 0 && 128 + (size_t)pl->slab_bytes + ws_bytes * min_staged_warps <= budget;
+    bool staged = !batched && !lasso_fast && env_int("AMX_NO_TMA", 0) == 0 && 128 + (size_t)pl->slab_bytes + ws_bytes * min_staged_warps <= budget;
     size_t fixed = 128 + (staged ? pl->slab_bytes : 0);
     int nwarps = (int)std::min<size_t>(want_warps, (budget - fixed) / ws_bytes);
     if (nwarps < 1) return fail(AMX_E_INVALID, "per-warp workspace (%zu B) does not fit in shared memory (m=%d, n=%d)", ws_bytes, pl->m, pl->n);
@@ -646,7 +735,10 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
     int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count * ctas_per_sm));
 
-    if (p.batched) {
+    if (p.batched == 3) {
+        CK(wk.scratch.reserve((size_t)grid * 32 * BV * p.NA * sizeof(double)));
+        p.scratch = (double *)wk.scratch.p;
+    } else if (p.batched) {
         CK(wk.scratch.reserve((size_t)grid * 32 * 2 * BV * p.NA * sizeof(double)));
         p.scratch = (double *)wk.scratch.p;
         CK(wk.xiso.reserve((size_t)n_vox * 2 * sizeof(double)));
@@ -663,6 +755,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         if (p.batched == 2) {
             const char *tol = getenv("AMX_EXACT_TOL");
             p.exact_tol = (tol && *tol) ? atof(tol) : 1e-6;
+            if (a->flags & AMX_FLAG_EXACT) p.exact_tol = 1e300;  // bit-reproducible mode: every voxel is re-fitted by the A-space path
             p.exact_cap = n_vox;
             CK(wk.exact_list.reserve((size_t)n_vox * sizeof(int)));
             p.exact_list = (int *)wk.exact_list.p;
@@ -756,9 +849,14 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     //  Host buffers: the copy engine moves a voxel ~5x faster than the fit consumes it, so the chunks GROW geometrically
     //  (n/16, n/4, rest): only the small first chunk's upload and the last chunk's download are exposed, and the stage
     //  kernels see three ragged ends instead of one per fixed-size chunk.  AMX_HOST_CHUNK=<voxels> restores equal chunks.
+    // Pageable or float64 host signals go through pinned staging filled by host threads (stage_signal): equal chunks, so that
+    // the conversion of chunk i + 1 overlaps the upload of chunk i and the fit of chunk i - 1.
+    const bool staged_host = host && env_int("AMX_HOST_STAGE", 1) && (a->y_dtype == AMX_F64 || !is_pinned(a->y));
     std::vector<long long> bounds{0};
     {
-        const long long fixed = env_int(host ? "AMX_HOST_CHUNK" : "AMX_DEVICE_CHUNK", host ? 0 : 0x7fffffff);
+        long long fixed = env_int(host ? "AMX_HOST_CHUNK" : "AMX_DEVICE_CHUNK", host ? 0 : 0x7fffffff);
+        if (staged_host && fixed <= 0 && (long long)n >= 131072)
+            fixed = std::max<long long>(32768, ((long long)n / std::max(2, env_int("AMX_STAGE_CHUNKS", 8)) + 7) & ~7LL);
         if (fixed > 0) {
             const long long c = std::max<long long>(8192, fixed);
             if ((long long)n <= c + c / 2) bounds.push_back((long long)n);
@@ -797,6 +895,18 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             if (a->lut_out) CK(sg.lut.reserve((size_t)chunk * sizeof(int)));
         }
     }
+    const int n_host_threads = host_threads();
+    if (staged_host) {
+        for (int b = 0; b < nset; ++b) {
+            const size_t want = (size_t)chunk * m * ysz;
+            if (pl->hpin_cap[b] < want) {
+                if (pl->hpin[b]) cudaFreeHost(pl->hpin[b]);
+                pl->hpin[b] = nullptr; pl->hpin_cap[b] = 0;
+                CK(cudaHostAlloc(&pl->hpin[b], want + want / 8, cudaHostAllocDefault));
+                pl->hpin_cap[b] = want + want / 8;
+            }
+        }
+    }
     cudaStream_t cs[2] = {st, ncs > 1 ? pl->cs[1] : st};
     cudaStream_t s_in = (host && nset > 1) ? pl->s_in : st, s_out = (host && nset > 1) ? pl->s_out : st;
     CK(cudaEventRecord(pl->ev[3], st));
@@ -824,7 +934,13 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
                 CK(cudaStreamWaitEvent(s_in, pl->ev_comp[b], 0));  // inputs of this set consumed by chunk i-2 ...
                 CK(cudaStreamWaitEvent(s_in, pl->ev_out[b], 0));   // ... and its flipped dirs (same buffer) read back
             }
-            CK(cudaMemcpyAsync(sg.y.p, (const char *)a->y + off * m * ysz, cnt * m * ysz, cudaMemcpyHostToDevice, s_in));
+            if (staged_host) {
+                if (i >= 2) CK(cudaEventSynchronize(pl->ev_in[b]));  // the upload of chunk i - 2 has left this pinned set
+                c.y_dtype = stage_signal((const char *)a->y + off * m * ysz, a->y_dtype, pl->hpin[b], cnt * m, n_host_threads);
+                CK(cudaMemcpyAsync(sg.y.p, pl->hpin[b], cnt * m * (c.y_dtype == AMX_F64 ? 8 : 4), cudaMemcpyHostToDevice, s_in));
+            } else {
+                CK(cudaMemcpyAsync(sg.y.p, (const char *)a->y + off * m * ysz, cnt * m * ysz, cudaMemcpyHostToDevice, s_in));
+            }
             if (a->dirs) CK(cudaMemcpyAsync(sg.dirs.p, a->dirs + off * 3, cnt * 3 * sizeof(double), cudaMemcpyHostToDevice, s_in));
             c.y = sg.y.p; c.estimates = (double *)sg.est.p;
             c.dirs = a->dirs ? (double *)sg.dirs.p : nullptr;

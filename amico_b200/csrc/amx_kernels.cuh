@@ -5,7 +5,7 @@
 namespace amx {
 
 enum { MODEL_NODDI = 0, MODEL_FREEWATER = 1, MODEL_CZB = 2, MODEL_SANDI = 3 };
-enum { FLAG_RMSE = 1, FLAG_NRMSE = 2, FLAG_EXTRA = 4 };
+enum { FLAG_RMSE = 1, FLAG_NRMSE = 2, FLAG_EXTRA = 4, FLAG_EXACT = 8 };
 
 // ------------------------------------------------------------------------------------------------
 // direction -> LUT index (amico/lut.pyx:314-356), flips `d` in place; -1 when out of range.
@@ -199,6 +199,33 @@ __global__ void k_set_ridge(double *G, int K, int ldG, size_t G_stride, const do
         G[(size_t)d * G_stride + (size_t)k * ldG + k] = __dadd_rn(diag0[(size_t)d * K + k], ridge);
 }
 
+// W[d] = (G_d + ridge I)^-1 for n <= 32 (dense-start NNQP, warp_nnqp_dense): one warp per direction, Gauss-Jordan on [H | I] in
+// shared memory, result symmetrised.
+__global__ void __launch_bounds__(32) k_invert_spd(const double *__restrict__ H, int n, int ldH, size_t H_stride, double *W, int ldW, size_t W_stride)
+{
+    __shared__ double M[32][65];
+    const int d = blockIdx.x, lane = threadIdx.x;
+    const double *Hd = H + (size_t)d * H_stride;
+    if (lane < n) {
+        for (int q = 0; q < n; ++q) { M[lane][q] = Hd[(size_t)lane * ldH + q]; M[lane][n + q] = (q == lane) ? 1.0 : 0.0; }
+    }
+    __syncwarp();
+    for (int pv = 0; pv < n; ++pv) {
+        const double ip = 1.0 / M[pv][pv];
+        __syncwarp();
+        if (lane == pv) for (int q = 0; q < 2 * n; ++q) M[pv][q] *= ip;
+        __syncwarp();
+        if (lane < n && lane != pv) {
+            const double f = M[lane][pv];
+            for (int q = 0; q < 2 * n; ++q) M[lane][q] = fma(-f, M[pv][q], M[lane][q]);
+        }
+        __syncwarp();
+    }
+    double *Wd = W + (size_t)d * W_stride;
+    if (lane < n)
+        for (int q = 0; q < n; ++q) Wd[(size_t)lane * ldW + q] = 0.5 * (M[lane][n + q] + M[q][n + lane]);
+}
+
 // ------------------------------------------------------------------------------------------------
 struct FitParams {
     int model, m, n, n_pad, ndirs, n_maps, NA;
@@ -208,6 +235,7 @@ struct FitParams {
     // Gram tables
     const double *T1; int ldT1; size_t T1_stride;  // NODDI: full dictionary (NNLS stages)
     const double *T2; int ldT2; size_t T2_stride; int K2;  // LARS system
+    const double *W; int ldW; size_t W_stride;  // (T2)^-1 per direction: dense-start NNQP of CylinderZeppelinBall (NULL: off)
     // voxels
     const void *y; int y_f64; long long n_vox;
     const int *order; const int4 *tiles; const int *n_tiles_ptr; int *tile_counter;
@@ -738,27 +766,25 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
 }
 
 // ------------------------------------------------------------------------------------------------
-// NODDI, batched: every warp is an independent worker pulling 8-voxel batches (same LUT direction) from a global
-// queue.  Per batch both A^T y products run on the FP64 tensor pipe (DMMA m8n8k4, M = the 8 voxels), their results
-// go through a warp-private L2-resident scratch, and the three active-set stages run per voxel as in k_fit.
-// Dictionary B-fragments stream from the per-direction slab in global memory (read once per batch and stage:
-// ~14 KB/voxel of L2 traffic), which keeps shared memory for solver state and L1 for the Gram rows.
-template <int NPL, typename TS>
-__global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
+// FreeWater / CylinderZeppelinBall / SANDI, throughput path: the NODDI stage-2 design applied to the single-fit models.  Every warp
+// pulls 8-voxel batches of one LUT direction from a global queue; c = A^T y of the batch runs on the FP64 tensor pipe (DMMA
+// m8n8k4, M = the 8 voxels; ||y||^2 rides along), then each voxel walks the SPAMS homotopy path with warp_lars_fast (same path and
+// stopping rules as the reference's lasso -- amico/models.pyx:615, 1238, 1569 --, fused arithmetic) and its maps are formed in the
+// same warp.  The elastic net is strictly convex, so the minimiser is unique and the maps agree with the bit-exact kernel (k_fit,
+// AMX_FLAG_EXACT) to ~1e-12; that one follows the reference's un-fused CPU arithmetic operation for operation and stays available.
+template <int MODEL, int NPL, typename TS, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_lasso_batched(const FitParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles, p.NA, p.m_pad, p.dc_pad);
-    constexpr int NT = 4 * NPL, TP = NT;
-    const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
-    double *scr1 = p.scratch + ((size_t)blockIdx.x * p.nwarps + warp) * (size_t)(2 * BV) * NA;
-    double *scr2 = scr1 + (size_t)BV * NA;
+    const int cap = p.cap_stage[1];
+    WarpWS ws = carve((double *)(smem + p.ws_smem_off) + (size_t)warp * p.ws_doubles_stage[1], p.NA, p.m_pad, 0, 1, cap);
+    constexpr int NT = 4 * NPL, TP = (MAXT > 768 && NPL > 1) ? NT / 2 : NT;
+    const int m = p.m, n = p.n, n_pad = p.n_pad, NA = p.NA;
+    double *scr = p.scratch + ((size_t)blockIdx.x * 32 + warp) * (size_t)BV * NA;
     const int g = lane >> 2;
-    unsigned all = 0;
-#pragma unroll
-    for (int s = 0; s < NPL; ++s) all |= (lane + 32 * s < n ? 1u : 0u) << s;
-    long long n_overflow = 0;
     const int n_tiles = *p.n_tiles_ptr;
+    long long n_overflow = 0;
     for (;;) {
         int b = 0;
         if (lane == 0) b = atomicAdd(p.tile_counter, 1);
@@ -767,59 +793,33 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
         const int4 tile = p.tiles[b];
         const int nb = tile.z;  // <= BV
         const TS *S = (const TS *)p.slab + (size_t)tile.x * p.slab_stride;
-        const double *T1 = p.T1 + (size_t)tile.x * p.T1_stride;
         const double *T2 = p.T2 + (size_t)tile.x * p.T2_stride;
         const bool vvalid = g < nb;
-        const long long myvox = (long long)p.order[tile.y + (vvalid ? g : 0)];
-        gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr1, NA, lane);
-        // stage 1 per voxel: isotropic fraction (amico/models.pyx:911)
+        const long long mypos = tile.y + (vvalid ? g : 0);
+        const long long myvox = p.order ? (long long)p.order[mypos] : mypos;
+        gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane, ws.bx);
         #pragma unroll 1
         for (int v = 0; v < nb; ++v) {
+            const long long vox = p.order ? (long long)p.order[tile.y + v] : (long long)tile.y + v;
 #pragma unroll
-            for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr1[(size_t)v * NA + lane + 32 * s];
+            for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
             __syncwarp();
-            int ov = warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * n, ws.c1, ws.x, all, ws.mat, ws.rd, ws.P, lane, nullptr);
-            if (lane == 0) {
-                ws.bx[v] = ws.x[n - 1];
-                ws.bx[BV + v] = p.exvivo ? ws.x[n - 2] : 0.0;
+            bool solved = false;
+            if (MODEL == MODEL_CZB && NPL == 1 && p.W) {  // dense minimiser: start from the unconstrained ridge solution (certified)
+                double xl = 0.0;
+                solved = warp_nnqp_dense(T2, p.ldT2, p.W + (size_t)tile.x * p.W_stride, p.ldW, n, ws.dtr[lane], ws.mat, xl, lane);
+                if (solved) ws.x[lane] = xl;
+                __syncwarp();
             }
-            if (ov) ++n_overflow;
-            __syncwarp();
-        }
-        // stage 2 right-hand sides for the whole batch (:914-925)
-        if (p.norms_const)
-            gemm_c2<NT, TP, TS, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
-                                  ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
-        else
-            gemm_c2<NT, TP, TS, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, ws.bx[vvalid ? g : 0],
-                                   ws.bx[BV + (vvalid ? g : 0)], p.exvivo, p.norms, n_wm, scr2, NA, ws.bx + 2 * BV, lane);
-        #pragma unroll 1
-        for (int v = 0; v < nb; ++v) {
-            const long long vox = (long long)p.order[tile.y + v];
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) ws.dtr[lane + 32 * s] = scr2[(size_t)v * NA + lane + 32 * s];
-            __syncwarp();
-            int overflow = warp_lars<NPL>(T2, p.ldT2, p.lambda2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, ws.dtr,
-                                          ws.bx[2 * BV + v], ws.mat, ws.u, ws.gs, ws.P, ws.x, lane, nullptr);
-            // stage 3: debias on the support (:929-942)
-            unsigned allowed = 0;
-            int support = 0;
-#pragma unroll
-            for (int s = 0; s < NPL; ++s) {
-                int j = lane + 32 * s;
-                bool on = (j < n_wm && ws.x[j] > 0.0) || (j >= n_wm && j < n);
-                allowed |= (on ? 1u : 0u) << s;
-                support += __popc(__ballot_sync(FULL, on));
-                ws.c1[j] = scr1[(size_t)v * NA + j];
+            if (!solved) {
+                unsigned sup[NPL];
+                const int ov = warp_lars_fast<NPL>(T2, p.ldT2, n, m < n ? m : n, p.lambda1, ws.dtr, ws.bx[v], ws.mat, ws.u, ws.gs, ws.P, ws.x,
+                                                   lane, cap, sup);
+                if (ov) ++n_overflow;
             }
+            const int support = lasso_maps<MODEL, NPL>(p, ws.x, vox, lane);
             __syncwarp();
-            overflow |= warp_nnls<NPL>(T1, p.ldT1, n, m, 3 * support, ws.c1, ws.x, allowed, ws.mat, ws.rd, ws.P, lane, nullptr);
-            noddi_maps<NPL>(p.icvf, p.kappa, n, n_wm, p.exvivo, p.flags, p.est + vox * p.n_maps,
-                            (p.flags & FLAG_EXTRA) ? p.extra + 2 * vox : nullptr, ws.x, lane);
-            if (p.support_out && lane == 0) p.support_out[vox] = support;
-            if (p.coeff_out)
-                for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
-            if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {
+            if (p.m_pad) {  // debug / error / corrected-signal outputs want the signal as doubles
                 if (p.y_f64) {
                     const double *yg = (const double *)p.y + vox * m;
                     #pragma unroll 1
@@ -830,10 +830,12 @@ __global__ void __launch_bounds__(512, 1) k_fit_noddi_batched(const FitParams p)
                     for (int i = lane; i < m; i += 32) ws.y[i] = (double)yg[i];
                 }
                 __syncwarp();
-                fit_errors<NPL, TS>(S, n_pad, n, m, ws.y, ws.x, p.flags, p.rmse ? p.rmse + vox : nullptr,
-                                    p.nrmse ? p.nrmse + vox : nullptr, lane);
+                lasso_outputs<MODEL, NPL, TS>(p, S, ws.y, ws.x, vox, support, lane);
+            } else if (p.support_out || p.coeff_out) {
+                if (p.support_out && lane == 0) p.support_out[vox] = support;
+                if (p.coeff_out)
+                    for (int j = lane; j < n; j += 32) p.coeff_out[vox * n + j] = ws.x[j];
             }
-            if (overflow) ++n_overflow;
             __syncwarp();
         }
     }
@@ -851,7 +853,7 @@ __device__ __forceinline__ void queue_slow(const FitParams &p, long long vox, in
 
 // ------------------------------------------------------------------------------------------------
 // NODDI as three stage kernels over the same batch queue (STAGE 1: NNLS for the isotropic fraction, 2: LARS support
-// selection, 3: NNLS on the support + maps).  Same arithmetic as k_fit_noddi_batched; the split exists because the
+// selection, 3: NNLS on the support + maps).  One solver per kernel: a fused kernel's
 // fused kernel's ~90 KB of SASS thrashes the instruction cache once 16 independent warps per SM sit in different
 // solvers (ncu: `no_instruction` was the top stall).  Each stage kernel keeps one solver hot.  Between stages only
 // 16 B (x_iso, x_dot) + 4 NPL B (support mask) per voxel travel through HBM; stage 3 recomputes c1 = A^T y on the

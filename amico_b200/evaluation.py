@@ -32,11 +32,27 @@ MIN_POSITIVE_SIGNAL = 0.0001  # dipy.reconst.dti.MIN_POSITIVE_SIGNAL
 _DIPY_B0_THRESHOLD = 50       # dipy.core.gradients.gradient_table default
 
 
-def dti_design_matrix(bvals, bvecs):
-    """dipy's ``design_matrix(gtab)`` (lower-triangular order Dxx, Dxy, Dyy, Dxz, Dyz, Dzz, dummy; negated)."""
+def dipy_gradient_table(bvals, bvecs, b0_threshold=_DIPY_B0_THRESHOLD, atol=1e-2):
+    """(bvals, bvecs) as dipy's ``gradient_table(bvals, bvecs)`` -> ``GradientTable`` exposes them (restated from the published
+    dipy.core.gradients; dipy is absent here, so unpinned): directions whose norm is not within ``atol`` of 1 are zeroed together
+    with their b-value (that is how b0 rows with a (0, 0, 0) direction drop out), a diffusion-weighted row (b > 50) with such a
+    direction is an error, and the table then holds ``gradients = b * g`` from which ``bvals = |gradients|``,
+    ``bvecs = gradients / bvals`` are derived -- so a low-b volume with a unit direction (HCP-style b = 5) KEEPS its gradient."""
     bvals = np.asarray(bvals, dtype=np.float64)
     g = np.array(bvecs, dtype=np.float64)
-    g[bvals <= _DIPY_B0_THRESHOLD] = 0.0
+    g = np.where(np.isnan(g), 0.0, g)
+    close = np.abs(np.sqrt((g * g).sum(axis=1)) - 1.0) <= atol
+    if not np.all(close[bvals > b0_threshold]):
+        raise ValueError("The vectors in bvecs should be unit (The tolerance can be modified as an input parameter)")
+    g = np.where(close[:, None], g, 0.0)
+    gradients = (bvals * close)[:, None] * g
+    b = np.sqrt((gradients * gradients).sum(axis=1))
+    return b, gradients / (b + (b == 0))[:, None]
+
+
+def dti_design_matrix(bvals, bvecs):
+    """dipy's ``design_matrix(gtab)`` (lower-triangular order Dxx, Dxy, Dyy, Dxz, Dyz, Dzz, dummy; negated)."""
+    bvals, g = dipy_gradient_table(bvals, bvecs)
     B = np.empty((len(bvals), 7))
     B[:, 0] = g[:, 0] * g[:, 0] * bvals
     B[:, 1] = g[:, 0] * g[:, 1] * 2.0 * bvals
@@ -383,7 +399,7 @@ class Evaluation:
         # the fit flips the directions in place to the y >= 0 hemisphere; RESULTS['DIRs'] holds the DTI output (core.py:477-478)
         fit_dirs = None if self._dirs is None else self._dirs.clone()
         res = plan.fit(self._y, fit_dirs, self.model.solver_params["lambda1"], self.model.solver_params["lambda2"],
-                       rmse=bool(cfg("doComputeRMSE")), nrmse=bool(cfg("doComputeNRMSE")), extra=extra)
+                       rmse=bool(cfg("doComputeRMSE")), nrmse=bool(cfg("doComputeNRMSE")), extra=extra, exact=bool(cfg("amx_exact")))
         torch.cuda.synchronize(dev)
         self.set_config("fit_time", time.time() - t)
         # ---- store results (core.py:469-498)

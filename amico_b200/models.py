@@ -106,7 +106,6 @@ class BaseModel:
         y = evaluation.y
         y = np.ascontiguousarray(y) if y.dtype in (np.float32, np.float64) else np.ascontiguousarray(y, dtype=np.float64)
         dirs = None
-        write_back = None
         if self.id != "SANDI":
             src = evaluation.DIRs
             # The reference flips the hemisphere on np.ascontiguousarray(DIRs, dtype=double): a view -- hence
@@ -115,13 +114,12 @@ class BaseModel:
             dirs = np.ascontiguousarray(src, dtype=np.float64)
             if dirs.ndim != 2 or dirs.shape != (y.shape[0], 3):
                 raise ValueError("evaluation.DIRs must be (n_vox, 3)")
-            if dirs is not src and not np.shares_memory(dirs, src):
-                write_back = None  # a copy was made: the caller's array stays untouched, like the reference
+            # (when a copy was made the caller's array stays untouched, like the reference)
         cfg = evaluation.get_config
         extra = bool(cfg("doSaveModulatedMaps")) if self.id == "NODDI" else bool(cfg("doSaveCorrectedDWI")) if self.id == "FreeWater" else False
+        # "amx_exact" is not a reference key: it selects the bit-reproducible kernels (AMX_FLAG_EXACT)
         res = plan.fit(y, dirs, self.solver_params["lambda1"], self.solver_params["lambda2"], rmse=bool(cfg("doComputeRMSE")),
-                       nrmse=bool(cfg("doComputeNRMSE")), extra=extra)
-        del write_back
+                       nrmse=bool(cfg("doComputeNRMSE")), extra=extra, exact=bool(cfg("amx_exact")))
         return res
 
 

@@ -119,18 +119,21 @@ class Plan:
         self.close()
 
     # ------------------------------------------------------------------ fit
-    def fit(self, y, dirs, lambda1, lambda2, *, rmse=False, nrmse=False, extra=False, debug=False, out=None):
+    def fit(self, y, dirs, lambda1, lambda2, *, rmse=False, nrmse=False, extra=False, debug=False, out=None, exact=False):
         """Fit every row of ``y``.
 
         Host path: ``y`` (n_vox, m) float32/float64 ndarray, ``dirs`` (n_vox, 3) float64 C-contiguous ndarray
         (FLIPPED IN PLACE like the reference) or None for SANDI.  Device path: the same as CUDA torch tensors.
-        Returns a dict like ``<Model>.fit`` (amico/models.pyx:185-203).
+        Returns a dict like ``<Model>.fit`` (amico/models.pyx:185-203).  ``exact=True`` (``AMX_FLAG_EXACT``): the bit-reproducible
+        kernels that follow the reference's CPU arithmetic operation for operation (same maps to ~1e-12, lower throughput).
         """
         lib = L.load()
         flags = (L.FLAG_RMSE if rmse else 0) | (L.FLAG_NRMSE if nrmse else 0)
         has_extra = extra and self.model in ("NODDI", "FreeWater")
         if has_extra:
             flags |= L.FLAG_EXTRA
+        if exact:
+            flags |= L.FLAG_EXACT
         dev = _is_torch(y)
         a = L.FitArgs()
         a.lambda1, a.lambda2, a.flags = float(lambda1), float(lambda2), flags

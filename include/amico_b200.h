@@ -48,6 +48,11 @@ extern "C" {
 #define AMX_FLAG_NRMSE 2u /* doComputeNRMSE  -> nrmse */
 #define AMX_FLAG_EXTRA 4u /* NODDI: doSaveModulatedMaps -> extra (n_vox x 2);
                              FreeWater: doSaveCorrectedDWI -> extra (n_vox x m) */
+#define AMX_FLAG_EXACT 8u /* bit-reproducible mode: follow the reference's CPU arithmetic operation for operation (un-fused, same
+                             summation order).  FreeWater / CylinderZeppelinBall / SANDI: the TMA-staged kernel with the SPAMS path
+                             restated step by step instead of the DMMA-batched throughput kernel (identical maps to ~1e-12);
+                             NODDI: every voxel through the A-space Lawson-Hanson path (amico/models.pyx:911, 940), not only
+                             the exact-fit ones.  Results equal the CPU oracle bit for bit; throughput is not the point. */
 
 /* element type of y */
 #define AMX_F32 0

@@ -81,11 +81,25 @@ def preprocess(dwi, scheme, mask=None, *, b0_min_signal=0.0, replace_bad_voxels=
     return {"y": y, "vox_idx": vox_idx, "mean_b0s": mean_b0s, "img": img, "b0_threshold": thr}
 
 
-def dti_design_matrix(bvals, bvecs):
-    """dipy ``design_matrix(gtab)``: columns Dxx, Dxy, Dyy, Dxz, Dyz, Dzz, dummy (lower-triangular order), negated."""
+def gradient_table(bvals, bvecs, b0_threshold=B0_THRESHOLD_DIPY, atol=1e-2):
+    """``gtab.bvals, gtab.bvecs`` of dipy's ``gradient_table(bvals, bvecs)`` (published dipy.core.gradients, restated -- dipy is
+    absent, unpinned): non-unit directions (|norm - 1| > atol) are zeroed with their b-value, which must not happen to a
+    diffusion-weighted row; ``gradients = b g``; ``bvals = |gradients|``; ``bvecs = gradients / bvals``."""
     bvals = np.asarray(bvals, dtype=np.float64)
     bvecs = np.array(bvecs, dtype=np.float64)
-    bvecs[bvals <= B0_THRESHOLD_DIPY] = 0.0  # gradient_table zeroes the b0 directions
+    bvecs = np.where(np.isnan(bvecs), 0, bvecs)
+    close = np.abs(np.linalg.norm(bvecs, axis=1) - 1) <= atol
+    if not np.all(close[bvals > b0_threshold]):
+        raise ValueError("The vectors in bvecs should be unit (The tolerance can be modified as an input parameter)")
+    bvecs = np.where(close[:, None], bvecs, 0)
+    gradients = (bvals * close)[:, None] * bvecs
+    b = np.linalg.norm(gradients, axis=1)
+    return b, gradients / (b + (b == 0))[:, None]
+
+
+def dti_design_matrix(bvals, bvecs):
+    """dipy ``design_matrix(gtab)``: columns Dxx, Dxy, Dyy, Dxz, Dyz, Dzz, dummy (lower-triangular order), negated."""
+    bvals, bvecs = gradient_table(bvals, bvecs)
     B = np.zeros((len(bvals), 7))
     B[:, 0] = bvecs[:, 0] * bvecs[:, 0] * 1.0 * bvals
     B[:, 1] = bvecs[:, 0] * bvecs[:, 1] * 2.0 * bvals

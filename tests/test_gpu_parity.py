@@ -4,9 +4,10 @@
 * the committed golden fixtures produced by the reference's own Cython glue (tests/golden/),
 * size-independent properties at the benchmark's full size.
 
-Bars: LUT indices and every lasso-only model (FreeWater, CylinderZeppelinBall, SANDI) BIT-EXACT against the
-oracle (same algorithm, same operation order); NODDI (its two NNLS stages run in Gram space)
-within the north-star tolerance |gpu - ref| <= 1e-4 * max(|ref|, 1e-3) on >= 99.9 % of the voxels.
+Bars: LUT indices bit-exact.  Default (throughput) kernels: every map within the north-star tolerance
+|gpu - ref| <= 1e-4 * max(|ref|, 1e-3) on >= 99.99 % of the voxels (golden fixtures: 100 %).  Bit-reproducible kernels
+(``exact=True`` = AMX_FLAG_EXACT): FreeWater, CylinderZeppelinBall, SANDI and NODDI BIT-EXACT against the oracle (same
+algorithm, same operation order, un-fused arithmetic).
 """
 import os
 
@@ -88,7 +89,7 @@ def test_lut_out_of_range_raises():
 def test_lasso_models_bit_exact_vs_oracle(cfg, model, n_vox):
     P = synth.make_problem(cfg, n_vox=n_vox, model=model)
     ref = orc().fit_problem(P, rmse=True, nrmse=True, extra=True, return_debug=True, nthreads=os.cpu_count())
-    got = gpu_fit(P, rmse=True, nrmse=True, extra=True, debug=True)
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=True, debug=True, exact=True)
     assert got["_counters"]["launches"] >= 1 and got["_counters"]["overflow_voxels"] == 0
     assert np.array_equal(got["lut"], ref["lut"]) or model == "SANDI"
     assert np.array_equal(got["estimates"], ref["estimates"])
@@ -98,6 +99,30 @@ def test_lasso_models_bit_exact_vs_oracle(cfg, model, n_vox):
         assert np.array_equal(got["y_corrected"], ref["y_corrected"])
     if model != "SANDI":
         assert np.array_equal(got["_dirs"], ref["dirs"])
+
+
+@pytest.mark.parametrize("cfg,model,n_vox", [(1, "FreeWater", 20000), (1, "FreeWaterMouse", 20000), (5, "CylinderZeppelinBall", 20000),
+                                              (4, "SANDI", 50000)])
+def test_lasso_models_throughput_kernel_vs_oracle(cfg, model, n_vox):
+    """Default path of the single-fit models (DMMA-batched A^T y + fused LARS): the elastic net is strictly convex, so the maps
+    must agree with the oracle far inside the 1e-4 band; supports must be identical."""
+    P = synth.make_problem(cfg, n_vox=n_vox, model=model)
+    ref = orc().fit_problem(P, rmse=True, nrmse=True, extra=True, return_debug=True, nthreads=os.cpu_count())
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=True, debug=True)
+    assert got["_counters"]["overflow_voxels"] == 0
+    rel = rel_err(got["estimates"], ref["estimates"])
+    frac = float((rel <= TOL).all(axis=1).mean())
+    exact = gpu_fit(P, debug=True, exact=True)  # the bit-reproducible kernel reports the oracle's supports and coefficients
+    sup = float((got["support"] == exact["support"]).mean())
+    dx = np.abs(got["x"] - exact["x"]).max()
+    print(f"{model}: pass fraction {frac:.6f}, support equality {sup:.6f}, p99 {np.percentile(rel, 99):.2e}, max {rel.max():.2e}, max |dx| {dx:.2e}")
+    assert frac >= 0.9999 and sup >= 0.9999
+    ok = (rel <= TOL).all(axis=1)
+    # (FreeWater's ridge is 1e-3 on highly coherent zeppelins: fused vs un-fused arithmetic shows up at the 1e-7 level there)
+    assert np.abs(got["rmse"][ok] - ref["rmse"][ok]).max() < 1e-6
+    assert np.abs(got["nrmse"][ok] - ref["nrmse"][ok]).max() < 1e-6
+    if "y_corrected" in ref:
+        assert np.abs(got["y_corrected"][ok] - ref["y_corrected"][ok]).max() < 1e-6
 
 
 # ----------------------------------------------------------------------------------------------- NODDI
@@ -183,14 +208,15 @@ def test_noddi_known_answers():
 def test_golden_reference_glue(name, cfg, model, n_vox, seed):
     g = np.load(os.path.join(GOLDEN, name + ".npz"))
     P = synth.make_problem(cfg, n_vox=n_vox, model=model, seed=seed)
-    got = gpu_fit(P, rmse=True, nrmse=True, extra=model in ("NODDI", "FreeWater", "FreeWaterMouse"))
-    if model == "NODDI":
-        assert pass_fraction(got["estimates"], g["estimates"]) == 1.0
-        assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
-    else:
-        for k in ("estimates", "rmse", "nrmse", "y_corrected"):
-            if k in g.files:
-                assert np.array_equal(got[k], g[k]), k
+    has_extra = model in ("NODDI", "FreeWater", "FreeWaterMouse")
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=has_extra)
+    assert pass_fraction(got["estimates"], g["estimates"]) == 1.0
+    assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
+    # the bit-reproducible kernels reproduce the reference glue's output exactly -- NODDI included (A-space Lawson-Hanson)
+    got = gpu_fit(P, rmse=True, nrmse=True, extra=has_extra, exact=True)
+    for k in ("estimates", "rmse", "nrmse", "y_corrected", "estimates_mod"):
+        if k in g.files and k in got:
+            assert np.array_equal(got[k], g[k]), k
 
 
 def test_golden_on_reference_direction_set():
@@ -221,8 +247,10 @@ def test_zero_signal_and_regularisation_sweep():
     P.y[::7] = 0.0
     for l1, l2 in ((0.0, 1e-3), (0.05, 1e-3), (0.5, 0.0), (0.0, 4.0), (10.0, 1e-3)):
         ref = orc().fit_problem(P, lambda1=l1, lambda2=l2)
-        got = gpu_fit(P, lambda1=l1, lambda2=l2)
+        got = gpu_fit(P, lambda1=l1, lambda2=l2, exact=True)
         assert np.array_equal(got["estimates"], ref["estimates"]), (l1, l2)
+        got = gpu_fit(P, lambda1=l1, lambda2=l2)
+        assert pass_fraction(got["estimates"], ref["estimates"]) == 1.0, (l1, l2)
 
 
 def test_single_b0_scheme_rows():
@@ -256,6 +284,25 @@ def test_device_tensor_path_matches_host_path():
         assert np.array_equal(dev64["estimates"].cpu().numpy(), host["estimates"])
 
 
+def test_host_staging_of_pageable_float64_signals():
+    """The plugin hands the library `evaluation.y`: pageable float64 (amico/core.py:451-452).  Host threads narrow it to float32 in
+    pinned staging when that is lossless, chunk by chunk, and keep float64 for a chunk that holds a value float32 cannot carry;
+    either way the maps equal those of the device-resident fit of the same values."""
+    import torch
+    P = synth.make_problem(2, n_vox=300000, seed=23)
+    l1, l2 = orc().DEFAULT_LAMBDAS["NODDI"]
+    y64 = P.y.astype(np.float64)
+    with make_plan(P) as plan:
+        dev = plan.fit(torch.from_numpy(P.y).cuda(), torch.from_numpy(np.array(P.DIRs)).cuda(), l1, l2)["estimates"].cpu().numpy()
+        host = plan.fit(y64, np.array(P.DIRs), l1, l2)["estimates"]
+        assert np.array_equal(host, dev)
+        y64[123456, 7] += 1e-12  # not representable in float32: that chunk travels as float64
+        host2 = plan.fit(y64, np.array(P.DIRs), l1, l2)["estimates"]
+        dev2 = plan.fit(torch.from_numpy(y64).cuda(), torch.from_numpy(np.array(P.DIRs)).cuda(), l1, l2)["estimates"].cpu().numpy()
+        assert np.array_equal(host2, dev2)
+        assert np.array_equal(np.delete(host2, 123456, axis=0), np.delete(dev, 123456, axis=0))
+
+
 def test_model_plugin_surface_end_to_end():
     """The drop-in classes: model.fit(evaluation) with the attributes the reference's Evaluation provides."""
     from amico_b200 import models
@@ -287,7 +334,10 @@ def test_model_plugin_surface_end_to_end():
     ev = Evaluation(P, {})
     s = models.SANDI()
     s.set_solver()
-    assert np.array_equal(s.fit(ev)["estimates"], orc().fit_problem(P)["estimates"])
+    want = orc().fit_problem(P)["estimates"]
+    assert pass_fraction(s.fit(ev)["estimates"], want) == 1.0
+    ev._cfg["amx_exact"] = True  # our own key: the bit-reproducible kernels
+    assert np.array_equal(s.fit(ev)["estimates"], want)
 
 
 # ----------------------------------------------------------------------------------------------- full-size properties
@@ -359,11 +409,9 @@ def test_default_geometric_host_schedule_matches_single_shot(monkeypatch):
     assert np.array_equal(d0, d1) and (d0[:, 1] >= 0).all()
 
 
-@pytest.mark.parametrize("env", [{"AMX_NODDI_SPLIT": "0"}, {"AMX_NODDI_BATCHED": "0"}, {"AMX_NODDI_BATCHED": "0", "AMX_NO_TMA": "1"},
-                                 {"AMX_WARPS": "8"}, {"AMX_COMPACT3": "0"}, {"AMX_STAGE1_WARPS": "24", "AMX_STAGE2_WARPS": "24"}, {"AMX_STAGE2_WARPS": "28", "AMX_STAGE3_WARPS": "28"}])
+@pytest.mark.parametrize("env", [{"AMX_WARPS": "8"}, {"AMX_COMPACT3": "0"}, {"AMX_STAGE1_WARPS": "24", "AMX_STAGE2_WARPS": "24"}, {"AMX_FAST_LARS": "0"}])
 def test_noddi_kernel_variants_agree(monkeypatch, env):
-    """Fused / per-voxel / non-TMA / voxel-group variants of the NODDI path are kept for A/B measurements: same maps within
-    tolerance."""
+    """Launch-geometry / solver variants of the NODDI stage kernels that remain selectable: same maps within tolerance."""
     P = synth.make_problem(2, n_vox=6000, seed=8)
     base = gpu_fit(P, extra=True)
     for k, v in env.items():
