@@ -171,6 +171,8 @@ struct amx_plan {
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
     void *hpin[2] = {nullptr, nullptr};  // pinned host staging of pageable / float64 signals (host path)
     size_t hpin_cap[2] = {0, 0};
+    void *hout[4] = {nullptr, nullptr, nullptr, nullptr};  // pinned landing buffers of pageable outputs: estimates, dirs, rmse, nrmse
+    size_t hout_cap[4] = {0, 0, 0, 0};
     int max_smem = 0, sm_count = 0;
     // last-call records
     double last_ms[8] = {0};
@@ -312,6 +314,7 @@ int amx_plan_destroy(amx_plan *pl)
         for (DevBuf *b : bufs) b->release();
     }
     for (void *h : pl->hpin) if (h) cudaFreeHost(h);
+    for (void *h : pl->hout) if (h) cudaFreeHost(h);
     if (pl->cs[1]) cudaStreamDestroy(pl->cs[1]);
     if (pl->ev_fork) cudaEventDestroy(pl->ev_fork);
     for (auto &e : pl->ev_join) if (e) cudaEventDestroy(e);
@@ -907,6 +910,27 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             }
         }
     }
+    // A device -> host copy into PAGEABLE memory blocks the calling thread until the data are there, i.e. until that chunk's fit
+    // has finished -- which would serialise the host-side staging of the next chunk behind it.  Pageable outputs therefore land in
+    // pinned buffers and are moved to the caller's arrays by host threads after the last chunk.
+    double *o_est = a->estimates, *o_dirs = a->dirs, *o_rmse = a->rmse, *o_nrmse = a->nrmse;
+    bool landed[4] = {false, false, false, false};
+    if (host && n_chunks > 1 && env_int("AMX_HOST_STAGE", 1)) {
+        double **dst[4] = {&o_est, &o_dirs, &o_rmse, &o_nrmse};
+        const size_t bytes[4] = {n * nm * sizeof(double), a->dirs ? n * 3 * sizeof(double) : 0, (d.flags & AMX_FLAG_RMSE) ? n * sizeof(double) : 0,
+                                 (d.flags & AMX_FLAG_NRMSE) ? n * sizeof(double) : 0};
+        for (int k = 0; k < 4; ++k) {
+            if (!bytes[k] || !*dst[k] || is_pinned(*dst[k])) continue;
+            if (pl->hout_cap[k] < bytes[k]) {
+                if (pl->hout[k]) cudaFreeHost(pl->hout[k]);
+                pl->hout[k] = nullptr; pl->hout_cap[k] = 0;
+                CK(cudaHostAlloc(&pl->hout[k], bytes[k], cudaHostAllocDefault));
+                pl->hout_cap[k] = bytes[k];
+            }
+            *dst[k] = (double *)pl->hout[k];
+            landed[k] = true;
+        }
+    }
     cudaStream_t cs[2] = {st, ncs > 1 ? pl->cs[1] : st};
     cudaStream_t s_in = (host && nset > 1) ? pl->s_in : st, s_out = (host && nset > 1) ? pl->s_out : st;
     CK(cudaEventRecord(pl->ev[3], st));
@@ -974,16 +998,16 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
             // kernel has flipped them, i.e. behind the fit instead of after it
             if (early_dirs) {
                 CK(cudaStreamWaitEvent(s_out, pl->ev_lut[b], 0));
-                CK(cudaMemcpyAsync(a->dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+                CK(cudaMemcpyAsync(o_dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             }
             if (nset > 1) {
                 CK(cudaEventRecord(pl->ev_comp[b], cs[wb]));
                 CK(cudaStreamWaitEvent(s_out, pl->ev_comp[b], 0));
             }
-            if (a->dirs && !early_dirs) CK(cudaMemcpyAsync(a->dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
-            CK(cudaMemcpyAsync(a->estimates + off * nm, c.estimates, cnt * nm * sizeof(double), cudaMemcpyDeviceToHost, s_out));
-            if (c.rmse) CK(cudaMemcpyAsync(a->rmse + off, c.rmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
-            if (c.nrmse) CK(cudaMemcpyAsync(a->nrmse + off, c.nrmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (a->dirs && !early_dirs) CK(cudaMemcpyAsync(o_dirs + off * 3, c.dirs, cnt * 3 * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            CK(cudaMemcpyAsync(o_est + off * nm, c.estimates, cnt * nm * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.rmse) CK(cudaMemcpyAsync(o_rmse + off, c.rmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
+            if (c.nrmse) CK(cudaMemcpyAsync(o_nrmse + off, c.nrmse, cnt * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             if (c.extra) CK(cudaMemcpyAsync(a->extra + off * extra_w, c.extra, cnt * extra_w * sizeof(double), cudaMemcpyDeviceToHost, s_out));
             if (c.support_out) CK(cudaMemcpyAsync(a->support_out + off, c.support_out, cnt * sizeof(int), cudaMemcpyDeviceToHost, s_out));
             if (c.coeff_out) CK(cudaMemcpyAsync(a->coeff_out + off * pl->n, c.coeff_out, cnt * pl->n * sizeof(double), cudaMemcpyDeviceToHost, s_out));
@@ -1005,6 +1029,18 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     long long h_status[2][8] = {{0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}, {0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}};
     for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(h_status[b], pl->work[b].status.p, sizeof h_status[b], cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    {   // pageable outputs: pinned landing buffers -> the caller's arrays
+        double *user[4] = {a->estimates, a->dirs, a->rmse, a->nrmse};
+        const size_t bytes[4] = {n * nm * sizeof(double), n * 3 * sizeof(double), n * sizeof(double), n * sizeof(double)};
+        for (int k = 0; k < 4; ++k) {
+            if (!landed[k]) continue;
+            constexpr size_t BLK = 1 << 20;
+            const char *src = (const char *)pl->hout[k];
+            char *dst = (char *)user[k];
+            const size_t total = bytes[k];
+            parallel_blocks((total + BLK - 1) / BLK, n_host_threads, [&](size_t b) { memcpy(dst + b * BLK, src + b * BLK, std::min(BLK, total - b * BLK)); });
+        }
+    }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]) == cudaSuccess) pl->last_ms[0] = ms;
     if (cudaEventElapsedTime(&ms, pl->ev[3], pl->ev[4]) == cudaSuccess) pl->last_ms[2] = ms;

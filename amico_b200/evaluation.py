@@ -102,6 +102,27 @@ class Evaluation:
 
     # ------------------------------------------------------------------ load_data (core.py:107-283)
     def load_data(self, dwi, scheme, mask=None, b0_thr=0, b0_min_signal=0, replace_bad_voxels=None, shard=None):
+        """See ``_load_data_local``.  With ``shard=(rank, world)`` the ranks first agree that every slab loaded (a rank that raised
+        -- NaN policy, geometry mismatch -- would otherwise leave the others waiting in the gathers of ``fit``)."""
+        if shard is None or int(shard[1]) <= 1:
+            return self._load_data_local(dwi, scheme, mask, b0_thr, b0_min_signal, replace_bad_voxels, shard)
+        import torch
+        import torch.distributed as dist
+        err = None
+        try:
+            self._load_data_local(dwi, scheme, mask, b0_thr, b0_min_signal, replace_bad_voxels, shard)
+        except Exception as e:  # noqa: BLE001 -- re-raised below, on every rank
+            err = e
+        flag = torch.tensor([0 if err is None else 1], dtype=torch.int32,
+                            device=torch.device("cuda", self.device) if dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            if err is not None:
+                raise err
+            raise RuntimeError("loading the data failed on another rank's voxel slab")
+        return self
+
+    def _load_data_local(self, dwi, scheme, mask=None, b0_thr=0, b0_min_signal=0, replace_bad_voxels=None, shard=None):
         """``dwi``: file name, (X, Y, Z, nS) array (numpy, or a CUDA float32 torch tensor); ``scheme``: file name, a ``Scheme``
         or an Nx4 / Nx7 table; ``mask``: file name, (X, Y, Z) array or None.  Same pre-processing, same float32 arithmetic as
         the reference.  ``shard=(rank, world)``: this process takes one contiguous slab of the flat voxel list (multi-GPU: one
@@ -239,11 +260,13 @@ class Evaluation:
         a.mean_b0s = mean_b0s.data_ptr() if mean_b0s is not None else None
         a.stream = stream
         kept, mo = C.c_int64(0), C.c_int(0)
-        rc = lib.amx_preprocess(C.byref(a), C.byref(kept), C.byref(mo))
-        if rc == L.AMX_E_NONFINITE:
-            raise FloatingPointError(lib.amx_last_error().decode())
-        L.check(rc)
-        assert kept.value == n_kept and mo.value == m_out
+        if n_total > 0:
+            rc = lib.amx_preprocess(C.byref(a), C.byref(kept), C.byref(mo))
+            if rc == L.AMX_E_NONFINITE:
+                raise FloatingPointError(lib.amx_last_error().decode())
+            L.check(rc)
+            assert kept.value == n_kept and mo.value == m_out
+        # (an empty slab -- more ranks than voxels -- has nothing to pre-process but still takes part in the gathers of fit())
         self._y = y[:n_kept]
         self._vox_idx = vox_idx[:n_kept]
         self._mean_b0s_dev = mean_b0s
@@ -267,14 +290,26 @@ class Evaluation:
             raise ValueError(f'Model "{model_name}" not recognized')
         self.model = getattr(_models, model_name)()
         self.model.device = self.device
-        self.set_config("ATOMS_path", None)
+        self.set_config("ATOMS_path", None)  # set by generate_kernels (the reference points it at <study>/kernels/<id> right away)
+        self.set_solver()  # default parameters of the fit, like core.py:298
         return self.model
 
     def set_solver(self, **params):
-        """``core.py:316-325``."""
+        """``core.py:300-325``: parameters the model's ``set_solver`` does not know are ignored with a warning, and the accepted
+        ones are recorded in ``CONFIG['solver_params']``."""
         if self.model is None:
             raise RuntimeError('Model not set; call "set_model()" method first')
-        self.model.set_solver(**params)
+        import inspect
+        import warnings
+        known = list(inspect.signature(self.model.set_solver).parameters)
+        accepted = {}
+        for key, value in params.items():
+            if key not in known:
+                warnings.warn(f"Cannot find the '{key}' solver-parameter for the {self.model.name} model. It will be ignored")
+            else:
+                accepted[key] = value
+        self.model.set_solver(**accepted)
+        self.set_config("solver_params", accepted)
 
     def set_lut(self, directions, htable):
         """The LUT direction set and its 181x181 hash table -- what the reference reads from its package data
@@ -324,6 +359,7 @@ class Evaluation:
         self.KERNELS = KERNELS
         if htable is not None:
             self.htable = htable
+        self.model.invalidate_plan()  # new tables: the device copies follow
 
     # ------------------------------------------------------------------ fit (core.py:407-498)
     @property
@@ -336,6 +372,8 @@ class Evaluation:
         if not getattr(self, "_forder", False):
             return rows
         f = self._vox_idx.cpu().numpy().astype(np.int64)  # flat index with x fastest
+        if getattr(self, "_shard", None) is not None:
+            f = f + self._slab[0]  # vox_idx counts from the start of this rank's slab
         X, Y, Z = self._dim
         x, yz = f % X, f // X
         c = (x * Y + yz % Y) * Z + yz // Y
@@ -383,11 +421,60 @@ class Evaluation:
             raise RuntimeError('Response functions not generated; call "generate_kernels()" and "load_kernels()" first')
         if self.KERNELS["model"] != self.model.id:
             raise RuntimeError("Response functions were not created with the same model")
+        if self.get_config("peaks_filename"):
+            # the reference leaves DIRs 4-D on this path (core.py:440-445), which its own chunked fit cannot consume (SURVEY 8a vi)
+            raise NotImplementedError('"peaks_filename" is not supported: directions come from the DTI fit')
+        if self._shard is None:
+            out, res = self._fit_local()
+        else:
+            # Every rank must reach the gathers below: a rank whose slab fails (NaN policy, LUT range, ...) would otherwise leave the
+            # others blocked in the collective.  Agree on the status first; the failing rank re-raises its own exception.
+            import torch.distributed as dist
+            err = None
+            try:
+                out, res = self._fit_local()
+            except Exception as e:  # noqa: BLE001 -- re-raised below, on every rank
+                err, out, res = e, None, None
+            flag = torch.tensor([0 if err is None else 1], dtype=torch.int32,
+                                device=self._y.device if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            if int(flag.item()):
+                if err is not None:
+                    raise err
+                raise RuntimeError("the fit failed on another rank's voxel slab")
+        dev = self._y.device
+        cfg = self.get_config
+        if self._shard is not None:  # one gather per volume: rank 0 ends up with the whole thing, in rank (= voxel) order
+            from .parallel import gather_maps
+            out = {k: gather_maps(v, self._shard[0], self._shard[1]) for k, v in sorted(out.items())}
+            if self._shard[0] != 0:
+                self.RESULTS = None
+                self._last_fit = res
+                return None
+        self.RESULTS = {}
+        for k, v in out.items():
+            a = v.cpu().numpy()
+            tail = (a.shape[1],) if k not in ("RMSE", "NRMSE") else ()
+            if self._forder:  # memory [z][y][x][c] -> logical (x, y, z, c) as a view
+                a = a.reshape(self._dim[::-1] + tail)
+                self.RESULTS[k] = a.transpose((2, 1, 0, 3) if tail else (2, 1, 0))
+            else:
+                self.RESULTS[k] = a.reshape(self._dim + tail)
+        self._last_fit = res
+        return self.RESULTS
+
+    def _fit_local(self):
+        """Directions, fit and scatter of this process's voxels -> ({name: device volume (n_total, k) float32}, fit result)."""
+        import torch
         dev = self._y.device
         lib = L.load()
         t = time.time()
+        n_vox = self._y.shape[0]
         if not self.get_config("doDirectionalAverage") and self.model.id != "SANDI":
-            self.estimate_directions()
+            if n_vox > 0:
+                self.estimate_directions()
+            else:
+                self._dirs = torch.empty((0, 3), dtype=torch.float64, device=dev)
         torch.cuda.synchronize(dev)
         self.set_config("dirs_precomputing_time", time.time() - t)
         t = time.time()
@@ -405,12 +492,12 @@ class Evaluation:
         # ---- store results (core.py:469-498)
         n_total = int(np.prod(self._dim)) if self._shard is None else self._slab[1] - self._slab[0]
         stream = torch.cuda.current_stream(dev).cuda_stream
-        n_vox = self._y.shape[0]
 
         def scatter(values, k):
-            vol = torch.empty((n_total, k), dtype=torch.float32, device=dev)
-            L.check(lib.amx_scatter_maps(self.device, L.SPACE_DEVICE, values.data_ptr(), n_vox, k, self._vox_idx.data_ptr(),
-                                         vol.data_ptr(), n_total, stream))
+            vol = torch.zeros((n_total, k), dtype=torch.float32, device=dev) if n_vox == 0 else torch.empty((n_total, k), dtype=torch.float32, device=dev)
+            if n_vox > 0:
+                L.check(lib.amx_scatter_maps(self.device, L.SPACE_DEVICE, values.data_ptr(), n_vox, k, self._vox_idx.data_ptr(),
+                                             vol.data_ptr(), n_total, stream))
             return vol
 
         out = {"MAPs": scatter(res["estimates"], len(self.model.maps_name))}
@@ -435,24 +522,7 @@ class Evaluation:
                 raise NotImplementedError("doKeepb0Intact without doNormalizeSignal reads mean_b0s the reference never sets")
             out["DWI_corrected"] = scatter(yc.contiguous(), yc.shape[1])
         torch.cuda.synchronize(dev)
-        if self._shard is not None:  # one gather per volume: rank 0 ends up with the whole thing, in rank (= voxel) order
-            from .parallel import gather_maps
-            out = {k: gather_maps(v, self._shard[0], self._shard[1]) for k, v in sorted(out.items())}
-            if self._shard[0] != 0:
-                self.RESULTS = None
-                self._last_fit = res
-                return None
-        self.RESULTS = {}
-        for k, v in out.items():
-            a = v.cpu().numpy()
-            tail = (a.shape[1],) if k not in ("RMSE", "NRMSE") else ()
-            if self._forder:  # memory [z][y][x][c] -> logical (x, y, z, c) as a view
-                a = a.reshape(self._dim[::-1] + tail)
-                self.RESULTS[k] = a.transpose((2, 1, 0, 3) if tail else (2, 1, 0))
-            else:
-                self.RESULTS[k] = a.reshape(self._dim + tail)
-        self._last_fit = res
-        return self.RESULTS
+        return out, res
 
     # ------------------------------------------------------------------ save_results (core.py:501-648)
     def save_results(self, path_suffix=None):

@@ -28,6 +28,21 @@ from .plan import Plan
 __all__ = ["NODDI", "FreeWater", "CylinderZeppelinBall", "SANDI", "BaseModel"]
 
 
+def _fingerprint(a):
+    """Cheap content fingerprint of a table for the plan cache: shape, dtype and a CRC of a strided sample (<= 64 Ki elements) plus
+    the array's ends.  Object identity is not enough -- an id can be reused after garbage collection and KERNELS can be rebuilt in
+    place -- and hashing 30-80 MB per ``fit`` call would cost more than the fit.  (An edit confined to elements the sample
+    misses goes unnoticed: call ``invalidate_plan()`` after poking single entries into a table.)"""
+    if a is None:
+        return None
+    import zlib
+    a = np.asarray(a)
+    flat = a.reshape(-1) if a.flags.c_contiguous else np.asfortranarray(a).reshape(-1, order="F") if a.flags.f_contiguous else a.ravel()
+    step = max(1, flat.size // 65536)
+    sample = np.ascontiguousarray(flat[::step])
+    return (a.shape, a.dtype.str, zlib.crc32(sample.tobytes()), zlib.crc32(np.ascontiguousarray(flat[-64:]).tobytes()))
+
+
 class BaseModel:
     """Common part of the plugin surface (``amico/models.pyx:75-217``)."""
 
@@ -87,8 +102,9 @@ class BaseModel:
         if K.get("model") != self.id:
             raise RuntimeError("Response functions were not created with the same model")  # core.py:417-418
         ht = getattr(evaluation, "htable", None)
-        key = (id(K), id(ht), self.device, repr(sorted((k, np.asarray(v).tobytes()) for k, v in self._model_params().items()
-                                                       if not isinstance(v, str))),
+        dwi = getattr(self.scheme, "dwi_idx", None) if self.scheme is not None else None
+        key = (tuple((k, _fingerprint(v)) for k, v in sorted(K.items()) if k != "model"), _fingerprint(ht), _fingerprint(dwi), self.device,
+               repr(sorted((k, np.asarray(v).tobytes()) for k, v in self._model_params().items() if not isinstance(v, str))),
                tuple(sorted((k, v) for k, v in self._model_params().items() if isinstance(v, str))))
         if self._plan is None or self._plan_key != key:
             if self._plan is not None:
@@ -97,6 +113,12 @@ class BaseModel:
             self._plan = Plan(self.id, K, ht, self._model_params(), dwi_idx=dwi_idx, device=self.device)
             self._plan_key = key
         return self._plan
+
+    def invalidate_plan(self):
+        """Drop the device-resident tables; the next ``fit`` uploads ``evaluation.KERNELS`` again."""
+        if self._plan is not None:
+            self._plan.close()
+        self._plan = self._plan_key = None
 
     def fit(self, evaluation):
         """``<Model>.fit(evaluation)`` (``amico/models.pyx:795-811`` etc.) on the GPU."""

@@ -51,16 +51,18 @@ def reference_tables(ndirs=500):
     return dirs, ht
 
 
-def refdirs_case():
-    """NODDI cfg2 on the reference's REAL 500-direction set + hash table: the fixture carries both tables, test directions
-    that include every degree-grid edge case, and the reference fit's maps."""
-    dirs, ht = reference_tables(500)
-    P = synth.make_problem(2, n_vox=384, seed=77, lut_dirs=dirs, htable=ht)
+def refdirs_case(ndirs=500, cfg=2, n_vox=384, seed=77):
+    """NODDI on the reference's REAL direction sets + hash tables (amico/directions/ndirs=*.bin: 1, 500 ... 10000, 32761 --
+    amico/lut.pyx:18-25): the fixture carries both tables, test directions that include every degree-grid edge case, and the
+    reference fit's maps.  ndirs = 1 (one atom orientation for every voxel) and a large set exercise the table sizes either
+    side of the default 500."""
+    dirs, ht = reference_tables(ndirs)
+    P = synth.make_problem(cfg, n_vox=n_vox, seed=seed, lut_dirs=dirs, htable=ht)
     res = ref_runner.fit_problem(P, nthreads=2, rmse=True)
     out = {k: np.asarray(v) for k, v in res.items()}
     out.update(lut_dirs=dirs, htable=ht, input_sha256=np.array(input_digest(P)))
-    np.savez_compressed(os.path.join(HERE, "noddi_refdirs500.npz"), **out)
-    print("noddi_refdirs500", {k: v.shape for k, v in out.items()})
+    np.savez_compressed(os.path.join(HERE, "noddi_refdirs%d.npz" % ndirs), **out)
+    print("noddi_refdirs%d" % ndirs, {k: v.shape for k, v in out.items()})
 
 
 def synthesis_case():
@@ -99,7 +101,8 @@ def synthesis_case():
 def main():
     if not ref_runner.available():
         raise SystemExit("oracle/_ref is not built: run python oracle/build_ref.py first")
-    refdirs_case()
+    for nd in (500, 1, 5000):
+        refdirs_case(nd)
     synthesis_case()
     for name, cfg, model, n_vox, seed, flags in CASES:
         P = synth.make_problem(cfg, n_vox=n_vox, model=model, seed=seed)

@@ -216,15 +216,26 @@ def test_golden_reference_glue(name, cfg, model, n_vox, seed):
     got = gpu_fit(P, rmse=True, nrmse=True, extra=has_extra, exact=True)
     for k in ("estimates", "rmse", "nrmse", "y_corrected", "estimates_mod"):
         if k in g.files and k in got:
-            assert np.array_equal(got[k], g[k]), k
+            if model == "NODDI" and k in ("estimates", "estimates_mod"):
+                # NDI and FWF are rational functions of the coefficients: bit-equal.  ODI = 2/pi atan2(1, k1) goes through the device
+                # atan2, which is accurate to ~2 ulp where glibc's is correctly rounded: equal to the last few bits.
+                assert np.array_equal(got[k][:, 0], g[k][:, 0]), k
+                if k == "estimates":
+                    assert np.array_equal(got[k][:, 2], g[k][:, 2]), k
+                assert np.abs(got[k][:, 1] - g[k][:, 1]).max() <= 8 * np.finfo(np.float64).eps, k
+            else:
+                assert np.array_equal(got[k], g[k]), k
 
 
-def test_golden_on_reference_direction_set():
-    """NODDI on the reference's own 500-direction set + hash table (amico/directions/*.bin, carried by the fixture)."""
-    g = np.load(os.path.join(GOLDEN, "noddi_refdirs500.npz"))
+@pytest.mark.parametrize("ndirs", [500, 1, 5000])
+def test_golden_on_reference_direction_set(ndirs):
+    """NODDI on the reference's own direction sets + hash tables (amico/directions/ndirs=*.bin, carried by the fixtures): the
+    default 500, the single-direction table and a large one (amico/lut.pyx:18-25 allows 1, 500 ... 10000, 32761)."""
+    g = np.load(os.path.join(GOLDEN, f"noddi_refdirs{ndirs}.npz"))
     P = synth.make_problem(2, n_vox=384, seed=77, lut_dirs=g["lut_dirs"], htable=g["htable"])
     got = gpu_fit(P, rmse=True, debug=True)
     assert np.array_equal(got["lut"], synth.lut_index_numpy(np.array(P.DIRs), g["htable"]))
+    assert got["lut"].max() < ndirs
     assert pass_fraction(got["estimates"], g["estimates"]) == 1.0
     assert np.abs(got["rmse"] - g["rmse"]).max() < 1e-5
 
@@ -236,10 +247,15 @@ def test_empty_and_tiny_inputs():
         r = plan.fit(P.y[:0], np.zeros((0, 3)), 0.0, 1e-3)
         assert r["estimates"].shape == (0, 2)
         ref = orc().fit_problem(P)
-        r = plan.fit(P.y, np.array(P.DIRs), 0.0, 1e-3)
-        assert np.array_equal(r["estimates"], ref["estimates"])
-        one = plan.fit(P.y[:1], np.array(P.DIRs[:1]), 0.0, 1e-3)
-        assert np.array_equal(one["estimates"], ref["estimates"][:1])
+        for exact in (True, False):  # three voxels / one voxel: ragged batches of the throughput kernel, one tile of the exact one
+            r = plan.fit(P.y, np.array(P.DIRs), 0.0, 1e-3, exact=exact)
+            one = plan.fit(P.y[:1], np.array(P.DIRs[:1]), 0.0, 1e-3, exact=exact)
+            if exact:
+                assert np.array_equal(r["estimates"], ref["estimates"])
+                assert np.array_equal(one["estimates"], ref["estimates"][:1])
+            else:
+                assert pass_fraction(r["estimates"], ref["estimates"]) == 1.0
+                assert np.array_equal(one["estimates"], r["estimates"][:1])
 
 
 def test_zero_signal_and_regularisation_sweep():

@@ -148,8 +148,8 @@ def test_chunking_is_invisible():
 
 
 # ----------------------------------------------------------------------------------------------- the reference's own LUT tables
-def _refdirs_problem():
-    g = np.load(os.path.join(GOLDEN, "noddi_refdirs500.npz"))
+def _refdirs_problem(ndirs=500):
+    g = np.load(os.path.join(GOLDEN, f"noddi_refdirs{ndirs}.npz"))
     return g, synth.make_problem(2, n_vox=384, seed=77, lut_dirs=g["lut_dirs"], htable=g["htable"])
 
 
@@ -164,10 +164,13 @@ def test_reference_hash_table_semantics():
     assert np.array_equal(synth.build_htable(dirs), ht)
 
 
-def test_oracle_reproduces_golden_on_reference_direction_set():
-    """NODDI on the reference's REAL 500-direction set and hash table: outputs of the reference's Cython fit."""
+@pytest.mark.parametrize("ndirs", [500, 1, 5000])
+def test_oracle_reproduces_golden_on_reference_direction_set(ndirs):
+    """NODDI on the reference's REAL direction sets and hash tables (500, 1 and 5000 directions): outputs of the reference's
+    Cython fit."""
     import hashlib
-    g, P = _refdirs_problem()
+    g, P = _refdirs_problem(ndirs)
+    assert g["lut_dirs"].shape == (ndirs, 3)
     h = hashlib.sha256()
     h.update(np.ascontiguousarray(P.y).tobytes())
     h.update(np.ascontiguousarray(P.DIRs).tobytes())
