@@ -3,6 +3,7 @@
 #include "amx_kernels.cuh"
 #include "amx_slow.cuh"
 #include "amx_exact.cuh"
+#include "amx_small.cuh"
 #include "amx_err.h"
 
 #include <algorithm>
@@ -165,7 +166,7 @@ struct amx_plan {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
     // per-launch workspace; two sets so that consecutive voxel chunks can be in flight on two compute streams
-    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws, exact_list, exact_a; } work[2];
+    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws, exact_list, exact_a, c1_all; } work[2];
     cudaStream_t cs[2] = {nullptr, nullptr};          // [0] == stream
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
@@ -310,7 +311,7 @@ int amx_plan_destroy(amx_plan *pl)
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &wk : pl->work) {
         DevBuf *bufs[] = {&wk.lut, &wk.order, &wk.bins, &wk.tiles, &wk.status, &wk.scratch, &wk.xiso, &wk.supmask, &wk.ovf_list, &wk.slow_ws,
-                          &wk.exact_list, &wk.exact_a};
+                          &wk.exact_list, &wk.exact_a, &wk.c1_all};
         for (DevBuf *b : bufs) b->release();
     }
     for (void *h : pl->hpin) if (h) cudaFreeHost(h);
@@ -561,6 +562,15 @@ int launch_lasso_batched(const FitParams &p, int grid, int block, size_t smem, c
 template <int MODEL, typename TS>
 int dispatch_npl(int npl, const FitParams &p, int grid, int block, size_t smem, cudaStream_t st)
 {
+    if constexpr (MODEL == MODEL_FREEWATER || MODEL == MODEL_SANDI) {
+        if (p.batched == 4) {  // thread-per-voxel kernel for dictionaries of <= 16 atoms (amx_small.cuh); grid = n_vox / 128, no shared memory
+            const int blocks = (int)std::max<long long>(1, std::min<long long>((p.n_vox + 127) / 128, (long long)grid * 16));
+            if (std::min(p.m, p.n) <= 4) k_lasso_small<MODEL, TS, 16, 4><<<blocks, 128, 0, st>>>(p);
+            else k_lasso_small<MODEL, TS, 16, 12><<<blocks, 128, 0, st>>>(p);
+            CK(cudaGetLastError());
+            return AMX_OK;
+        }
+    }
     if (MODEL != MODEL_NODDI && p.batched == 3) {
         switch (npl) {
         case 1: return block > 768 ? launch_lasso_batched<MODEL, 1, TS, 1024>(p, grid, block, smem, st)
@@ -640,6 +650,11 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     const bool batched = pl->model == AMX_MODEL_NODDI && pl->npl <= 5;  // larger dictionaries: the per-voxel kernel (k_fit)
     // single-fit models: DMMA-batched throughput kernel unless the caller asks for the bit-reproducible one
     const bool lasso_fast = pl->model != AMX_MODEL_NODDI && pl->npl <= 4 && !(a->flags & AMX_FLAG_EXACT) && env_int("AMX_LASSO_FAST", 1);
+    // ... and one voxel per THREAD when the dictionary is tiny (FreeWater, SANDI)
+    // (measured: SANDI, <= 4 active atoms, 860 M voxels/s against 317 M warp-per-voxel; FreeWater, <= 11 active atoms and 1.7 KB of
+    //  thread-local state, 44 M against 95 M -- so only paths of <= AMX_LASSO_SMALL_L atoms take it)
+    const bool lasso_small = lasso_fast && (pl->model == AMX_MODEL_FREEWATER || pl->model == AMX_MODEL_SANDI) && pl->n <= 16 &&
+                             std::min(pl->m, pl->n) <= std::min(12, env_int("AMX_LASSO_SMALL_L", 4)) && env_int("AMX_LASSO_SMALL", 1);
     const int tile_v = (batched || lasso_fast) ? BV : std::max(1, env_int("AMX_TILE_VOX", 256));
     const bool rotated = pl->model != AMX_MODEL_SANDI;
     const long long max_tiles = n_vox / tile_v + pl->ndirs + 1;
@@ -696,7 +711,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.lut = lut;
     p.est = a->estimates; p.rmse = a->rmse; p.nrmse = a->nrmse; p.extra = a->extra; p.support_out = a->support_out; p.coeff_out = a->coeff_out;
     p.status = status;
-    p.batched = batched ? 2 : lasso_fast ? 3 : 0;
+    p.batched = batched ? 2 : lasso_small ? 4 : lasso_fast ? 3 : 0;
     p.fast_lars = env_int("AMX_FAST_LARS", 1);
     p.compact3 = env_int("AMX_COMPACT3", 1);
     p.aspace = env_int("AMX_ASPACE", 1);
@@ -706,7 +721,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     p.ws_doubles = ws_doubles_for(p.NA, p.m_pad, p.dc_pad, p.batched == 2 ? 1 : 0);
 
     // shared-memory budget: [header 128][slab (optional)][nwarps x workspace]
-    if (p.batched == 3) {
+    if (p.batched == 3 || p.batched == 4) {
         p.cap_stage[1] = std::max(4, std::min(LC, std::min(pl->n, std::min(pl->m, pl->n)) + 1));  // the path never holds more than min(m, n) atoms
         if (p.W) p.cap_stage[1] = std::max(p.cap_stage[1], 18);  // the block-pivoting scratch (NNQP_KMAX x (NNQP_KMAX + 1)) lives in the same matrix area
         p.ws_doubles_stage[1] = ws_doubles_for(p.NA, p.m_pad, 0, 1, p.cap_stage[1]);
@@ -738,7 +753,9 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     if (staged) ctas_per_sm = std::max(1, std::min(ctas_per_sm, env_int("AMX_CTAS_PER_SM", 1)));
     int grid = (int)std::max<long long>(1, std::min<long long>(n_tiles_bound, (long long)pl->sm_count * ctas_per_sm));
 
-    if (p.batched == 3) {
+    if (p.batched == 4) {
+        // no per-warp scratch
+    } else if (p.batched == 3) {
         CK(wk.scratch.reserve((size_t)grid * 32 * BV * p.NA * sizeof(double)));
         p.scratch = (double *)wk.scratch.p;
     } else if (p.batched) {
@@ -748,6 +765,12 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         CK(wk.supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
         p.xiso = (double *)wk.xiso.p;
         p.supmask = (unsigned *)wk.supmask.p;
+        // stage 1's c1 = A^T y kept per voxel for stage 3 when it fits the budget (AMX_C1_STORE_MB, default 4096 MB)
+        const size_t c1_bytes = (size_t)n_vox * p.NA * sizeof(double);
+        if (c1_bytes <= (size_t)std::max(0, env_int("AMX_C1_STORE_MB", 4096)) * 1048576) {
+            CK(wk.c1_all.reserve(c1_bytes));
+            p.c1_all = (double *)wk.c1_all.p;
+        }
         p.ovf_cap = 4 * n_vox;
         CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
         p.ovf_list = (int *)wk.ovf_list.p;

@@ -258,6 +258,8 @@ struct FitParams {
     double *scratch;  // batched NODDI path: per-warp [2][8][NA] doubles
     int batched;
     double *xiso;        // split NODDI path: [n_vox][2] (x_iso, x_dot) by sorted position
+    double *c1_all;      // split NODDI path: c1 = A^T y of every voxel [n_vox][NA] by sorted position, written by stage 1 and reused by
+                         // stage 3 (NULL: stage 3 recomputes it on the tensor pipe -- volumes whose c1 would not fit the budget)
     const int *lut;      // LUT index per voxel (k_lut)
     int *ovf_list;       // voxels whose active set outgrew a warp: re-fitted by the scalar slow path (amx_slow.cuh)
     long long ovf_cap;
@@ -926,12 +928,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage(const FitParams p)
             }
         } else {
             const double *T1 = p.T1 + (size_t)tile.x * p.T1_stride;
-            gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, scr, NA, lane, STAGE == 1 ? ws.bx : nullptr);
+            // c1 of the batch: stage 1 computes it (DMMA) -- into the per-voxel store when there is one, so that stage 3 only reads it
+            double *c1b = p.c1_all ? p.c1_all + (size_t)tile.y * NA : scr;
+            if (STAGE == 1 || !p.c1_all) gemm_c1<NT, TP, TS>(S, n_pad, m, p.y, p.y_f64, myvox, vvalid, c1b, NA, lane, STAGE == 1 ? ws.bx : nullptr);
             #pragma unroll 1
             for (int v = 0; v < nb; ++v) {
                 const long long pos = tile.y + v;
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
+                for (int s = 0; s < NPL; ++s) ws.c1[lane + 32 * s] = c1b[(size_t)v * NA + lane + 32 * s];
                 __syncwarp();
                 const ASpace asp{(const float *)S, n_pad, m, p.y, p.y_f64, (long long)p.order[pos]};
                 const ASpace *as = (p.aspace && sizeof(TS) == 4) ? &asp : nullptr;

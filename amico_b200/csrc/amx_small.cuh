@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(128) k_lasso_small(const FitParams p)
                     na = i + 1;
                     // path direction u = invGs * sign(DtR_S)
                     #pragma unroll 1
-                    for (int j = 0; j <= i; ++j) gs[j] = DtR_at(DtR, ind[j]) > 0.0 ? 1.0 : -1.0;
+                    for (int j = 0; j <= i; ++j) gs[j] = DtR[ind[j]] > 0.0 ? 1.0 : -1.0;
                     #pragma unroll 1
                     for (int r = 0; r <= i; ++r) {
                         double s = 0.0;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(128) k_lasso_small(const FitParams p)
                         const double r = -coef[j] / u[j];
                         if (r > 0.0 && r <= step_max) { step_max = r; fz = j; }
                     }
-                    const double cc = fabs(DtR_at(DtR, ind[0]));
+                    const double cc = fabs(DtR[ind[0]]);
                     // correlation slopes and the first inactive atom reaching the common correlation (smallest |step|, lowest index)
                     double sl[NMAX];
                     double best = INFINITY, step = INFINITY;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128) k_lasso_small(const FitParams p)
                     double coeff1 = 0.0, coeff2 = 0.0;
                     #pragma unroll 1
                     for (int j = 0; j <= i; ++j) {
-                        const double dl = DtR_at(DtR, ind[j]);
+                        const double dl = DtR[ind[j]];
                         coeff1 += dl > 0.0 ? u[j] : -u[j];
                         coeff2 = fma(dl, u[j], coeff2);
                     }
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(128) k_lasso_small(const FitParams p)
                 }
                 #pragma unroll 1
                 for (int j = 0; j < na; ++j)
-                    if (ind[j] >= 0) set_at(x, ind[j], coef[j]);
+                    if (ind[j] >= 0) x[ind[j]] = coef[j];
             }
         }
         // ---- maps and optional outputs

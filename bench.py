@@ -323,7 +323,8 @@ def config_record(cfg, dev, steps, warmup, kind, cores, n_vox=None, cpu=True):
     cnt = plan.last_counters()
     rec.update({"ms_per_step": ms, "voxels_per_s": n_vox / ms * 1e3, "fit_kernel_ms": k_ms, "bytes_per_voxel": B,
                 "roofline_frac": B * n_vox / (ms * 1e-3) / 1e9 / peak, "overflow_voxels": cnt["overflow_voxels"],
-                "slow_path_voxels": cnt["slow_path_voxels"], "gpu_launches_per_step": cnt["launches"] + (3 if model == "SANDI" else 0)})
+                "slow_path_voxels": cnt["slow_path_voxels"], "exact_path_voxels": cnt["exact_path_voxels"],
+                "nan_values": int(torch.isnan(est).sum().item()), "gpu_launches_per_step": cnt["launches"] + (3 if model == "SANDI" else 0)})
     if cpu:
         # parity sample + CPU baseline on the first voxels of the same data (the CPU arm reads the fit's own inputs)
         n_s = cpu_sample_size(cores, n_vox, plan.m, model)
@@ -354,10 +355,22 @@ def sharded_cfg3(rank, world, dev, steps):
     torch.cuda.synchronize(); dist.barrier()
     t_bcast = time.perf_counter() - t0  # includes rank 0's kernel synthesis; the NCCL part alone is timed below
     kbytes = sum(np.asarray(v).nbytes for k, v in P.KERNELS.items() if k != "model")
-    t0 = time.perf_counter()
-    parallel.broadcast_arrays({k: v for k, v in P.KERNELS.items() if k != "model"} if rank == 0 else None, 0, rank, world, dev)
+    # the NCCL broadcast alone: the tables as device tensors, CUDA events around the collectives
+    dts = [torch.from_numpy(np.ascontiguousarray(v).view(np.uint8).reshape(-1)).to(dev) for k, v in sorted(P.KERNELS.items()) if k != "model"]
+    for _ in range(2):
+        for t in dts:
+            dist.broadcast(t, src=0)
     torch.cuda.synchronize(); dist.barrier()
-    t_bcast_nccl = time.perf_counter() - t0
+    eb0, eb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eb0.record()
+    for t in dts:
+        dist.broadcast(t, src=0)
+    eb1.record()
+    torch.cuda.synchronize()
+    tb = torch.tensor([eb0.elapsed_time(eb1)], dtype=torch.float64, device=dev)
+    dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+    t_bcast_nccl = float(tb.item()) / 1e3
+    del dts
     mdl = amx_models.NODDI()
     mdl.set_solver()
     l1, l2 = mdl.solver_params["lambda1"], mdl.solver_params["lambda2"]
@@ -388,7 +401,7 @@ def sharded_cfg3(rank, world, dev, steps):
             "voxels": n_total, "ranks": world, "kernels_bytes": int(kbytes), "setup_broadcast_ms_incl_synthesis": 1e3 * t_bcast,
             "broadcast_ms": 1e3 * t_bcast_nccl, "fit_ms_per_rank": [float(x) for x in np.mean(np.array(fit_ms), axis=0)],
             "gather_ms": float(np.mean(gather_ms)), "gather_bytes": int(n_total * 3 * 4), "ms_per_volume": tot,
-            "voxels_per_s": n_total / tot * 1e3, "checksum": float(maps.sum().item()),
+            "voxels_per_s": n_total / tot * 1e3, "checksum": float(torch.nan_to_num(maps).sum().item()), "nan_values": int(torch.isnan(maps).sum().item()),
             "what": "per step: barrier, fit of the rank's slab (device-resident), NCCL gather of the float32 maps on rank 0; max over ranks"}
 
 

@@ -101,11 +101,16 @@ def test_lasso_models_bit_exact_vs_oracle(cfg, model, n_vox):
         assert np.array_equal(got["_dirs"], ref["dirs"])
 
 
-@pytest.mark.parametrize("cfg,model,n_vox", [(1, "FreeWater", 20000), (1, "FreeWaterMouse", 20000), (5, "CylinderZeppelinBall", 20000),
-                                              (4, "SANDI", 50000)])
-def test_lasso_models_throughput_kernel_vs_oracle(cfg, model, n_vox):
-    """Default path of the single-fit models (DMMA-batched A^T y + fused LARS): the elastic net is strictly convex, so the maps
-    must agree with the oracle far inside the 1e-4 band; supports must be identical."""
+@pytest.mark.parametrize("cfg,model,n_vox,env", [(1, "FreeWater", 20000, {}), (1, "FreeWaterMouse", 20000, {}), (5, "CylinderZeppelinBall", 20000, {}),
+                                                  (4, "SANDI", 50000, {}), (1, "FreeWater", 20000, {"AMX_LASSO_SMALL_L": "12"}),
+                                                  (4, "SANDI", 50000, {"AMX_LASSO_SMALL": "0"}), (5, "CylinderZeppelinBall", 20000, {"AMX_CZB_DENSE": "0"})])
+def test_lasso_models_throughput_kernel_vs_oracle(cfg, model, n_vox, env, monkeypatch):
+    """Default paths of the single-fit models -- thread-per-voxel LARS for SANDI's 4-atom paths, DMMA-batched A^T y + fused LARS
+    for FreeWater, + certified dense-start NNQP for CylinderZeppelinBall -- and the alternatives behind the env switches
+    (thread-per-voxel FreeWater, warp-per-voxel SANDI, LARS-only CylinderZeppelinBall):
+    the elastic net is strictly convex, so the maps must agree with the oracle far inside the 1e-4 band; supports must be identical."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
     P = synth.make_problem(cfg, n_vox=n_vox, model=model)
     ref = orc().fit_problem(P, rmse=True, nrmse=True, extra=True, return_debug=True, nthreads=os.cpu_count())
     got = gpu_fit(P, rmse=True, nrmse=True, extra=True, debug=True)
