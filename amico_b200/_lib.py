@@ -24,7 +24,7 @@ EXPORTS = [
     "amx_plan_create_noddi", "amx_plan_create_freewater", "amx_plan_create_czb", "amx_plan_create_sandi",
     "amx_plan_destroy", "amx_plan_info", "amx_fit", "amx_lut_indices", "amx_plan_last_timing",
     "amx_plan_last_counters",
-    "amx_preprocess", "amx_mean_b0", "amx_dti_directions", "amx_scatter_maps", "amx_resample_kernels", "amx_volume_to_voxel_major",
+    "amx_preprocess", "amx_mean_b0", "amx_dti_directions", "amx_dti_directions_wls", "amx_scatter_maps", "amx_resample_kernels", "amx_volume_to_voxel_major",
 ]
 
 
@@ -86,6 +86,7 @@ def load():
     lib.amx_preprocess.argtypes = [C.POINTER(PreArgs), C.POINTER(i64), C.POINTER(i32)]
     lib.amx_mean_b0.argtypes = [i32, i32, vp, i64, i32, vp, i32, vp, vp]
     lib.amx_dti_directions.argtypes = [i32, i32, vp, i32, i64, i32, vp, dbl, vp, vp]
+    lib.amx_dti_directions_wls.argtypes = [i32, i32, vp, i32, i64, i32, vp, vp, dbl, vp, vp]
     lib.amx_scatter_maps.argtypes = [i32, i32, vp, i64, i32, vp, vp, i64, vp]
     lib.amx_resample_kernels.argtypes = [i32, i32, vp, i64, i32, vp, vp, i32, vp, i32, i32, vp, vp]
     lib.amx_volume_to_voxel_major.argtypes = [i32, i32, vp, i32, i64, i32, dbl, dbl, vp, vp]

@@ -515,8 +515,8 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     if (wide_ok && w2 == 32 && fits(32, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 1024>, 32, p.ws_doubles_stage[1]);
     else k2<<<grid, block, s2, st>>>(p);
     if (rc) return rc;
-    (void)w3;
-    k3<<<grid, block, s3, st>>>(p);
+    if (wide_ok && w3 == 32 && fits(32, p.ws_doubles_stage[2])) rc = launch_wide(k_noddi_stage<3, NPL, float, 1024>, 32, p.ws_doubles_stage[2]);
+    else k3<<<grid, block, s3, st>>>(p);
     if (rc) return rc;
     CK(cudaGetLastError());
     return AMX_OK;
@@ -787,6 +787,12 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
             p.exact_list = (int *)wk.exact_list.p;
         }
     }
+    if (pl->model == AMX_MODEL_NODDI && !p.batched) {  // per-voxel kernel (dictionaries of > 160 atoms): overflow queue of the slow path
+        p.ovf_cap = n_vox;
+        CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
+        p.ovf_list = (int *)wk.ovf_list.p;
+        CK(cudaMemsetAsync(status + 2, 0, sizeof(long long), st));
+    }
     int rc;
     switch (pl->model) {
     case AMX_MODEL_NODDI:
@@ -816,7 +822,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
             *launches += 1;
         }
     }
-    if (p.batched == 2) {
+    if (p.batched == 2 || (pl->model == AMX_MODEL_NODDI && !p.batched)) {
         // voxels whose active set outgrew a warp (possible with a small lambda1) are re-fitted by the scalar slow path;
         // the launch is unconditional and returns at once when the queue is empty
         const int cap = std::min(pl->m, pl->n) + 2;

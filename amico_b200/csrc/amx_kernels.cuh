@@ -636,6 +636,15 @@ __device__ __forceinline__ void lasso_outputs(const FitParams &p, const TS *S, d
         fit_errors<NPL, TS>(S, n_pad, n, m, yv, x, p.flags, p.rmse ? p.rmse + vox : nullptr, p.nrmse ? p.nrmse + vox : nullptr, lane);
 }
 
+// queue a voxel for the scalar slow path (status[2] counts the entries)
+__device__ __forceinline__ void queue_slow(const FitParams &p, long long vox, int lane)
+{
+    if (lane == 0) {
+        unsigned long long idx = atomicAdd((unsigned long long *)&p.status[2], 1ull);
+        if ((long long)idx < p.ovf_cap) p.ovf_list[idx] = (int)vox;
+    }
+}
+
 template <int MODEL, int NPL, typename TS>
 __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
 {
@@ -755,7 +764,10 @@ __global__ void __launch_bounds__(512, 1) k_fit(const FitParams p)
             } else {
                 lasso_outputs<MODEL, NPL, TS>(p, S, ws.y, ws.x, vox, support, lane);
             }
-            if (overflow) ++n_overflow;
+            if (overflow) {
+                if (MODEL == MODEL_NODDI && p.ovf_list) queue_slow(p, vox, lane);  // re-fitted by the scalar slow path
+                else ++n_overflow;
+            }
             __syncwarp();
             // next voxel of this tile
             int nv = 0;
@@ -842,15 +854,6 @@ __global__ void __launch_bounds__(MAXT, 1) k_lasso_batched(const FitParams p)
         }
     }
     if (lane == 0 && n_overflow) atomicAdd((unsigned long long *)&p.status[3], (unsigned long long)n_overflow);
-}
-
-// queue a voxel for the scalar slow path (status[2] counts the entries)
-__device__ __forceinline__ void queue_slow(const FitParams &p, long long vox, int lane)
-{
-    if (lane == 0) {
-        unsigned long long idx = atomicAdd((unsigned long long *)&p.status[2], 1ull);
-        if ((long long)idx < p.ovf_cap) p.ovf_list[idx] = (int)vox;
-    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -502,6 +502,86 @@ __global__ void __launch_bounds__(256) k_dti(const T *__restrict__ y, long long 
     }
 }
 
+// WLS variant (DTI_fit_method 'WLS', amico/core.py:95, 419, 436 -> dipy wls_fit_tensor): weights w = exp(X beta_ols) -- the OLS
+// prediction of the signal --, then beta = argmin || diag(w) (X beta - log s) ||, here through the 7 x 7 normal equations
+// X^T W^2 X beta = X^T W^2 log s (Cholesky, columns of X scaled to unit size; dipy takes pinv(diag(w) X): same minimiser).
+// One thread per voxel, two passes over its row; W7 (7 x m rows of pinv(X)) and X (m x 7) in shared memory.
+template <typename T>
+__global__ void __launch_bounds__(128) k_dti_wls(const T *__restrict__ y, long long n_vox, int m, const double *__restrict__ W7,
+                                                 const double *__restrict__ X, double min_signal, double *dirs)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *sW = reinterpret_cast<double *>(smem_raw), *sX = sW + 7 * m;
+    __shared__ double cs[7];
+    for (int i = threadIdx.x; i < 7 * m; i += blockDim.x) { sW[i] = W7[i]; sX[i] = X[i]; }
+    __syncthreads();
+    if (threadIdx.x < 7) {  // column scale: 1 / max |X[:, k]|
+        double mx = 0.0;
+        for (int j = 0; j < m; ++j) mx = fmax(mx, fabs(sX[j * 7 + threadIdx.x]));
+        cs[threadIdx.x] = mx > 0.0 ? 1.0 / mx : 1.0;
+    }
+    __syncthreads();
+    for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vox; v += (long long)gridDim.x * blockDim.x) {
+        const T *r = y + v * m;
+        double b[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll 2
+        for (int j = 0; j < m; ++j) {
+            const double ls = log(fmax((double)r[j], min_signal));
+#pragma unroll
+            for (int k = 0; k < 7; ++k) b[k] = fma(sW[k * m + j], ls, b[k]);
+        }
+        double N[28], rhs[7];  // lower triangle of X^T W^2 X (scaled), row-major packed
+#pragma unroll
+        for (int k = 0; k < 28; ++k) N[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) rhs[k] = 0.0;
+#pragma unroll 1
+        for (int j = 0; j < m; ++j) {
+            const double ls = log(fmax((double)r[j], min_signal));
+            double xs[7], yh = 0.0;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) { const double x = sX[j * 7 + k]; yh = fma(x, b[k], yh); xs[k] = x * cs[k]; }
+            const double w = exp(yh), w2 = w * w;
+#pragma unroll
+            for (int a = 0; a < 7; ++a) {
+                const double wa = w2 * xs[a];
+                rhs[a] = fma(wa, ls, rhs[a]);
+#pragma unroll
+                for (int c = 0; c <= a; ++c) N[a * (a + 1) / 2 + c] = fma(wa, xs[c], N[a * (a + 1) / 2 + c]);
+            }
+        }
+        // Cholesky N = L L^T in place, then two triangular solves
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+#pragma unroll
+            for (int c = 0; c <= a; ++c) {
+                double sum = N[a * (a + 1) / 2 + c];
+#pragma unroll
+                for (int k = 0; k < c; ++k) sum = fma(-N[a * (a + 1) / 2 + k], N[c * (c + 1) / 2 + k], sum);
+                N[a * (a + 1) / 2 + c] = (a == c) ? sqrt(fmax(sum, 1e-300)) : sum / N[c * (c + 1) / 2 + c];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 7; ++a) {
+            double sum = rhs[a];
+#pragma unroll
+            for (int k = 0; k < a; ++k) sum = fma(-N[a * (a + 1) / 2 + k], rhs[k], sum);
+            rhs[a] = sum / N[a * (a + 1) / 2 + a];
+        }
+#pragma unroll
+        for (int a = 6; a >= 0; --a) {
+            double sum = rhs[a];
+#pragma unroll
+            for (int k = a + 1; k < 7; ++k) sum = fma(-N[k * (k + 1) / 2 + a], rhs[k], sum);
+            rhs[a] = sum / N[a * (a + 1) / 2 + a];
+        }
+        double e[3];
+        principal_evec(rhs[0] * cs[0], rhs[1] * cs[1], rhs[2] * cs[2], rhs[3] * cs[3], rhs[4] * cs[4], rhs[5] * cs[5], e);
+        double *o = dirs + v * 3;
+        o[0] = e[0]; o[1] = e[1]; o[2] = e[2];
+    }
+}
+
 // ---- result scatter ----------------------------------------------------------------------------------------------------
 __global__ void k_scatter_maps(const double *__restrict__ values, long long n_vox, int k, const int *__restrict__ vox_idx,
                                float *volume)
@@ -850,6 +930,53 @@ int amx_dti_directions(int device, int space, const void *y, int y_dtype, int64_
     if (host) {
         AMX_CK(cudaMemcpyAsync(dirs, dst, (size_t)n_vox * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
         AMX_CK(cudaStreamSynchronize(s));
+    }
+    return AMX_OK;
+}
+
+int amx_dti_directions_wls(int device, int space, const void *y, int y_dtype, int64_t n_vox, int m, const double *W7, const double *X,
+                           double min_signal, double *dirs, void *stream)
+{
+    if (!y || !W7 || !X || !dirs || n_vox < 0 || m <= 0) return amx::set_error(AMX_E_INVALID, "bad arguments");
+    if (y_dtype != AMX_F32 && y_dtype != AMX_F64) return amx::set_error(AMX_E_INVALID, "bad y_dtype");
+    int rc, sm = 0, max_smem = 0;
+    if ((rc = pick_device(device, &sm, &max_smem))) return rc;
+    if (n_vox == 0) return AMX_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    Tmp tmp(s);
+    const bool host = space == AMX_SPACE_HOST;
+    const size_t esz = y_dtype == AMX_F64 ? 8 : 4;
+    double *d_W = nullptr, *d_X = nullptr;
+    AMX_CK(tmp.alloc((void **)&d_W, (size_t)7 * m * sizeof(double)));
+    AMX_CK(tmp.alloc((void **)&d_X, (size_t)7 * m * sizeof(double)));
+    AMX_CK(cudaMemcpyAsync(d_W, W7, (size_t)7 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+    AMX_CK(cudaMemcpyAsync(d_X, X, (size_t)7 * m * sizeof(double), cudaMemcpyHostToDevice, s));
+    const void *src = y;
+    double *dst = dirs;
+    if (host) {
+        void *d_y = nullptr;
+        double *d_d = nullptr;
+        AMX_CK(tmp.alloc(&d_y, (size_t)n_vox * m * esz));
+        AMX_CK(cudaMemcpyAsync(d_y, y, (size_t)n_vox * m * esz, cudaMemcpyHostToDevice, s));
+        AMX_CK(tmp.alloc((void **)&d_d, (size_t)n_vox * 3 * sizeof(double)));
+        src = d_y; dst = d_d;
+    }
+    const size_t smem = (size_t)14 * m * sizeof(double);
+    if (smem > (size_t)max_smem) return amx::set_error(AMX_E_INVALID, "m=%d too large for the shared-memory design matrix", m);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((n_vox + 127) / 128, (long long)sm * 8));
+    if (y_dtype == AMX_F64) {
+        AMX_CK(cudaFuncSetAttribute(k_dti_wls<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dti_wls<double><<<grid, 128, smem, s>>>((const double *)src, n_vox, m, d_W, d_X, min_signal, dst);
+    } else {
+        AMX_CK(cudaFuncSetAttribute(k_dti_wls<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_dti_wls<float><<<grid, 128, smem, s>>>((const float *)src, n_vox, m, d_W, d_X, min_signal, dst);
+    }
+    AMX_CK(cudaGetLastError());
+    if (host) {
+        AMX_CK(cudaMemcpyAsync(dirs, dst, (size_t)n_vox * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        AMX_CK(cudaStreamSynchronize(s));
+    } else {
+        AMX_CK(cudaStreamSynchronize(s));  // W7 / X are host memory read by asynchronous copies
     }
     return AMX_OK;
 }

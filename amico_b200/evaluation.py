@@ -383,7 +383,8 @@ class Evaluation:
     def DIRs(self):
         return None if self._dirs is None else self._rows_in_reference_order(self._dirs.cpu().numpy())
 
-    def _dti_weights(self):
+    def _dti_tables(self):
+        """(design matrix X (m, 7), its pseudo-inverse (7, m)) of the fit scheme, cached per scheme."""
         sch = self._fit_scheme
         if self.get_config("doMergeB0"):  # core.py:432-433
             bvals = np.hstack((0, sch.b[sch.dwi_idx]))
@@ -391,23 +392,31 @@ class Evaluation:
         else:
             bvals, bvecs = sch.b, sch.raw[:, :3]
         key = (bvals.tobytes(), np.ascontiguousarray(bvecs).tobytes())
-        if getattr(self, "_dti_W_key", None) != key:  # the SVD behind pinv costs milliseconds on the host: once per scheme
-            W = np.linalg.pinv(dti_design_matrix(bvals, bvecs))
-            self._dti_W, self._dti_W_key = np.ascontiguousarray(W[:6], dtype=np.float64), key
-        return self._dti_W
+        if getattr(self, "_dti_key", None) != key:  # the SVD behind pinv costs milliseconds on the host: once per scheme
+            X = np.ascontiguousarray(dti_design_matrix(bvals, bvecs), dtype=np.float64)
+            self._dti_X, self._dti_W, self._dti_key = X, np.ascontiguousarray(np.linalg.pinv(X), dtype=np.float64), key
+        return self._dti_X, self._dti_W
 
     def estimate_directions(self):
-        """Principal directions of every mask voxel (``core.py:456-458``) -> device tensor (n_vox, 3) float64."""
+        """Principal directions of every mask voxel (``core.py:456-458``) -> device tensor (n_vox, 3) float64.
+        ``DTI_fit_method``: 'OLS' / 'LS' (log-linear least squares, the reference's default) or 'WLS' (dipy's weighted
+        variant); 'NLLS', 'RT' / 'RESTORE' (iterative / robust fits, ``core.py:419-429``) are not part of the accelerated path."""
         import torch
-        if self.get_config("DTI_fit_method") not in ("OLS", "LS"):
-            raise NotImplementedError("only the default DTI fit method 'OLS' ('LS') runs on the GPU")
+        method = self.get_config("DTI_fit_method")
+        if method not in ("OLS", "LS", "WLS"):
+            raise NotImplementedError(f"DTI fit method {method!r}: only 'OLS' ('LS') and 'WLS' run on the GPU")
         n_vox, m = self._y.shape
         dirs = torch.empty((n_vox, 3), dtype=torch.float64, device=self._y.device)
-        W = self._dti_weights()
+        X, W = self._dti_tables()
         stream = torch.cuda.current_stream(self._y.device).cuda_stream
-        L.check(L.load().amx_dti_directions(self.device, L.SPACE_DEVICE, self._y.data_ptr(), L.F32, n_vox, m, W.ctypes.data,
-                                            MIN_POSITIVE_SIGNAL, dirs.data_ptr(), stream))
-        torch.cuda.current_stream(self._y.device).synchronize()  # W is host memory read by an async copy
+        if method == "WLS":
+            L.check(L.load().amx_dti_directions_wls(self.device, L.SPACE_DEVICE, self._y.data_ptr(), L.F32, n_vox, m, W.ctypes.data,
+                                                    X.ctypes.data, MIN_POSITIVE_SIGNAL, dirs.data_ptr(), stream))
+        else:
+            W6 = np.ascontiguousarray(W[:6])
+            L.check(L.load().amx_dti_directions(self.device, L.SPACE_DEVICE, self._y.data_ptr(), L.F32, n_vox, m, W6.ctypes.data,
+                                                MIN_POSITIVE_SIGNAL, dirs.data_ptr(), stream))
+        torch.cuda.current_stream(self._y.device).synchronize()  # the tables are host memory read by an async copy
         self._dirs = dirs
         return dirs
 

@@ -210,6 +210,12 @@ int amx_mean_b0(int space, int device, const float *dwi, int64_t n_total, int nS
 int amx_dti_directions(int device, int space, const void *y, int y_dtype, int64_t n_vox, int m, const double *W,
                        double min_signal, double *dirs, void *stream);
 
+/* The same with `fit_method='WLS'` (amico/core.py:95, 419, 436 -> dipy wls_fit_tensor): weights w = exp(X beta_ols), then the
+ * weighted least-squares tensor min || diag(w) (X beta - log max(y, min_signal)) ||.
+ * W7: HOST float64 [7][m] = pinv(design matrix) (all seven rows); X: HOST float64 [m][7] = the design matrix itself. */
+int amx_dti_directions_wls(int device, int space, const void *y, int y_dtype, int64_t n_vox, int m, const double *W7,
+                           const double *X, double min_signal, double *dirs, void *stream);
+
 /* RESULTS['MAPs'][mask==1, :] = estimates (amico/core.py:472-498): zero-fill volume [n_total][k] (float32) and
  * scatter the float64 rows values[i][0..k) to voxel vox_idx[i]. */
 int amx_scatter_maps(int device, int space, const double *values, int64_t n_vox, int k, const int32_t *vox_idx,

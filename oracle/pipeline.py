@@ -118,12 +118,24 @@ def scheme_gradients(scheme, doMergeB0=False):
     return scheme.b, scheme.raw[:, :3]
 
 
-def dti_directions(y, scheme, doMergeB0=False):
-    """Principal eigenvector of the OLS tensor fit per voxel: (n_vox, 3) float64 (sign arbitrary)."""
+def dti_directions(y, scheme, doMergeB0=False, method="OLS"):
+    """Principal eigenvector of the tensor fit per voxel: (n_vox, 3) float64 (sign arbitrary).  ``method``: 'OLS' (dipy
+    ``ols_fit_tensor``: pinv(X) log s) or 'WLS' (dipy ``wls_fit_tensor``: w = exp(U U^T log s) with U from the thin SVD of X, then
+    pinv(X * w[:, None]) (w * log s)), both restated from the published dipy.reconst.dti (dipy is absent: unpinned)."""
     bvals, bvecs = scheme_gradients(scheme, doMergeB0)
-    W = np.linalg.pinv(dti_design_matrix(bvals, bvecs))
+    X = dti_design_matrix(bvals, bvecs)
     data = np.maximum(np.asarray(y, dtype=np.float64), MIN_POSITIVE_SIGNAL)
-    D = np.einsum("ij,nj->ni", W, np.log(data))
+    log_s = np.log(data)
+    if method == "OLS":
+        D = np.einsum("ij,nj->ni", np.linalg.pinv(X), log_s)
+    elif method == "WLS":
+        U = np.linalg.svd(X, full_matrices=False)[0]
+        w = np.exp(np.einsum("ij,nj->ni", U @ U.T, log_s))
+        D = np.empty((len(log_s), 7))
+        for i in range(len(log_s)):
+            D[i] = np.linalg.pinv(X * w[i][:, None]) @ (w[i] * log_s[i])
+    else:
+        raise ValueError(method)
     T = np.empty((len(D), 3, 3))
     T[:, 0, 0], T[:, 0, 1], T[:, 1, 1], T[:, 0, 2], T[:, 1, 2], T[:, 2, 2] = (D[:, k] for k in range(6))
     T[:, 1, 0], T[:, 2, 0], T[:, 2, 1] = T[:, 0, 1], T[:, 0, 2], T[:, 1, 2]

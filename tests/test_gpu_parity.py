@@ -288,6 +288,26 @@ def test_single_b0_scheme_rows():
     assert pass_fraction(got["estimates"], ref["estimates"]) >= 0.9999
 
 
+@pytest.mark.parametrize("n_vf,n_od,bar", [(4, 3, 0.9999), (8, 6, 0.9999), (12, 12, 0.9999), (15, 14, 0.995)])
+def test_noddi_custom_grids(n_vf, n_od, bar):
+    """NODDI with user grids (model.set(IC_VFs=, IC_ODs=), amico/models.pyx:677-681): 13, 49 and 145 atoms run as stage kernels
+    with 1, 2 and 5 atoms per lane; 211 atoms (> 160) take the per-voxel kernel, whose NNLS has no A-space re-evaluation of
+    near-dependent candidates -- hence its lower bar."""
+    scheme = synth.make_scheme(2)
+    lut = synth.lut_directions(500)
+    ht = synth.build_htable(lut)
+    params = dict(IC_VFs=np.linspace(0.1, 0.99, n_vf), IC_ODs=np.linspace(0.03, 0.99, n_od))
+    K, p = synth.make_kernels("NODDI", scheme, lut, params)
+    y, dirs = synth.make_voxels("NODDI", K, ht, 3000, 99 + n_vf)
+    P = synth.Problem(0, "NODDI", scheme, lut, ht, K, p, y, dirs)
+    ref = orc().fit_problem(P, nthreads=os.cpu_count(), return_debug=True)
+    got = gpu_fit(P, debug=True)
+    assert got["_counters"]["overflow_voxels"] == 0
+    frac = pass_fraction(got["estimates"], ref["estimates"])
+    print(f"NODDI {n_vf * n_od + 1} atoms: pass fraction {frac:.5f}, support equality {float((got['support'] == ref['support']).mean()):.5f}")
+    assert frac >= bar
+
+
 def test_device_tensor_path_matches_host_path():
     import torch
     P = synth.make_problem(2, n_vox=5000, seed=21)

@@ -132,3 +132,20 @@ def test_resample_oracle_exact_vs_float32_statement():
     b = opl.resample_kernel_exact(lm, sch.nS, idx_out, Ylm, False, 6)
     assert a.dtype == np.float32 and (a[:, sch.b0_idx] == 1).all()
     np.testing.assert_allclose(a, b, atol=2e-6)
+
+
+def test_oracle_dti_wls_sanity():
+    """The WLS restatement: on a noise-free single-tensor signal both fits return the generating direction; with noise they differ."""
+    sch = synth.make_scheme(2)
+    b, g = sch.b, sch.raw[:, :3]
+    e = np.array([0.6, 0.48, 0.64])
+    D = 0.3e-3 * np.eye(3) + 1.4e-3 * np.outer(e, e)
+    s = np.exp(-b * np.einsum("ij,jk,ik->i", g, D, g))[None, :]
+    for method in ("OLS", "WLS"):
+        d = opl.dti_directions(s, sch, method=method)[0]
+        assert abs(abs(d @ e) - 1.0) < 1e-10, method
+    rng = np.random.default_rng(0)
+    noisy = np.abs(s + 0.05 * rng.standard_normal((50, len(b))))
+    a, w = opl.dti_directions(noisy, sch, method="OLS"), opl.dti_directions(noisy, sch, method="WLS")
+    assert (1.0 - np.abs((a * w).sum(1))).max() > 1e-6
+    assert (np.abs((w * e).sum(1)) > 0.9).all()
