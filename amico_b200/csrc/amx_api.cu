@@ -827,7 +827,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         // the launch is unconditional and returns at once when the queue is empty
         const int cap = std::min(pl->m, pl->n) + 2;
         const size_t wsb = slow_ws_bytes(cap, p.NA);
-        const int slow_threads = pl->sm_count * 16;
+        const int slow_threads = pl->sm_count * std::max(1, env_int("AMX_SLOW_WARPS_PER_SM", 2)) * 32;  // one voxel per thread, ~100-200 KB of workspace each
         CK(wk.slow_ws.reserve(wsb * slow_threads));
         k_slow_noddi<float><<<slow_threads / 32, 32, 0, st>>>(p, p.ovf_list, status, (unsigned char *)wk.slow_ws.p, wsb, cap);
         CK(cudaGetLastError());
