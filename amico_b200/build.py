@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libamico_b200.so")
 SOURCES = ["amx_api.cu", "amx_pre.cu"]
-HEADERS = ["amx_err.h", "amx_warp.cuh", "amx_solvers.cuh", "amx_kernels.cuh", "amx_slow.cuh", os.path.join("..", "..", "include", "amico_b200.h")]
+HEADERS = ["amx_err.h", "amx_warp.cuh", "amx_solvers.cuh", "amx_kernels.cuh", "amx_lean.cuh", "amx_slow.cuh", "amx_exact.cuh", "amx_small.cuh", os.path.join("..", "..", "include", "amico_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "--threads", "2"]
 

@@ -1,6 +1,7 @@
 // C ABI of the B200-native per-voxel fit (see include/amico_b200.h).
 #include "../../include/amico_b200.h"
 #include "amx_kernels.cuh"
+#include "amx_lean.cuh"
 #include "amx_slow.cuh"
 #include "amx_exact.cuh"
 #include "amx_small.cuh"
@@ -166,7 +167,7 @@ struct amx_plan {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // [0] pre-LUT [1] post-binning [2] post-fit [3] start [4] end
     // workspace
     // per-launch workspace; two sets so that consecutive voxel chunks can be in flight on two compute streams
-    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws, exact_list, exact_a, c1_all; } work[2];
+    struct Work { DevBuf lut, order, bins, tiles, status, scratch, xiso, supmask, ovf_list, slow_ws, exact_list, exact_a, c1_all, redo; } work[2];
     cudaStream_t cs[2] = {nullptr, nullptr};          // [0] == stream
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     struct Stage { DevBuf y, dirs, est, rmse, nrmse, extra, sup, coef, lut; } stg[2];  // host-path staging, double buffered
@@ -311,7 +312,7 @@ int amx_plan_destroy(amx_plan *pl)
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto &wk : pl->work) {
         DevBuf *bufs[] = {&wk.lut, &wk.order, &wk.bins, &wk.tiles, &wk.status, &wk.scratch, &wk.xiso, &wk.supmask, &wk.ovf_list, &wk.slow_ws,
-                          &wk.exact_list, &wk.exact_a, &wk.c1_all};
+                          &wk.exact_list, &wk.exact_a, &wk.c1_all, &wk.redo};
         for (DevBuf *b : bufs) b->release();
     }
     for (void *h : pl->hpin) if (h) cudaFreeHost(h);
@@ -492,7 +493,38 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     // 1024 threads (64 registers, a few spilled words); more resident warps hide the L2 latency of the Gram rows.
     const int w1 = env_int("AMX_STAGE1_WARPS", 32);
     const size_t s1w = fixed + (size_t)p.ws_doubles_stage[0] * 8 * 32;
-    if (MAXT == 768 && block == 768 && w1 == 32 && s1w <= 227 * 1024) {
+    // stage 1 with two voxels per warp (amx_lean.cuh: half-warp per voxel, passive sets <= 16)
+    const bool pair1 = env_int("AMX_PAIR1", 0) && MAXT == 768 && block == 768 && p.cap_stage[0] <= 16;
+    const bool lean1 = env_int("AMX_LEAN1", 1) && MAXT == 768 && block == 768 && p.cap_stage[0] <= 16;
+    if (pair1) {
+        const int warps = (w1 == 24 || w1 == 28) ? w1 : 32;
+        const size_t sw = fixed + (size_t)(2 * (PairWS<16>::CS + 16 * 2 * NPL) + BV) * 8 * warps;
+        auto launch_pair = [&](auto kern) -> int {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (sw * 100 + 233471) / 233472 + 1)));
+            kern<<<grid, warps * 32, sw, st>>>(p);
+            return AMX_OK;
+        };
+        int rc;
+        if (warps == 32) rc = launch_pair(k_noddi_stage1_pair<2 * NPL, 1024, 16>);
+        else if (warps == 28) rc = launch_pair(k_noddi_stage1_pair<2 * NPL, 896, 16>);
+        else rc = launch_pair(k_noddi_stage1_pair<2 * NPL, 768, 16>);
+        if (rc) return rc;
+    } else if (lean1) {  // one voxel per warp, lean solver (same arithmetic as k_noddi_stage<1>, fewer instructions)
+        const int warps = (w1 == 24 || w1 == 28) ? w1 : 32;
+        const size_t sw = fixed + (size_t)(LeanWS<16>::SIZE + 32 * NPL) * 8 * warps;
+        auto launch_lean = [&](auto kern) -> int {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (sw * 100 + 233471) / 233472 + 1)));
+            kern<<<grid, warps * 32, sw, st>>>(p);
+            return AMX_OK;
+        };
+        int rc;
+        if (warps == 32) rc = launch_lean(k_noddi_stage1_lean<NPL, 1024, 16>);
+        else if (warps == 28) rc = launch_lean(k_noddi_stage1_lean<NPL, 896, 16>);
+        else rc = launch_lean(k_noddi_stage1_lean<NPL, 768, 16>);
+        if (rc) return rc;
+    } else if (MAXT == 768 && block == 768 && w1 == 32 && s1w <= 227 * 1024) {
         auto k1w = k_noddi_stage<1, NPL, float, 1024>;
         CK(cudaFuncSetAttribute(k1w, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1w));
         CK(cudaFuncSetAttribute(k1w, cudaFuncAttributePreferredSharedMemoryCarveout, (int)std::min<size_t>(100, (s1w * 100 + 233471) / 233472 + 1)));
@@ -515,8 +547,25 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     if (wide_ok && w2 == 32 && fits(32, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 1024>, 32, p.ws_doubles_stage[1]);
     else k2<<<grid, block, s2, st>>>(p);
     if (rc) return rc;
-    if (wide_ok && w3 == 32 && fits(32, p.ws_doubles_stage[2])) rc = launch_wide(k_noddi_stage<3, NPL, float, 1024>, 32, p.ws_doubles_stage[2]);
-    else k3<<<grid, block, s3, st>>>(p);
+    const bool tpv3 = p.tpv3 != 0;
+    FitParams p3 = p;
+    if (tpv3) {
+        // one voxel per thread (amx_lean.cuh); what it hands back runs through the warp-per-voxel kernel as one-voxel tiles
+        auto kt = k_noddi_stage3_tpv<NPL, 6>;
+        constexpr int smem_t = tpv_smem_bytes<6>();
+        CK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+        const long long blocks = std::max<long long>(1, std::min<long long>((p.n_vox + TPV_THREADS - 1) / TPV_THREADS, (long long)grid * 64));
+        kt<<<(int)blocks, TPV_THREADS, smem_t, st>>>(p, p.redo_tiles, p.redo_count);
+        p3.tiles = p.redo_tiles;
+        p3.n_tiles_ptr = p.redo_count;
+        p3.tile_counter = p.redo_count + 1 - 2;  // stage 3 pulls from tile_counter[2]
+    }
+    if (wide_ok && w3 == 32 && fits(32, p.ws_doubles_stage[2])) {
+        const size_t sw = fixed + (size_t)p.ws_doubles_stage[2] * 8 * 32;
+        auto kern = k_noddi_stage<3, NPL, float, 1024>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+        kern<<<grid, 1024, sw, st>>>(p3);
+    } else k3<<<grid, block, s3, st>>>(p3);
     if (rc) return rc;
     CK(cudaGetLastError());
     return AMX_OK;
@@ -765,12 +814,18 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
         CK(wk.supmask.reserve((size_t)n_vox * 8 * sizeof(unsigned)));
         p.xiso = (double *)wk.xiso.p;
         p.supmask = (unsigned *)wk.supmask.p;
+        // stage 3, one voxel per thread: voxels it hands back (passive set > 6 atoms, support > 32) as one-voxel tiles + 2 counters
+        CK(wk.redo.reserve((size_t)n_vox * sizeof(int4) + 16));
+        p.redo_count = (int *)wk.redo.p;
+        p.redo_tiles = (int4 *)((char *)wk.redo.p + 16);
+        CK(cudaMemsetAsync(p.redo_count, 0, 16, st));
         // stage 1's c1 = A^T y kept per voxel for stage 3 when it fits the budget (AMX_C1_STORE_MB, default 4096 MB)
         const size_t c1_bytes = (size_t)n_vox * p.NA * sizeof(double);
         if (c1_bytes <= (size_t)std::max(0, env_int("AMX_C1_STORE_MB", 4096)) * 1048576) {
             CK(wk.c1_all.reserve(c1_bytes));
             p.c1_all = (double *)wk.c1_all.p;
         }
+        p.tpv3 = env_int("AMX_TPV3", 1) && p.c1_all && !p.coeff_out && !(p.flags & (FLAG_RMSE | FLAG_NRMSE)) && p.n <= 255;
         p.ovf_cap = 4 * n_vox;
         CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
         p.ovf_list = (int *)wk.ovf_list.p;
@@ -803,7 +858,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     default: rc = dispatch_npl<MODEL_SANDI, double>(pl->npl, p, grid, nwarps * 32, smem, st); break;
     }
     if (rc) return rc;
-    *launches += (p.batched == 2) ? 3 : 1;
+    *launches += (p.batched == 2) ? 3 + p.tpv3 : 1;
     if (p.batched == 2 && p.exact_tol > 0.0) {
         // exact-fit voxels queued by stage 1 are re-fitted from scratch by the reference's own algorithm (A-space Lawson-Hanson
         // with Householder QR, amx_exact.cuh); unconditional launch, returns at once when the queue is empty

@@ -267,6 +267,9 @@ struct FitParams {
     int *exact_list;     // NODDI: exact-fit voxels queued by stage 1 for the A-space QR path (amx_exact.cuh); status[4] counts them
     long long exact_cap;
     double exact_tol;    // ... when ||y - Ax||^2 < exact_tol ||y||^2
+    int4 *redo_tiles;    // NODDI stage 3 (thread per voxel): voxels handed back to the warp-per-voxel kernel as one-voxel tiles
+    int *redo_count;     // [0] their number, [1] the queue head the second pass pulls from
+    int tpv3;            // stage 3 runs as k_noddi_stage3_tpv + a second pass over redo_tiles
 };
 
 struct WarpWS {

@@ -15,6 +15,9 @@
 #define AMX_GD 2  // Gram rows fetched per batch (measured at 64-80 registers: 1 -> 39.6 ms, 2 -> 37.7, 3 -> 39.1, 4 -> 38.9) in the NODDI solvers' O(n |P|) passes (NPL > 2)
 #endif
 #include <math.h>
+#ifndef AMX_SOLVER_INLINE
+#define AMX_SOLVER_INLINE __noinline__
+#endif
 
 namespace amx {
 
@@ -119,7 +122,7 @@ __device__ __forceinline__ void chol_delete(double *Lp, int q, int pn, double &r
 // atoms, so the dual pass touches one Gram entry per lane and row instead of NPL.
 // zz_out (optional): ||z||^2 = ||A x||^2 of the final passive system.
 template <int NPL, bool MAPPED = false>
-__device__ __noinline__ int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
+__device__ AMX_SOLVER_INLINE int warp_nnls(const double *__restrict__ T, int ldT, int n, int mcap, int itmax, const double *c, double *x,
                          unsigned allowed, double *Lp, double *, int *P, int lane, NnlsStat *st, int cap = LC,
                          const int *map = nullptr, const ASpace *as = nullptr, double *zz_out = nullptr)
 {

@@ -1,21 +1,14 @@
 set -x
 mkdir -p gpurun_out
-python bench.py > gpurun_out/bench_r02.json 2> gpurun_out/bench_r02.err; tail -3 gpurun_out/bench_r02.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_r02_reference.json 2>> gpurun_out/bench_r02.err
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-configs > gpurun_out/launches_bench.log 2>&1
-T=/tmp/ncu; mkdir -p $T
-ncu --set full --clock-control none --import-source on -k regex:k_noddi_stage -s 9 -c 3 -o $T/full_stage_r02 -f python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-pipeline --no-configs > gpurun_out/full_stage.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_lasso_batched -s 2 -c 1 -o $T/full_lasso_czb_r02 -f python tools/bench_models.py 1048576 CylinderZeppelinBall5 > gpurun_out/full_czb.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_lasso_small -s 2 -c 1 -o $T/full_lasso_sandi_r02 -f python tools/bench_models.py 1048576 SANDI4 > gpurun_out/full_sandi.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_lasso_batched -s 2 -c 1 -o $T/full_lasso_fw_r02 -f python tools/bench_models.py 1048576 FreeWater1 > gpurun_out/full_fw.log 2>&1
-python tools/ncu_to_json.py $T/full_stage_r02.ncu-rep "ncu --set full --clock-control none --import-source on -k regex:k_noddi_stage -s 9 -c 3 python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e --no-pipeline --no-configs" 1048576 > gpurun_out/ncu_full_r02_noddi_stage_kernels.json
-python tools/ncu_to_json.py $T/full_lasso_czb_r02.ncu-rep "ncu --set full --clock-control none --import-source on -k regex:k_lasso_batched -s 2 -c 1 python tools/bench_models.py 1048576 CylinderZeppelinBall5" 1048576 > gpurun_out/ncu_full_r02_k_lasso_batched_czb.json
-python tools/ncu_to_json.py $T/full_lasso_sandi_r02.ncu-rep "ncu --set full --clock-control none --import-source on -k regex:k_lasso_small -s 2 -c 1 python tools/bench_models.py 1048576 SANDI4" 1048576 > gpurun_out/ncu_full_r02_k_lasso_small_sandi.json
-python tools/ncu_to_json.py $T/full_lasso_fw_r02.ncu-rep "ncu --set full --clock-control none --import-source on -k regex:k_lasso_batched -s 2 -c 1 python tools/bench_models.py 1048576 FreeWater1" 1048576 > gpurun_out/ncu_full_r02_k_lasso_batched_freewater.json
-ncu -i $T/full_stage_r02.ncu-rep --page source --csv --print-source cuda,sass > $T/src.csv 2>/dev/null
-python tools/ncu_src_lines.py $T/src.csv 60 > gpurun_out/ncu_r02_noddi_stage_by_line.txt
-cp $T/full_stage_r02.ncu-rep gpurun_out/
-python tools/bench_models.py 1048576 > gpurun_out/bench_models_r02.log 2>&1; cp gpurun_out/bench_models.json gpurun_out/bench_models_r02.json
-python tools/parity_at_scale.py 262144 2 > gpurun_out/parity_r02_cfg2.json 2>/dev/null
-python tools/parity_at_scale.py 65536 3 > gpurun_out/parity_r02_cfg3.json 2>/dev/null
-du -sh gpurun_out
+python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "noddi" > gpurun_out/h6_tests.log 2>&1; tail -5 gpurun_out/h6_tests.log
+bash tools/bench_sweep.sh "AMX_TPV3=0" "AMX_TPV3=1" > gpurun_out/h6_sweep.log 2>&1
+cat gpurun_out/h6_sweep.log
+for L in 0 1; do
+AMX_TPV3=$L python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-pipeline --no-configs 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('checksum', repr(d['maps_checksum']))"
+done
+ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active -k regex:k_noddi_stage -c 4 --csv --log-file gpurun_out/h6_stage.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-pipeline --no-configs > /dev/null 2>&1
+python - <<'P'
+import csv
+for r in csv.reader(open('gpurun_out/h6_stage.csv')):
+    if len(r)>10 and r[0].isdigit(): print(r[4][:50], r[7], r[-3], r[-1])
+P
