@@ -493,9 +493,32 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     // 1024 threads (64 registers, a few spilled words); more resident warps hide the L2 latency of the Gram rows.
     const int w1 = env_int("AMX_STAGE1_WARPS", 32);
     const size_t s1w = fixed + (size_t)p.ws_doubles_stage[0] * 8 * 32;
-    // stage 1 with two voxels per warp (amx_lean.cuh: half-warp per voxel, passive sets <= 16)
     const bool pair1 = env_int("AMX_PAIR1", 0) && MAXT == 768 && block == 768 && p.cap_stage[0] <= 16;
     const bool lean1 = env_int("AMX_LEAN1", 1) && MAXT == 768 && block == 768 && p.cap_stage[0] <= 16;
+    // stage 1 with one voxel per thread and warp-cooperative dual passes (amx_lean.cuh); voxels it hands back (passive set > CAPT)
+    // run through the warp-per-voxel lean kernel as one-voxel tiles
+    if (p.tpv1) {
+        const int capt = env_int("AMX_TPV1_CAP", 8);
+        auto launch_tpv = [&](auto kern, int smem_t) -> int {
+            CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+            const int ctas = std::max(1, std::min(env_int("AMX_TPV1_CTAS", 4), (int)(232448 / (smem_t + 1024))));
+            kern<<<grid * ctas, TPV_THREADS, smem_t, st>>>(p, p.redo_tiles, p.redo_count);
+            return AMX_OK;
+        };
+        int rc = capt <= 6   ? launch_tpv(k_noddi_stage1_tpv<NPL, 6>, tpv1_smem_bytes<NPL, 6>())
+                 : capt == 7 ? launch_tpv(k_noddi_stage1_tpv<NPL, 7>, tpv1_smem_bytes<NPL, 7>())
+                             : launch_tpv(k_noddi_stage1_tpv<NPL, 8>, tpv1_smem_bytes<NPL, 8>());
+        if (rc) return rc;
+        FitParams p1 = p;
+        p1.tiles = p.redo_tiles;
+        p1.n_tiles_ptr = p.redo_count;
+        p1.tile_counter = p.redo_count + 1;
+        const int warps = 32;
+        const size_t sw = fixed + (size_t)(LeanWS<16>::SIZE + 32 * NPL) * 8 * warps;
+        auto kern = k_noddi_stage1_lean<NPL, 1024, 16>;
+        CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
+        kern<<<grid, warps * 32, sw, st>>>(p1);
+    } else
     if (pair1) {
         const int warps = (w1 == 24 || w1 == 28) ? w1 : 32;
         const size_t sw = fixed + (size_t)(2 * (PairWS<16>::CS + 16 * 2 * NPL) + BV) * 8 * warps;
@@ -534,7 +557,7 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     }
     // Stages 2 and 3: more resident warps hide more of the L2 latency of the Gram rows as long as registers (64K / threads)
     // and shared memory (workspace x warps <= 227 KB) allow; the 1024-thread builds spill ~150 bytes.
-    const int w2 = env_int("AMX_STAGE2_WARPS", 32), w3 = env_int("AMX_STAGE3_WARPS", 24);
+    const int w2 = env_int("AMX_STAGE2_WARPS", 28), w3 = env_int("AMX_STAGE3_WARPS", 24);
     auto launch_wide = [&](auto kern, int warps, unsigned ws_doubles) -> int {
         const size_t sw = fixed + (size_t)ws_doubles * 8 * warps;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
@@ -544,7 +567,12 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     const bool wide_ok = MAXT == 768 && block == 768;
     auto fits = [&](int warps, unsigned ws_doubles) { return fixed + (size_t)ws_doubles * 8 * warps <= (size_t)227 * 1024; };
     int rc = AMX_OK;
-    if (wide_ok && w2 == 32 && fits(32, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 1024>, 32, p.ws_doubles_stage[1]);
+    if (env_int("AMX_LEAN2", 1) && p.fast_lars && wide_ok && p.NA == 32 * NPL) {  // inlined stage-2 solver (amx_lean.cuh), own workspace layout
+        const unsigned wsd = Lars2WS<NPL>::SIZE;
+        if (w2 == 24) rc = launch_wide(k_noddi_stage2_lean<NPL, 768>, 24, wsd);
+        else if (w2 == 32 && fits(32, wsd)) rc = launch_wide(k_noddi_stage2_lean<NPL, 1024>, 32, wsd);
+        else rc = launch_wide(k_noddi_stage2_lean<NPL, 896>, 28, wsd);
+    } else if (wide_ok && w2 == 32 && fits(32, p.ws_doubles_stage[1])) rc = launch_wide(k_noddi_stage<2, NPL, float, 1024>, 32, p.ws_doubles_stage[1]);
     else k2<<<grid, block, s2, st>>>(p);
     if (rc) return rc;
     const bool tpv3 = p.tpv3 != 0;
@@ -552,13 +580,13 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     if (tpv3) {
         // one voxel per thread (amx_lean.cuh); what it hands back runs through the warp-per-voxel kernel as one-voxel tiles
         auto kt = k_noddi_stage3_tpv<NPL, 6>;
-        constexpr int smem_t = tpv_smem_bytes<6>();
+        constexpr int smem_t = tpv3_smem_bytes<6>();
         CK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
         const long long blocks = std::max<long long>(1, std::min<long long>((p.n_vox + TPV_THREADS - 1) / TPV_THREADS, (long long)grid * 64));
-        kt<<<(int)blocks, TPV_THREADS, smem_t, st>>>(p, p.redo_tiles, p.redo_count);
+        kt<<<(int)blocks, TPV_THREADS, smem_t, st>>>(p, p.redo_tiles, p.redo_count + 2);
         p3.tiles = p.redo_tiles;
-        p3.n_tiles_ptr = p.redo_count;
-        p3.tile_counter = p.redo_count + 1 - 2;  // stage 3 pulls from tile_counter[2]
+        p3.n_tiles_ptr = p.redo_count + 2;
+        p3.tile_counter = p.redo_count + 3 - 2;  // stage 3 pulls from tile_counter[2]
     }
     if (wide_ok && w3 == 32 && fits(32, p.ws_doubles_stage[2])) {
         const size_t sw = fixed + (size_t)p.ws_doubles_stage[2] * 8 * 32;
@@ -826,6 +854,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
             p.c1_all = (double *)wk.c1_all.p;
         }
         p.tpv3 = env_int("AMX_TPV3", 1) && p.c1_all && !p.coeff_out && !(p.flags & (FLAG_RMSE | FLAG_NRMSE)) && p.n <= 255;
+        p.tpv1 = env_int("AMX_TPV1", 0) && p.c1_all && p.cap_stage[0] <= 16 && p.n <= 255;
         p.ovf_cap = 4 * n_vox;
         CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));
         p.ovf_list = (int *)wk.ovf_list.p;
@@ -858,7 +887,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
     default: rc = dispatch_npl<MODEL_SANDI, double>(pl->npl, p, grid, nwarps * 32, smem, st); break;
     }
     if (rc) return rc;
-    *launches += (p.batched == 2) ? 3 + p.tpv3 : 1;
+    *launches += (p.batched == 2) ? 3 + p.tpv3 + p.tpv1 : 1;
     if (p.batched == 2 && p.exact_tol > 0.0) {
         // exact-fit voxels queued by stage 1 are re-fitted from scratch by the reference's own algorithm (A-space Lawson-Hanson
         // with Householder QR, amx_exact.cuh); unconditional launch, returns at once when the queue is empty

@@ -268,8 +268,9 @@ struct FitParams {
     long long exact_cap;
     double exact_tol;    // ... when ||y - Ax||^2 < exact_tol ||y||^2
     int4 *redo_tiles;    // NODDI stage 3 (thread per voxel): voxels handed back to the warp-per-voxel kernel as one-voxel tiles
-    int *redo_count;     // [0] their number, [1] the queue head the second pass pulls from
+    int *redo_count;     // stage 1: [0] their number, [1] the queue head the second pass pulls from; stage 3: [2], [3]
     int tpv3;            // stage 3 runs as k_noddi_stage3_tpv + a second pass over redo_tiles
+    int tpv1;            // stage 1 runs as k_noddi_stage1_tpv + a second pass over redo_tiles
 };
 
 struct WarpWS {

@@ -248,8 +248,11 @@ template <int NPL, int MAXT, int CAP>
 __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage1_lean(const FitParams p)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double *wsb = (double *)(smem + p.ws_smem_off) + warp * (LeanWS<CAP>::SIZE + 32 * NPL);
+    int lane = threadIdx.x & 31;
+    unsigned wso = p.ws_smem_off + (threadIdx.x >> 5) * ((LeanWS<CAP>::SIZE + 32 * NPL) * 8);
+    asm volatile("" : "+r"(lane), "+r"(wso));  // opaque: kept in registers instead of being re-derived from %tid at every use
+    const int warp = threadIdx.x >> 5;
+    double *wsb = (double *)(smem + wso);
     double *Lp = wsb + LeanWS<CAP>::LP, *xs = wsb + LeanWS<CAP>::XS, *bx = wsb + LeanWS<CAP>::BX, *cs = wsb + LeanWS<CAP>::CS;
     int *P = (int *)(wsb + LeanWS<CAP>::PI);
     constexpr int NT = 4 * NPL, TP = (MAXT > 512 && NT % 2 == 0) ? NT / 2 : NT;
@@ -701,39 +704,541 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage1_pair(const FitParams p
     }
 }
 
-// ================================================================================================
-// NODDI stage 3 (debias on the support, amico/models.pyx:929-942 + maps :945-979), ONE VOXEL PER THREAD.
-// The system is tiny -- ~11 support atoms, never more than 6 passive ones on the default grids -- and a warp solving one
-// such voxel spends ~4.4 k instructions mostly on cross-lane glue.  Here every thread runs the complete Lawson-Hanson
-// iteration of warp_nnls<1, MAPPED> for its own voxel: same pivoting rules and the same floating-point operations in the same
-// order (column-oriented substitutions, the butterfly trees of the two short sums written out for <= 8 terms, the same Givens
-// downdates), so the coefficients are bit-identical.  Voxels are taken in LUT-direction order: the threads of a warp read the
-// same Gram table / dictionary slab (L1 broadcast).  The one long step, the A-space re-evaluation of a near-dependent candidate
-// (m x |P| products), is served COOPERATIVELY: the warp collects the requesting threads by ballot and evaluates one request
-// at a time with all 32 lanes, rows strided over the lanes exactly as warp_nnls does it.
-// A voxel whose passive set would outgrow CAPT (or whose support exceeds 32 atoms) is appended to `redo` as a one-voxel
-// tile and re-fitted by k_noddi_stage<3>.  Per-thread state lives in shared memory as [index][thread].
-constexpr int TPV_THREADS = 128;
-template <int CAPT>
-__host__ __device__ constexpr int tpv_smem_bytes()
+// ------------------------------------------------------------------------------------------------
+// NODDI stage 2 (support selection, amico/models.pyx:918-936) on an inlined copy of warp_lars_fast: same path, same rules,
+// same arithmetic (identical support words), with what the stage-1 rewrite taught -- no call ABI around the Gram-row loads
+// (the __noinline__ solver re-materialised its global-memory descriptor before every load), 32-bit offsets, 64-bit
+// shuffles without the register swaps, no coefficient vector.
+template <int NPL>
+struct Lars2WS {  // per-warp workspace of stage 2 (doubles), active-set capacity LC
+    static constexpr int DTR = 0, MI = 32 * NPL, U = MI + LC * (LC + 1) / 2, GS = U + LC, IND = GS + LC, BX = IND + LC / 2, SIZE = BX + BV;
+};
+
+template <int NPL>
+__device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int ldT, const int K, const int Ltrue, const double lambda1, double *wsb,
+                                         double normX, const int lane, int cap, unsigned (&sup)[NPL])
 {
-    return TPV_THREADS * ((CAPT * (CAPT + 1) / 2 + 4 * CAPT) * 8 + CAPT * 4 + 32);
+    // one base, compile-time offsets (a struct of pointers was re-materialised from the kernel parameters at every use at 64 registers)
+    double *DtR = wsb + Lars2WS<NPL>::DTR, *Mi = wsb + Lars2WS<NPL>::MI, *u = wsb + Lars2WS<NPL>::U, *gs = wsb + Lars2WS<NPL>::GS;
+    int *ind = (int *)(wsb + Lars2WS<NPL>::IND);
+    // Result: sup[s] bit l set <=> atom l + 32 s ends with a positive coefficient (all lanes hold the words).
+    cap = min(cap, c_lc_cap);
+    int L = Ltrue < K ? Ltrue : K;
+    int overflow = 0;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) sup[s] = 0u;
+    if (L <= 0) return 0;
+    int cur;
+    {
+        double bv = 0.0;
+        int bi = -1;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            if (k < K) {
+                double v = DtR[k];
+                if (bi < 0 || v > bv) { bv = v; bi = k; }
+            }
+        }
+        warp_argmax(bv, bi);
+        if (fabs(bv) < lambda1) return 0;
+        cur = bi;
+    }
+    int newAtom = 1, iter = 0, na = 0;
+    double coef_l = 0.0, rs_l = 0.0;  // coefficient / row sum of (G_SS)^-1 of this lane's active position
+    int ind_l = -1;
+    unsigned act = 0;
+    const int length_path = 4 * L;
+#pragma unroll 1
+    for (int i = 0; i < L; ++i) {
+        if (i < 0) break;
+        ++iter;
+        if (newAtom) {
+            if (i >= cap) { overflow = 1; na = i; break; }
+            if (lane == i) { ind_l = cur; coef_l = 0.0; ind[i] = cur; }
+            if ((cur & 31) == lane) act |= 1u << (cur >> 5);
+            __syncwarp();
+            double g = 0.0;
+            if (lane <= i) {
+                g = T[(unsigned)(cur * ldT + ind_l)];
+                gs[lane] = g;
+            }
+            __syncwarp();
+            if (i == 0) {
+                if (lane == 0) Mi[0] = 1.0 / g;
+                rs_l = (lane == 0) ? 1.0 / g : 0.0;
+            } else {
+                double ur = 0.0;
+                if (lane < i) {
+                    ur = sym_row_dot(Mi, lane, i, gs);
+                    u[lane] = ur;
+                }
+                double dot = lane < i ? ur * g : 0.0, usum = lane < i ? ur : 0.0;  // two interleaved butterfly sums
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    dot += shfl2_xor(dot, o);
+                    usum += shfl2_xor(usum, o);
+                }
+                const double schur = 1.0 / (shfl2(g, i) - dot);
+                // row sums of the inverse after the Schur update: old rows += schur u_r (sum(u) - 1), new row = schur (1 - sum(u))
+                if (lane < i) rs_l = fma(schur * ur, usum - 1.0, rs_l);
+                if (lane == i) rs_l = schur * (1.0 - usum);
+                __syncwarp();
+                if (lane < i) {
+                    const double su = schur * ur;
+#pragma unroll 1
+                    for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = fma(su, u[k], Mi[tri(k, lane)]);
+                    Mi[tri(i, lane)] = -su;
+                }
+                if (lane == i) Mi[tri(i, i)] = schur;
+            }
+            __syncwarp();
+        }
+        na = i + 1;
+        // path direction u = invGs * sign(DtR_S)
+        double dl = 0.0, sg = 0.0;
+        if (lane <= i) {
+            dl = DtR[ind_l];
+            sg = dl > 0.0 ? 1.0 : -1.0;
+            gs[lane] = sg;
+        }
+        __syncwarp();
+        // With the positivity constraint every active correlation is positive (never observed otherwise: 0 of 150,000 model voxels),
+        // so u = (G_SS)^-1 1 is the vector of row sums of the inverse, which is carried along in O(1) per lane and step; the
+        // general form stays as the fallback.
+        double ul = 0.0;
+        if (!__any_sync(FULL, lane <= i && !(dl > 0.0))) {
+            if (lane <= i) {
+                ul = rs_l;
+                u[lane] = ul;
+            }
+        } else if (lane <= i) {
+            ul = sym_row_dot(Mi, lane, i + 1, gs);
+            u[lane] = ul;
+        }
+        __syncwarp();
+        // largest step before an active coefficient crosses zero (last index wins ties)
+        double step_max = INFINITY;
+        int fz = -1;
+        if (lane <= i) {
+            double r = -coef_l / ul;
+            if (r > 0.0) { step_max = r; fz = lane; }
+        }
+        warp_argmin<false>(step_max, fz);
+        if (fz < 0) step_max = INFINITY;
+        const double cc = fabs(shfl2(dl, 0));
+        // correlation slopes T[:, S] u; rows are L2-resident: fetch GD rows at a time
+        double sl[NPL];
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
+        constexpr int GD = (NPL <= 2) ? 4 : AMX_GD;
+#pragma unroll 1
+        for (int j0 = 0; j0 <= i; j0 += GD) {
+            double gq[GD][NPL];
+#pragma unroll
+            for (int q = 0; q < GD; ++q) {
+                const double *row = T + (unsigned)(ind[min(j0 + q, i)] * ldT + lane);
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) gq[q][s] = row[32 * s];  // columns >= K: finite values of the next row / the padding,
+                                                                       // only ever combined into slots that are masked by k < K
+            }
+#pragma unroll
+            for (int q = 0; q < GD; ++q) {
+                const double uj = (j0 + q <= i) ? u[j0 + q] : 0.0;
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) sl[s] = fma(gq[q][s], uj, sl[s]);
+            }
+        }
+        // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index.  Each lane first
+        // picks the best of its own atoms by cross-multiplication (|a/b| < |c/d| <=> |a| d < |c| b for b, d > 0), so only one
+        // reciprocal per lane and step is needed.
+        double bnum = 0.0, bden = 0.0;  // best candidate of this lane: step = bnum / bden (bden > 0), none while bden == 0
+        int mk = -1;                    // its atom; lanes without a candidate still offer their lowest atom (step = inf)
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            const int k = lane + 32 * s;
+            if (k < K) {
+                if (mk < 0) mk = k;
+                if (!((act >> s) & 1u) && sl[s] < 1.0) {
+                    const double num = cc - DtR[k], den = 1.0 - sl[s];
+                    if (bden == 0.0 || fabs(num) * bden < fabs(bnum) * den) { bnum = num; bden = den; mk = k; }
+                }
+            }
+        }
+        const double mine = bden != 0.0 ? bnum * __drcp_rn(bden) : INFINITY;
+        double bt = fabs(mine);
+        int bk = mk;
+        warp_argmin<true>(bt, bk);
+        const double step0 = shfl2(mine, bk & 31);  // lane (bk & 31) owns atom bk and offered exactly it
+        double step = step0;
+        cur = bk;
+        double coeff1 = lane <= i ? sg * ul : 0.0, coeff2 = lane <= i ? dl * ul : 0.0;  // two interleaved butterfly sums
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            coeff1 += shfl2_xor(coeff1, o);
+            coeff2 += shfl2_xor(coeff2, o);
+        }
+        const double step_max2 = cc - lambda1;
+        step = fmin(fmin(step, step_max2), step_max);
+        if (step == INFINITY) break;
+        if (lane <= i) {
+            coef_l = fma(step, ul, coef_l);
+            if (coef_l < 0.0) coef_l = 0.0;
+        }
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) {
+            int k = lane + 32 * s;
+            if (k < K) DtR[k] = fma(-step, sl[s], DtR[k]);
+        }
+        normX += coeff1 * step * step - 2.0 * coeff2 * step;
+        __syncwarp();
+        if (step == step_max) {
+            const int z = fz;
+            const int az = ind[z];
+            const double schur_r = Mi[tri(z, z)];
+            double uk = 0.0;
+            if (lane < i) uk = (lane < z) ? Mi[tri(z, lane)] : Mi[tri(lane + 1, z)];
+            __syncwarp();
+            if (lane < i) u[lane] = uk;
+            double cn = shfl2(coef_l, min(lane + 1, 31));
+            int in_ = __shfl_down_sync(FULL, ind_l, 1);
+            const double rn = shfl2(rs_l, min(lane + 1, 31));
+            const double ksum = warp_sum(lane < i ? uk : 0.0);
+            if (lane >= z && lane < i) { coef_l = cn; ind_l = in_; rs_l = rn; }
+            if (lane == i) { coef_l = 0.0; ind_l = -1; rs_l = 0.0; }
+            if (lane < i) rs_l = rs_l - uk - uk * ksum / schur_r;  // row sums: without column z, then the rank-1 downdate
+            if ((az & 31) == lane) act &= ~(1u << (az >> 5));
+#pragma unroll 1
+            for (int j = z; j < i; ++j) {
+                double mv = 0.0;
+                if (lane <= j) mv = Mi[tri(j + 1, lane < z ? lane : lane + 1)];
+                __syncwarp();
+                if (lane <= j) Mi[tri(j, lane)] = mv;
+                __syncwarp();
+            }
+            if (lane <= i) ind[lane] = ind_l;
+            __syncwarp();
+            if (lane < i) {
+                const double ir = uk / schur_r;
+#pragma unroll 1
+                for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = fma(-ir, u[k], Mi[tri(k, lane)]);
+            }
+            __syncwarp();
+            newAtom = 0;
+            na = i;
+            i -= 2;
+        } else {
+            newAtom = 1;
+        }
+        if (iter >= length_path - 1 || fabs(step) < 1e-15 || step == step_max2 || normX < 1e-15 || i == L - 1) break;
+    }
+    {
+        const bool on = lane < na && ind_l >= 0 && coef_l > 0.0;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) sup[s] = __reduce_or_sync(FULL, (on && (ind_l >> 5) == s) ? (1u << (ind_l & 31)) : 0u);
+    }
+    return overflow;
 }
+
+
+template <int NPL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_noddi_stage2_lean(const FitParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    int lane = threadIdx.x & 31;
+    unsigned wso = p.ws_smem_off + (threadIdx.x >> 5) * (Lars2WS<NPL>::SIZE * 8);
+    asm volatile("" : "+r"(lane), "+r"(wso));  // opaque: kept in registers instead of being re-derived from %tid at every use
+    const int warp = threadIdx.x >> 5;
+    const int cap = p.cap_stage[1];
+    double *wsb = (double *)(smem + wso);
+    double *bx = wsb + Lars2WS<NPL>::BX;
+    constexpr int NT = 4 * NPL, TP = (MAXT > 512 && NT % 2 == 0) ? NT / 2 : NT;
+    const int m = p.m, n = p.n, n_pad = p.n_pad, n_wm = p.n_wm, NA = p.NA;
+    double *scr = p.scratch + ((size_t)blockIdx.x * 32 + warp) * (size_t)BV * NA;
+    const int g = lane >> 2;
+    int *counter = p.tile_counter + 1;
+    const int n_tiles = *p.n_tiles_ptr;
+    for (;;) {
+        int b = 0;
+        if (lane == 0) b = atomicAdd(counter, 1);
+        b = __reduce_add_sync(FULL, b);
+        if (b >= n_tiles) break;
+        const int4 tile = p.tiles[b];
+        const int nb = tile.z;  // <= BV
+        const float *S = (const float *)p.slab + (size_t)tile.x * p.slab_stride;
+        const bool vvalid = g < nb;
+        const long long mypos = tile.y + (vvalid ? g : 0);
+        const long long myvox = (long long)p.order[mypos];
+        const double *T2 = p.T2 + (size_t)tile.x * p.T2_stride;
+        const double xi = p.xiso[2 * mypos], xd = p.xiso[2 * mypos + 1];
+        if (p.norms_const)
+            gemm_c2<NT, TP, float, true>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms, n_wm, scr,
+                                         NA, bx, lane);
+        else
+            gemm_c2<NT, TP, float, false>(S, n_pad, n, n_wm, p.dc, p.dwi_rows, p.y, p.y_f64, m, myvox, vvalid, xi, xd, p.exvivo, p.norms, n_wm, scr,
+                                          NA, bx, lane);
+#pragma unroll 1
+        for (int v = 0; v < nb; ++v) {
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) wsb[Lars2WS<NPL>::DTR + lane + 32 * s] = scr[(size_t)v * NA + lane + 32 * s];
+            __syncwarp();
+            unsigned sup[NPL];
+            const int ov = lars_lean<NPL>(T2, p.ldT2, n_wm, p.dc < n_wm ? p.dc : n_wm, p.lambda1, wsb, bx[v], lane, cap, sup);
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) {
+                const int j = lane + 32 * s;
+                const unsigned w = sup[s] | __ballot_sync(FULL, j >= n_wm && j < n);  // dot / iso columns always belong
+                if (lane == s) p.supmask[(size_t)(tile.y + v) * NPL + s] = w;
+            }
+            if (ov) queue_slow(p, (long long)p.order[tile.y + v], lane);
+            __syncwarp();
+        }
+    }
+}
+
+// ================================================================================================
+// ONE VOXEL PER THREAD with warp-cooperative services (NODDI stages 1 and 3).
+// A warp solving ONE NNLS voxel spends most of its ~4-9 k instructions on cross-lane glue around a passive set of <= 8 atoms
+// (substitution steps through shuffles, butterflies, factor updates, control) with most lanes idle.  Here every THREAD owns a
+// voxel and runs the small part of Lawson-Hanson for it -- candidate test, factor append, passive solve, ratio test,
+// Givens downdates -- with its state in shared memory as [index][thread]; 32 voxels advance per instruction.  The WIDE parts
+// are served by the whole warp, one requesting thread at a time (requests collected by ballot, the requester's state read from
+// its shared-memory column):
+//   * stage 1: the dual pass w = c - T[:,P] x over the full dictionary and its arg-max (Gram rows read coalesced, lane l owns
+//     atoms l, l + 32, ... exactly as warp_nnls does),
+//   * both stages: the A-space re-evaluation of a near-dependent candidate (m x |P| products, rows strided over the lanes).
+// Same pivoting rules and the same floating-point operations in the same order as warp_nnls (column-oriented substitutions, the
+// butterfly trees of the two short sums written out for <= 8 terms, the same Givens downdates): bit-identical coefficients.
+// Voxels are taken in LUT-direction order, so a warp's threads mostly share the Gram table / dictionary slab.
+// A voxel whose passive set would outgrow CAPT (or, stage 3, whose support exceeds 32 atoms) is appended to `redo` as a
+// one-voxel tile and re-fitted by the warp-per-voxel kernel of the stage.
+constexpr int TPV_THREADS = 128;
+
+template <int CAPT>
+struct TpvWS {  // per-thread state, [index][thread]
+    static constexpr int NTH = TPV_THREADS, TRI_T = CAPT * (CAPT + 1) / 2;
+    double (*Ls)[NTH];   // packed lower factor
+    double (*rds)[NTH];  // 1 / diagonal
+    double (*zs)[NTH];   // z = L^-1 c_P
+    double (*xs)[NTH];   // coefficients by passive position
+    double (*bs)[NTH];   // scratch: t / v / s / beta
+    unsigned char (*Ps)[NTH];  // passive list (atoms / compact indices < 256)
+    static constexpr int BYTES_PER_THREAD = (TRI_T + 4 * CAPT) * 8 + 8;  // CAPT <= 8 list bytes
+    __device__ __forceinline__ unsigned char *carve(unsigned char *base)
+    {
+        Ls = (double (*)[NTH])base;
+        rds = Ls + TRI_T;
+        zs = rds + CAPT;
+        xs = zs + CAPT;
+        bs = xs + CAPT;
+        Ps = (unsigned char (*)[NTH])(bs + CAPT);
+        return (unsigned char *)(Ps + 8);
+    }
+};
+
+// Candidate test of atom `atomj` against the passive set (per thread): v = L^-1 t with t_k = T[P_k][j] (column-oriented forward
+// substitution, left in ws.bs), |v|^2 and v.z over the 32-lane butterfly tree restricted to its <= 8 non-zero leaves,
+// d2 = H_jj - |v|^2, znum = c_j - v.z.  ATOM(k): dictionary atom of passive position k.
+template <int CAPT, typename ATOM>
+__device__ __forceinline__ void tpv_candidate(const TpvWS<CAPT> &ws, const int tid, const int np, const double *Tj, const double hjj, const double cj,
+                                              ATOM atom_of, double &vv, double &d2, double &znum)
+{
+    for (int k = 0; k < np; ++k) ws.bs[k][tid] = Tj[atom_of(k)];
+    for (int k = 0; k < np; ++k) {
+        const double vk = ws.bs[k][tid] * ws.rds[k][tid];
+        for (int a = k + 1; a < np; ++a) ws.bs[a][tid] = fma(-ws.Ls[tri(a, k)][tid], vk, ws.bs[a][tid]);
+    }
+    double sq[8], sz[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const bool on = k < np && k < CAPT;
+        const int kk = k < CAPT ? k : 0;
+        const double vk = on ? ws.bs[kk][tid] * ws.rds[kk][tid] : 0.0;
+        if (on) ws.bs[kk][tid] = vk;  // bs now holds v
+        sq[k] = vk * vk;
+        sz[k] = vk * (on ? ws.zs[kk][tid] : 0.0);
+    }
+    vv = ((sq[0] + sq[4]) + (sq[2] + sq[6])) + ((sq[1] + sq[5]) + (sq[3] + sq[7]));
+    const double vz = ((sz[0] + sz[4]) + (sz[2] + sz[6])) + ((sz[1] + sz[5]) + (sz[3] + sz[7]));
+    d2 = hjj - vv;
+    znum = cj - vz;
+}
+
+// beta = L^-T v in place (column-oriented back substitution on ws.bs)
+template <int CAPT>
+__device__ __forceinline__ void tpv_back_inplace(const TpvWS<CAPT> &ws, const int tid, const int np)
+{
+    for (int k = np - 1; k >= 0; --k) {
+        const double sk = ws.bs[k][tid] * ws.rds[k][tid];
+        ws.bs[k][tid] = sk;
+        for (int a = 0; a < k; ++a) ws.bs[a][tid] = fma(-ws.Ls[tri(k, a)][tid], sk, ws.bs[a][tid]);
+    }
+}
+
+// A-space service (warp-cooperative): for every thread with `near`, r = a_j - A_P beta (beta in the requester's ws.bs),
+// d2 = |r|^2, znum = r.y with the rows strided over the lanes and summed exactly as warp_nnls does it.
+template <int CAPT, typename ATOMT>
+__device__ __forceinline__ void tpv_aspace_service(const TpvWS<CAPT> &ws, const FitParams &p, const bool near, const int tid, const int lane,
+                                                   const int np, const int atomj, const int dir, const long long vox, const double hjj,
+                                                   ATOMT atom_of_thread, double &d2, double &znum)
+{
+    const int m = p.m;
+    __syncwarp();  // the requesters' beta / passive lists are read by the other lanes
+    for (unsigned req = __ballot_sync(FULL, near); req; req &= req - 1) {
+        const int src = __ffs(req) - 1, st = (tid & ~31) + src;
+        const int r_np = __shfl_sync(FULL, np, src), r_atomj = __shfl_sync(FULL, atomj, src), r_dir = __shfl_sync(FULL, dir, src);
+        const long long r_vox = __shfl_sync(FULL, vox, src);
+        const float *S = (const float *)p.slab + (size_t)r_dir * p.slab_stride;
+        const float *Sj = S + r_atomj;
+        double a2 = 0.0, ay = 0.0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < m; i0 += 32) {
+            const int i = i0 + lane;
+            const bool on = i < m;
+            const float *Si = S + (size_t)(on ? i : 0) * p.n_pad;
+            double r = (double)Sj[(size_t)(on ? i : 0) * p.n_pad];
+#pragma unroll 1
+            for (int a = 0; a < r_np; a += 2) {
+                const int a1 = min(a + 1, r_np - 1);
+                const float s0 = Si[atom_of_thread(a, st)], s1 = Si[atom_of_thread(a1, st)];
+                const double b0 = ws.bs[a][st], b1 = (a + 1 < r_np) ? ws.bs[a1][st] : 0.0;
+                r = fma(-(double)s0, b0, r);
+                r = fma(-(double)s1, b1, r);
+            }
+            if (on) {
+                const double yi = p.y_f64 ? ((const double *)p.y)[r_vox * m + i] : (double)((const float *)p.y)[r_vox * m + i];
+                a2 = fma(r, r, a2);
+                ay = fma(r, yi, ay);
+            }
+        }
+        a2 = warp_sum(a2);
+        ay = warp_sum(ay);
+        if (lane == src) {
+            d2 = a2;
+            znum = ay;
+            if (d2 < 1e-24 * hjj) d2 = 0.0;
+        }
+    }
+}
+
+// v = L^-1 t again (ws.bs held beta during the service): same operations as tpv_candidate
+template <int CAPT, typename ATOM>
+__device__ __forceinline__ void tpv_restore_v(const TpvWS<CAPT> &ws, const int tid, const int np, const double *Tj, ATOM atom_of)
+{
+    for (int k = 0; k < np; ++k) ws.bs[k][tid] = Tj[atom_of(k)];
+    for (int k = 0; k < np; ++k) {
+        const double vk = ws.bs[k][tid] * ws.rds[k][tid];
+        for (int a = k + 1; a < np; ++a) ws.bs[a][tid] = fma(-ws.Ls[tri(a, k)][tid], vk, ws.bs[a][tid]);
+        ws.bs[k][tid] = vk;
+    }
+}
+
+// Candidate j (list entry `pj`) joins the passive set, then the secondary loop: solve on the passive set, step back to the
+// feasible boundary while a coefficient is not positive, Givens downdates for the atoms that leave.  REMOVED(entry): called
+// for every passive-list entry that leaves.  Returns false when the iteration cap stopped the voxel.
+template <int CAPT, typename REMOVED>
+__device__ __forceinline__ bool tpv_accept(const TpvWS<CAPT> &ws, const int tid, int &np, int &iter, const int itmax, const int pj,
+                                           const double d2, const double znum, REMOVED removed)
+{
+    {
+        const double ird = rsqrt(d2), dd = d2 * ird;
+        for (int k = 0; k < np; ++k) ws.Ls[tri(np, k)][tid] = ws.bs[k][tid];
+        ws.Ls[tri(np, np)][tid] = dd;
+        ws.rds[np][tid] = ird;
+        ws.zs[np][tid] = znum * ird;
+        ws.xs[np][tid] = 0.0;
+        ws.Ps[np][tid] = (unsigned char)pj;
+        ++np;
+    }
+    for (;;) {
+        if (++iter > itmax) return false;
+        for (int k = 0; k < np; ++k) ws.bs[k][tid] = ws.zs[k][tid];
+        tpv_back_inplace<CAPT>(ws, tid, np);  // s = L^-T z
+        double tmin = INFINITY;
+        int cand = -1;
+        bool anyneg = false;
+        for (int k = 0; k < np; ++k) {
+            const double sk = ws.bs[k][tid];
+            if (sk <= 0.0) {
+                anyneg = true;
+                const double xk = ws.xs[k][tid], tt = -xk / (sk - xk);
+                if (tt < 2.0 && tt < tmin) { tmin = tt; cand = k; }
+            }
+        }
+        if (!anyneg || cand < 0) {
+            for (int k = 0; k < np; ++k) ws.xs[k][tid] = ws.bs[k][tid];
+            return true;
+        }
+        unsigned rmask = 0u;
+        const int np_old = np;
+        int q = 0;
+        for (int k = 0; k < np_old; ++k) {
+            double xk = ws.xs[k][tid];
+            xk = fma(tmin, ws.bs[k][tid] - xk, xk);
+            if (k == cand) xk = 0.0;
+            if (xk > 0.0) {
+                ws.xs[q][tid] = xk;
+                ws.Ps[q][tid] = ws.Ps[k][tid];
+                ++q;
+            } else {
+                rmask |= 1u << k;
+                removed(ws.Ps[k][tid]);
+            }
+        }
+        np = q;
+        if (np == 0) return true;
+        for (int pn = np_old; rmask; --pn) {  // Cholesky downdate, highest removed position first (chol_delete, per thread)
+            const int qd = 31 - __clz(rmask);
+            rmask &= ~(1u << qd);
+            double carry[CAPT];
+#pragma unroll
+            for (int i = 0; i < CAPT; ++i) carry[i] = 0.0;
+            for (int i = qd; i < pn - 1; ++i)
+                for (int col = 0; col < qd; ++col) ws.Ls[tri(i, col)][tid] = ws.Ls[tri(i + 1, col)][tid];
+#pragma unroll
+            for (int i = 0; i < CAPT; ++i)
+                if (i >= qd && i < pn - 1) carry[i] = ws.Ls[tri(i + 1, qd)][tid];
+            for (int r = qd; r < pn - 1; ++r) {
+                double a = 0.0;
+#pragma unroll
+                for (int i = 0; i < CAPT; ++i)
+                    if (i == r) a = carry[i];
+                const double b = ws.Ls[tri(r + 1, r + 1)][tid];
+                const double ir = rsqrt(fma(a, a, b * b));
+                const double cs = a * ir, sn = b * ir;
+#pragma unroll
+                for (int i = 0; i < CAPT; ++i) {
+                    if (i >= r && i < pn - 1) {
+                        const double u2 = ws.Ls[tri(i + 1, r + 1)][tid];
+                        ws.Ls[tri(i, r)][tid] = fma(cs, carry[i], sn * u2);
+                        carry[i] = fma(cs, u2, -sn * carry[i]);
+                    }
+                }
+                ws.rds[r][tid] = ir;
+                const double zr = ws.zs[r][tid], zr1 = ws.zs[r + 1][tid];
+                ws.zs[r][tid] = fma(cs, zr, sn * zr1);
+                ws.zs[r + 1][tid] = fma(cs, zr1, -sn * zr);
+            }
+            ws.zs[pn - 1][tid] = 0.0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NODDI stage 3 (debias on the support, amico/models.pyx:929-942 + maps :945-979): the system is the sub-system on the ~11
+// support atoms (compact numbering, sa[] maps it to atoms), small enough for the dual pass to stay per thread as well.
+template <int CAPT>
+__host__ __device__ constexpr int tpv3_smem_bytes() { return TPV_THREADS * (TpvWS<CAPT>::BYTES_PER_THREAD + 32); }
 
 template <int NPL, int CAPT>
 __global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParams p, int4 *redo, int *redo_count)
 {
-    constexpr int NTH = TPV_THREADS, TRI_T = CAPT * (CAPT + 1) / 2;
+    constexpr int NTH = TPV_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*Ls)[NTH] = (double (*)[NTH])smem_raw;          // packed lower factor
-    double (*rds)[NTH] = Ls + TRI_T;                         // 1 / diagonal
-    double (*zs)[NTH] = rds + CAPT;                          // z = L^-1 c_P
-    double (*xs)[NTH] = zs + CAPT;                           // coefficients by passive position
-    double (*bs)[NTH] = xs + CAPT;                           // scratch: v / s / beta
-    int (*Ps)[NTH] = (int (*)[NTH])(bs + CAPT);              // passive list (compact indices)
-    unsigned char (*sa)[NTH] = (unsigned char (*)[NTH])(Ps + CAPT);  // compact index -> atom
+    TpvWS<CAPT> ws;
+    unsigned char (*sa)[NTH] = (unsigned char (*)[NTH])ws.carve(smem_raw);  // compact index -> atom
     const int tid = threadIdx.x, lane = tid & 31;
-    const int n = p.n, n_wm = p.n_wm, ldT = p.ldT1, NA = p.NA, m = p.m;
+    const int n_wm = p.n_wm, ldT = p.ldT1, NA = p.NA, m = p.m;
     const bool use_as = p.aspace != 0;
     for (long long base = (long long)blockIdx.x * NTH; base < p.n_vox; base += (long long)gridDim.x * NTH) {
         const long long pos = base + tid;
@@ -759,14 +1264,15 @@ __global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParam
         int np = 0, iter = 0;
         unsigned inP = 0u;  // bit a: compact index a is passive
         const unsigned allmask = ns >= 32 ? 0xffffffffu : ((1u << ns) - 1u);
+        auto atom_of = [&](int k) { return (int)sa[ws.Ps[k][tid]][tid]; };
+        auto atom_of_thread = [&](int k, int st) { return (int)sa[ws.Ps[k][st]][st]; };
         while (__any_sync(FULL, run)) {
-            // ---- candidate selection (per thread), with the warp-cooperative A-space service inside
             bool pend = run && np < m;
             if (pend && np >= CAPT) { pend = false; run = false; redo_me = true; }
             if (run && !pend) run = false;  // np reached m: done
             unsigned valid = allmask & ~inP;
             bool acc = false;
-            int j = -1;
+            int j = -1, atomj = 0;
             double d2 = 0.0, znum = 0.0, vv = 0.0, hjj = 0.0;
             while (__any_sync(FULL, pend)) {
                 bool near = false;
@@ -777,192 +1283,36 @@ __global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParam
                     for (unsigned mm = valid; mm; mm &= mm - 1) {
                         const int a = __ffs(mm) - 1, atom = sa[a][tid];
                         double w = cg[atom];
-                        for (int k = 0; k < np; ++k) w = fma(-T[(unsigned)(sa[Ps[k][tid]][tid] * ldT + atom)], xs[k][tid], w);
+                        for (int k = 0; k < np; ++k) w = fma(-T[(unsigned)(atom_of(k) * ldT + atom)], ws.xs[k][tid], w);
                         if (w > bv) { bv = w; j = a; }
                     }
                     if (j < 0) { pend = false; run = false; }
                 }
                 if (pend) {
-                    const int atomj = sa[j][tid];
+                    atomj = sa[j][tid];
                     const double *Tj = T + (unsigned)(atomj * ldT);
                     hjj = Tj[atomj];
-                    // v = L^-1 t, t_k = T[P_k][j]: column-oriented forward substitution (the order warp_nnls uses)
-                    for (int k = 0; k < np; ++k) bs[k][tid] = Tj[sa[Ps[k][tid]][tid]];
-                    for (int k = 0; k < np; ++k) {
-                        const double vk = bs[k][tid] * rds[k][tid];
-                        for (int a = k + 1; a < np; ++a) bs[a][tid] = fma(-Ls[tri(a, k)][tid], vk, bs[a][tid]);
-                    }
-                    // |v|^2 and v.z over the 32-lane butterfly tree (offsets 16, 8, 4, 2, 1) restricted to its <= 8 non-zero leaves
-                    double sq[8], sz[8];
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const bool on = k < np && k < CAPT;
-                        const double vk = on ? bs[k < CAPT ? k : 0][tid] * rds[k < CAPT ? k : 0][tid] : 0.0;
-                        if (on) bs[k < CAPT ? k : 0][tid] = vk;  // bs now holds v
-                        sq[k] = vk * vk;
-                        sz[k] = vk * (on ? zs[k < CAPT ? k : 0][tid] : 0.0);
-                    }
-                    vv = ((sq[0] + sq[4]) + (sq[2] + sq[6])) + ((sq[1] + sq[5]) + (sq[3] + sq[7]));
-                    const double vz = ((sz[0] + sz[4]) + (sz[2] + sz[6])) + ((sz[1] + sz[5]) + (sz[3] + sz[7]));
-                    d2 = hjj - vv;
-                    znum = cg[atomj] - vz;
+                    tpv_candidate<CAPT>(ws, tid, np, Tj, hjj, cg[atomj], atom_of, vv, d2, znum);
                     near = use_as && np > 0 && d2 < 1e-10 * hjj;
-                    if (near) {  // beta = L^-T v for the service below (column-oriented back substitution), into bs
-                        for (int k = np - 1; k >= 0; --k) {
-                            const double sk = bs[k][tid] * rds[k][tid];
-                            bs[k][tid] = sk;
-                            for (int a = 0; a < k; ++a) bs[a][tid] = fma(-Ls[tri(k, a)][tid], sk, bs[a][tid]);
-                        }
-                    }
+                    if (near) tpv_back_inplace<CAPT>(ws, tid, np);  // beta for the service
                 }
-                // ---- A-space service: r = a_j - A_P beta, d2 = |r|^2, numerator r.y, one requesting thread at a time
-                for (unsigned req = __ballot_sync(FULL, near); req; req &= req - 1) {
-                    const int src = __ffs(req) - 1, st = (tid & ~31) + src;
-                    const int r_np = __shfl_sync(FULL, np, src), r_j = __shfl_sync(FULL, j, src), r_dir = __shfl_sync(FULL, dir, src);
-                    const long long r_vox = __shfl_sync(FULL, vox, src);
-                    const float *S = (const float *)p.slab + (size_t)r_dir * p.slab_stride;
-                    const float *Sj = S + sa[r_j][st];
-                    double a2 = 0.0, ay = 0.0;
-#pragma unroll 1
-                    for (int i0 = 0; i0 < m; i0 += 32) {
-                        const int i = i0 + lane;
-                        const bool on = i < m;
-                        const float *Si = S + (size_t)(on ? i : 0) * p.n_pad;
-                        double r = (double)Sj[(size_t)(on ? i : 0) * p.n_pad];
-#pragma unroll 1
-                        for (int a = 0; a < r_np; a += 2) {
-                            const int a1 = min(a + 1, r_np - 1);
-                            const float s0 = Si[sa[Ps[a][st]][st]], s1 = Si[sa[Ps[a1][st]][st]];
-                            const double b0 = bs[a][st], b1 = (a + 1 < r_np) ? bs[a1][st] : 0.0;
-                            r = fma(-(double)s0, b0, r);
-                            r = fma(-(double)s1, b1, r);
-                        }
-                        if (on) {
-                            const double yi = p.y_f64 ? ((const double *)p.y)[r_vox * m + i] : (double)((const float *)p.y)[r_vox * m + i];
-                            a2 = fma(r, r, a2);
-                            ay = fma(r, yi, ay);
-                        }
-                    }
-                    a2 = warp_sum(a2);
-                    ay = warp_sum(ay);
-                    if (lane == src) {
-                        d2 = a2;
-                        znum = ay;
-                        if (d2 < 1e-24 * hjj) d2 = 0.0;
-                    }
-                }
+                tpv_aspace_service<CAPT>(ws, p, near, tid, lane, np, atomj, dir, vox, hjj, atom_of_thread, d2, znum);
                 if (pend) {
-                    if (near) {  // bs held beta: restore v = L^-1 t for the new factor row (same operations as above)
-                        const double *Tj = T + (unsigned)(sa[j][tid] * ldT);
-                        for (int k = 0; k < np; ++k) bs[k][tid] = Tj[sa[Ps[k][tid]][tid]];
-                        for (int k = 0; k < np; ++k) {
-                            const double vk = bs[k][tid] * rds[k][tid];
-                            for (int a = k + 1; a < np; ++a) bs[a][tid] = fma(-Ls[tri(a, k)][tid], vk, bs[a][tid]);
-                            bs[k][tid] = vk;
-                        }
-                    }
+                    if (near) tpv_restore_v<CAPT>(ws, tid, np, T + (unsigned)(atomj * ldT), atom_of);
                     if (d2 > 0.0 && d2 > 1.2325951644078309e-28 * vv && znum > 0.0) { acc = true; pend = false; }
                     else valid &= ~(1u << j);
                 }
             }
             if (!acc) continue;
-            // ---- j joins the passive set (from here on purely per thread)
-            {
-                const double ird = rsqrt(d2), dd = d2 * ird;
-                for (int k = 0; k < np; ++k) Ls[tri(np, k)][tid] = bs[k][tid];
-                Ls[tri(np, np)][tid] = dd;
-                rds[np][tid] = ird;
-                zs[np][tid] = znum * ird;
-                xs[np][tid] = 0.0;
-                Ps[np][tid] = j;
-                inP |= 1u << j;
-                ++np;
-            }
-            for (;;) {  // secondary loop
-                if (++iter > itmax) { run = false; break; }
-                // s = L^-T z into bs (column-oriented back substitution)
-                for (int k = 0; k < np; ++k) bs[k][tid] = zs[k][tid];
-                for (int k = np - 1; k >= 0; --k) {
-                    const double sk = bs[k][tid] * rds[k][tid];
-                    bs[k][tid] = sk;
-                    for (int a = 0; a < k; ++a) bs[a][tid] = fma(-Ls[tri(k, a)][tid], sk, bs[a][tid]);
-                }
-                double tmin = INFINITY;
-                int cand = -1;
-                bool anyneg = false;
-                for (int k = 0; k < np; ++k) {
-                    const double sk = bs[k][tid];
-                    if (sk <= 0.0) {
-                        anyneg = true;
-                        const double xk = xs[k][tid], tt = -xk / (sk - xk);
-                        if (tt < 2.0 && tt < tmin) { tmin = tt; cand = k; }
-                    }
-                }
-                if (!anyneg || cand < 0) {
-                    for (int k = 0; k < np; ++k) xs[k][tid] = bs[k][tid];
-                    break;
-                }
-                unsigned rmask = 0u;
-                const int np_old = np;
-                int q = 0;
-                for (int k = 0; k < np_old; ++k) {
-                    double xk = xs[k][tid];
-                    xk = fma(tmin, bs[k][tid] - xk, xk);
-                    if (k == cand) xk = 0.0;
-                    if (xk > 0.0) {
-                        xs[q][tid] = xk;
-                        Ps[q][tid] = Ps[k][tid];
-                        ++q;
-                    } else {
-                        rmask |= 1u << k;
-                        inP &= ~(1u << Ps[k][tid]);
-                    }
-                }
-                np = q;
-                if (np == 0) break;
-                for (int pn = np_old; rmask; --pn) {  // Cholesky downdate, highest removed position first
-                    const int qd = 31 - __clz(rmask);
-                    rmask &= ~(1u << qd);
-                    // rows qd+1.. move up one slot, Givens rotations restore the triangle, z is rotated along (chol_delete)
-                    double carry[CAPT];
-#pragma unroll
-                    for (int i = 0; i < CAPT; ++i) carry[i] = 0.0;
-                    for (int i = qd; i < pn - 1; ++i)
-                        for (int col = 0; col < qd; ++col) Ls[tri(i, col)][tid] = Ls[tri(i + 1, col)][tid];
-#pragma unroll
-                    for (int i = 0; i < CAPT; ++i)
-                        if (i >= qd && i < pn - 1) carry[i] = Ls[tri(i + 1, qd)][tid];
-                    for (int r = qd; r < pn - 1; ++r) {
-                        double a = 0.0;
-#pragma unroll
-                        for (int i = 0; i < CAPT; ++i)
-                            if (i == r) a = carry[i];
-                        const double b = Ls[tri(r + 1, r + 1)][tid];
-                        const double ir = rsqrt(fma(a, a, b * b));
-                        const double cs = a * ir, sn = b * ir;
-#pragma unroll
-                        for (int i = 0; i < CAPT; ++i) {
-                            if (i >= r && i < pn - 1) {
-                                const double u2 = Ls[tri(i + 1, r + 1)][tid];
-                                Ls[tri(i, r)][tid] = fma(cs, carry[i], sn * u2);
-                                carry[i] = fma(cs, u2, -sn * carry[i]);
-                            }
-                        }
-                        rds[r][tid] = ir;
-                        const double zr = zs[r][tid], zr1 = zs[r + 1][tid];
-                        zs[r][tid] = fma(cs, zr, sn * zr1);
-                        zs[r + 1][tid] = fma(cs, zr1, -sn * zr);
-                    }
-                    zs[pn - 1][tid] = 0.0;
-                }
-            }
+            inP |= 1u << j;
+            if (!tpv_accept<CAPT>(ws, tid, np, iter, itmax, j, d2, znum, [&](int a) { inP &= ~(1u << a); })) run = false;
         }
         // ---- maps (noddi_maps: sums over the positive coefficients in ascending atom order)
         if (active && !redo_me) {
             auto xof = [&](int a) {  // coefficient of compact index a (passive atoms only)
                 double xv = 0.0;
                 for (int k = 0; k < np; ++k)
-                    if (Ps[k][tid] == a) xv = xs[k][tid];
+                    if (ws.Ps[k][tid] == a) xv = ws.xs[k][tid];
                 return xv;
             };
             double s_all = 0.0;
@@ -1002,6 +1352,172 @@ __global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParam
                 p.extra[2 * vox + 1] = odi * tf;
             }
             if (p.support_out) p.support_out[vox] = ns;
+        }
+        if (redo_me) {
+            const int slot = atomicAdd(redo_count, 1);
+            redo[slot] = make_int4(dir, (int)pos, 1, 0);
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NODDI stage 1 (isotropic fraction, amico/models.pyx:911) on the full dictionary.  A warp pulls four batches (<= 32 voxels)
+// from the queue, computes their c1 = A^T y on the tensor pipe (gemm_c1, kept per voxel for stage 3), then lane 8 t + i owns
+// voxel i of batch t.  Dual pass + arg-max are served cooperatively (see above); inP / rej: per-voxel bit words over the atoms
+// (word s, bit l <-> atom l + 32 s) of the passive set and of the candidates dropped in the current round.
+template <int NPL, int CAPT>
+__host__ __device__ constexpr int tpv1_smem_bytes() { return TPV_THREADS * (TpvWS<CAPT>::BYTES_PER_THREAD + 8 * NPL) + (TPV_THREADS / 32) * BV * 8; }
+
+template <int NPL, int CAPT>
+__global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage1_tpv(const FitParams p, int4 *redo, int *redo_count)
+{
+    constexpr int NTH = TPV_THREADS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TpvWS<CAPT> ws;
+    unsigned (*inPw)[NTH] = (unsigned (*)[NTH])ws.carve(smem_raw);
+    unsigned (*rejw)[NTH] = inPw + NPL;
+    double *bx = (double *)(rejw + NPL) + (threadIdx.x >> 5) * BV;  // per warp: ||y||^2 of the batch in flight
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = p.n, ldT = p.ldT1, NA = p.NA, m = p.m;
+    const bool use_as = p.aspace != 0;
+    constexpr int NT = 4 * NPL, TP = (NT % 2 == 0) ? NT / 2 : NT;
+    unsigned availw = 0u;  // bit s: atom lane + 32 s exists
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) availw |= (lane + 32 * s < n ? 1u : 0u) << s;
+    int *counter = p.tile_counter;
+    const int n_tiles = *p.n_tiles_ptr;
+    const int itmax = 3 * n;
+    for (;;) {
+        int b0 = 0;
+        if (lane == 0) b0 = atomicAdd(counter, 4);
+        b0 = __reduce_add_sync(FULL, b0);
+        if (b0 >= n_tiles) break;
+        bool active = false;
+        long long pos = 0, vox = 0;
+        int dir = 0;
+        double yy = 0.0;
+#pragma unroll 1
+        for (int t = 0; t < 4; ++t) {
+            if (b0 + t >= n_tiles) break;
+            const int4 tile = p.tiles[b0 + t];
+            const int g = lane >> 2;
+            const bool vvalid = g < tile.z;
+            const float *S = (const float *)p.slab + (size_t)tile.x * p.slab_stride;
+            gemm_c1<NT, TP, float>(S, p.n_pad, m, p.y, p.y_f64, (long long)p.order[tile.y + (vvalid ? g : 0)], vvalid,
+                                   p.c1_all + (size_t)tile.y * NA, NA, lane, bx);
+            if ((lane >> 3) == t && (lane & 7) < tile.z) {
+                active = true;
+                pos = tile.y + (lane & 7);
+                dir = tile.x;
+                yy = bx[lane & 7];
+            }
+            __syncwarp();
+        }
+        if (active) vox = (long long)p.order[pos];
+        const double *T = p.T1 + (size_t)dir * p.T1_stride;
+        const double *cg = p.c1_all + (size_t)pos * NA;
+        bool redo_me = false, run = active;
+        int np = 0, iter = 0;
+#pragma unroll
+        for (int s = 0; s < NPL; ++s) inPw[s][tid] = 0u;
+        auto atom_of = [&](int k) { return ws.Ps[k][tid]; };
+        auto atom_of_thread = [&](int k, int st) { return ws.Ps[k][st]; };
+        while (__any_sync(FULL, run)) {
+            bool pend = run && np < m;
+            if (pend && np >= CAPT) { pend = false; run = false; redo_me = true; }
+            if (run && !pend) run = false;
+#pragma unroll
+            for (int s = 0; s < NPL; ++s) rejw[s][tid] = inPw[s][tid];  // blocked atoms of this round: passive + dropped candidates
+            bool acc = false;
+            int j = -1;
+            double d2 = 0.0, znum = 0.0, vv = 0.0, hjj = 0.0;
+            while (__any_sync(FULL, pend)) {
+                __syncwarp();  // passive lists, coefficients and bit words of the requesters are read by the other lanes
+                // ---- dual pass + arg-max service: w = c - T[:,P] x_P in passive order, lane l owns atoms l + 32 s
+                for (unsigned req = __ballot_sync(FULL, pend); req; req &= req - 1) {
+                    const int src = __ffs(req) - 1, st = (tid & ~31) + src;
+                    const int r_np = __shfl_sync(FULL, np, src), r_dir = __shfl_sync(FULL, dir, src);
+                    const long long r_pos = __shfl_sync(FULL, pos, src);
+                    const double *Tl = p.T1 + (size_t)r_dir * p.T1_stride + lane;
+                    const double *cl = p.c1_all + (size_t)r_pos * NA + lane;
+                    // rows in chunks of four, every load of a chunk issued before its first use (one L2 latency per chunk)
+                    double wl[NPL];
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) wl[s] = cl[32 * s];
+#pragma unroll 1
+                    for (int k0 = 0; k0 < r_np; k0 += 4) {
+                        double gq[4][NPL], xq[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int k = min(k0 + q, r_np - 1);
+                            const double *rk = Tl + (unsigned)(ws.Ps[k][st] * ldT);
+                            xq[q] = ws.xs[k][st];
+#pragma unroll
+                            for (int s = 0; s < NPL; ++s) gq[q][s] = rk[32 * s];
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            if (k0 + q < r_np) {
+#pragma unroll
+                                for (int s = 0; s < NPL; ++s) wl[s] = fma(-gq[q][s], xq[q], wl[s]);
+                            }
+                        }
+                    }
+                    double bv = 0.0;
+                    int bj = -1;
+#pragma unroll
+                    for (int s = 0; s < NPL; ++s) {
+                        const bool ok = ((availw >> s) & 1u) && !((rejw[s][st] >> lane) & 1u);
+                        if (ok && wl[s] > bv) { bv = wl[s]; bj = lane + 32 * s; }
+                    }
+                    warp_argmax_pos(bv, bj);
+                    if (lane == src) j = bj;
+                }
+                if (pend && j < 0) { pend = false; run = false; }  // no positive dual left: done
+                bool near = false;
+                if (pend) {
+                    const double *Tj = T + (unsigned)(j * ldT);
+                    hjj = Tj[j];
+                    tpv_candidate<CAPT>(ws, tid, np, Tj, hjj, cg[j], atom_of, vv, d2, znum);
+                    near = use_as && np > 0 && d2 < 1e-10 * hjj;
+                    if (near) tpv_back_inplace<CAPT>(ws, tid, np);
+                }
+                tpv_aspace_service<CAPT>(ws, p, near, tid, lane, np, j, dir, vox, hjj, atom_of_thread, d2, znum);
+                if (pend) {
+                    if (near) tpv_restore_v<CAPT>(ws, tid, np, T + (unsigned)(j * ldT), atom_of);
+                    if (d2 > 0.0 && d2 > 1.2325951644078309e-28 * vv && znum > 0.0) { acc = true; pend = false; }
+                    else rejw[j >> 5][tid] |= 1u << (j & 31);
+                }
+                __syncwarp();  // rej / passive words are read by the other lanes in the next service round
+            }
+            if (acc) {
+                inPw[j >> 5][tid] |= 1u << (j & 31);
+                if (!tpv_accept<CAPT>(ws, tid, np, iter, itmax, j, d2, znum, [&](int a) { inPw[a >> 5][tid] &= ~(1u << (a & 31)); })) run = false;
+            }
+            __syncwarp();
+        }
+        if (active && !redo_me) {
+            double x1 = 0.0, x2 = 0.0, zz = 0.0;
+            for (int k = 0; k < np; ++k) {
+                if (ws.Ps[k][tid] == n - 1) x1 = ws.xs[k][tid];
+                if (ws.Ps[k][tid] == n - 2) x2 = ws.xs[k][tid];
+            }
+            {   // ||z||^2 over the 32-lane butterfly tree, as warp_sum would add it
+                double q[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const double zk = (k < np && k < CAPT) ? ws.zs[k < CAPT ? k : 0][tid] : 0.0;
+                    q[k] = zk * zk;
+                }
+                zz = ((q[0] + q[4]) + (q[2] + q[6])) + ((q[1] + q[5]) + (q[3] + q[7]));
+            }
+            p.xiso[2 * pos] = x1;
+            p.xiso[2 * pos + 1] = p.exvivo ? x2 : 0.0;
+            if (yy > 0.0 && yy - zz < p.exact_tol * yy) {  // exact-fit voxel: queued for the A-space QR path (see k_noddi_stage)
+                const unsigned long long idx = atomicAdd((unsigned long long *)&p.status[4], 1ull);
+                if ((long long)idx < p.exact_cap) p.exact_list[idx] = (int)vox;
+            }
         }
         if (redo_me) {
             const int slot = atomicAdd(redo_count, 1);
