@@ -709,6 +709,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_noddi_stage1_pair(const FitParams p
 // same arithmetic (identical support words), with what the stage-1 rewrite taught -- no call ABI around the Gram-row loads
 // (the __noinline__ solver re-materialised its global-memory descriptor before every load), 32-bit offsets, 64-bit
 // shuffles without the register swaps, no coefficient vector.
+// sum_{c < n} M(r, c) v[c] for the packed symmetric matrix M (see sym_row_dot), with running indices instead of tri() per term
+__device__ __forceinline__ double sym_row_dot_lean(const double *Mi, const int r, const int n, const double *v)
+{
+    double acc = 0.0;
+    const double *prow = Mi + tri(r, 0);  // (r, c), c < r
+    const double *pcol = Mi + r;          // (c, r), c >= r: at tri(c, 0) + r
+    int step = 1;
+#pragma unroll 1
+    for (int c = 0; c < n; ++c) {
+        acc = fma(*(c < r ? prow : pcol), v[c], acc);
+        ++prow;
+        pcol += step++;
+    }
+    return acc;
+}
+
 template <int NPL>
 struct Lars2WS {  // per-warp workspace of stage 2 (doubles), active-set capacity LC
     static constexpr int DTR = 0, MI = 32 * NPL, U = MI + LC * (LC + 1) / 2, GS = U + LC, IND = GS + LC, BX = IND + LC / 2, SIZE = BX + BV;
@@ -770,7 +786,7 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
             } else {
                 double ur = 0.0;
                 if (lane < i) {
-                    ur = sym_row_dot(Mi, lane, i, gs);
+                    ur = sym_row_dot_lean(Mi, lane, i, gs);
                     u[lane] = ur;
                 }
                 double dot = lane < i ? ur * g : 0.0, usum = lane < i ? ur : 0.0;  // two interleaved butterfly sums
@@ -786,9 +802,13 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
                 __syncwarp();
                 if (lane < i) {
                     const double su = schur * ur;
+                    double *mp = Mi + tri(lane, lane);  // element (k, lane), k = lane..: the packed index grows by k + 1 per row
 #pragma unroll 1
-                    for (int k = lane; k < i; ++k) Mi[tri(k, lane)] = fma(su, u[k], Mi[tri(k, lane)]);
-                    Mi[tri(i, lane)] = -su;
+                    for (int k = lane; k < i; ++k) {
+                        *mp = fma(su, u[k], *mp);
+                        mp += k + 1;
+                    }
+                    *mp = -su;  // = Mi[tri(i, lane)]
                 }
                 if (lane == i) Mi[tri(i, i)] = schur;
             }
@@ -813,7 +833,7 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
                 u[lane] = ul;
             }
         } else if (lane <= i) {
-            ul = sym_row_dot(Mi, lane, i + 1, gs);
+            ul = sym_row_dot_lean(Mi, lane, i + 1, gs);
             u[lane] = ul;
         }
         __syncwarp();
@@ -831,22 +851,28 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
         double sl[NPL];
 #pragma unroll
         for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
-        constexpr int GD = (NPL <= 2) ? 4 : AMX_GD;
+        {   // two rows in flight, accumulated in path order
+            const double *Tl = T + lane;
+            int j = 0;
 #pragma unroll 1
-        for (int j0 = 0; j0 <= i; j0 += GD) {
-            double gq[GD][NPL];
+            for (; j + 2 <= i + 1; j += 2) {
+                const double *r0 = Tl + (unsigned)(ind[j] * ldT), *r1 = Tl + (unsigned)(ind[j + 1] * ldT);
+                double g0[NPL], g1[NPL];
 #pragma unroll
-            for (int q = 0; q < GD; ++q) {
-                const double *row = T + (unsigned)(ind[min(j0 + q, i)] * ldT + lane);
+                for (int s = 0; s < NPL; ++s) g0[s] = r0[32 * s];  // columns >= K: finite values of the next row / the padding,
 #pragma unroll
-                for (int s = 0; s < NPL; ++s) gq[q][s] = row[32 * s];  // columns >= K: finite values of the next row / the padding,
-                                                                       // only ever combined into slots that are masked by k < K
+                for (int s = 0; s < NPL; ++s) g1[s] = r1[32 * s];  // only ever combined into slots that are masked by k < K
+                const double u0 = u[j], u1 = u[j + 1];
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) sl[s] = fma(g0[s], u0, sl[s]);
+#pragma unroll
+                for (int s = 0; s < NPL; ++s) sl[s] = fma(g1[s], u1, sl[s]);
             }
+            if (j <= i) {
+                const double *r0 = Tl + (unsigned)(ind[j] * ldT);
+                const double u0 = u[j];
 #pragma unroll
-            for (int q = 0; q < GD; ++q) {
-                const double uj = (j0 + q <= i) ? u[j0 + q] : 0.0;
-#pragma unroll
-                for (int s = 0; s < NPL; ++s) sl[s] = fma(gq[q][s], uj, sl[s]);
+                for (int s = 0; s < NPL; ++s) sl[s] = fma(r0[32 * s], u0, sl[s]);
             }
         }
         // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index.  Each lane first
@@ -1231,7 +1257,7 @@ template <int CAPT>
 __host__ __device__ constexpr int tpv3_smem_bytes() { return TPV_THREADS * (TpvWS<CAPT>::BYTES_PER_THREAD + 32); }
 
 template <int NPL, int CAPT>
-__global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParams p, int4 *redo, int *redo_count)
+__global__ void __launch_bounds__(TPV_THREADS, 4) k_noddi_stage3_tpv(const FitParams p, int4 *redo, int *redo_count)
 {
     constexpr int NTH = TPV_THREADS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1247,6 +1273,7 @@ __global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParam
         const int dir = active ? p.lut[vox] : 0;
         const double *T = p.T1 + (size_t)dir * p.T1_stride;
         const double *cg = p.c1_all + (size_t)(active ? pos : 0) * NA;
+        asm volatile("" : "+l"(T), "+l"(cg));  // opaque: held in registers, not re-derived from the kernel parameters at every load
         int ns = 0;
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
@@ -1280,10 +1307,24 @@ __global__ void __launch_bounds__(TPV_THREADS) k_noddi_stage3_tpv(const FitParam
                     // dual w = c - T[:,P] x_P over the still valid atoms, largest positive one (ties: lowest index)
                     double bv = 0.0;
                     j = -1;
+                    int prow[CAPT];     // row offsets of the passive atoms and their coefficients, in registers:
+                    double xk[CAPT];    // the Gram entries of an atom are then loaded together, not one per dependent step
+#pragma unroll
+                    for (int k = 0; k < CAPT; ++k) {
+                        const bool on = k < np;
+                        prow[k] = on ? atom_of(k) * ldT : 0;
+                        xk[k] = on ? ws.xs[k][tid] : 0.0;
+                    }
                     for (unsigned mm = valid; mm; mm &= mm - 1) {
                         const int a = __ffs(mm) - 1, atom = sa[a][tid];
+                        const double *Ta = T + atom;
                         double w = cg[atom];
-                        for (int k = 0; k < np; ++k) w = fma(-T[(unsigned)(atom_of(k) * ldT + atom)], ws.xs[k][tid], w);
+                        double gk[CAPT];
+#pragma unroll
+                        for (int k = 0; k < CAPT; ++k) gk[k] = (k < np) ? Ta[prow[k]] : 0.0;
+#pragma unroll
+                        for (int k = 0; k < CAPT; ++k)
+                            if (k < np) w = fma(-gk[k], xk[k], w);
                         if (w > bv) { bv = w; j = a; }
                     }
                     if (j < 0) { pend = false; run = false; }
