@@ -579,11 +579,16 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     FitParams p3 = p;
     if (tpv3) {
         // one voxel per thread (amx_lean.cuh); what it hands back runs through the warp-per-voxel kernel as one-voxel tiles
-        auto kt = k_noddi_stage3_tpv<NPL, 6>;
-        constexpr int smem_t = tpv3_smem_bytes<6>();
-        CK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
         const long long blocks = std::max<long long>(1, std::min<long long>((p.n_vox + TPV_THREADS - 1) / TPV_THREADS, (long long)grid * 64));
-        kt<<<(int)blocks, TPV_THREADS, smem_t, st>>>(p, p.redo_tiles, p.redo_count + 2);
+        auto launch_t3 = [&](auto kt, int smem_t) -> int {
+            CK(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_t));
+            kt<<<(int)blocks, TPV_THREADS, smem_t, st>>>(p, p.redo_tiles, p.redo_count + 2);
+            return AMX_OK;
+        };
+        // AMX_TPV3_CAP = 3: test hook, most voxels outgrow the per-thread capacity and take the hand-back path
+        if (int rc3 = env_int("AMX_TPV3_CAP", 6) <= 3 ? launch_t3(k_noddi_stage3_tpv<NPL, 3>, tpv3_smem_bytes<3>())
+                                                      : launch_t3(k_noddi_stage3_tpv<NPL, 6>, tpv3_smem_bytes<6>()))
+            return rc3;
         p3.tiles = p.redo_tiles;
         p3.n_tiles_ptr = p.redo_count + 2;
         p3.tile_counter = p.redo_count + 3 - 2;  // stage 3 pulls from tile_counter[2]
@@ -853,7 +858,7 @@ int fit_device(amx_plan *pl, amx_plan::Work &wk, const amx_fit_args *a, cudaStre
             CK(wk.c1_all.reserve(c1_bytes));
             p.c1_all = (double *)wk.c1_all.p;
         }
-        p.tpv3 = env_int("AMX_TPV3", 1) && p.c1_all && !p.coeff_out && !(p.flags & (FLAG_RMSE | FLAG_NRMSE)) && p.n <= 255;
+        p.tpv3 = env_int("AMX_TPV3", 1) && p.c1_all && p.n <= 255;
         p.tpv1 = env_int("AMX_TPV1", 0) && p.c1_all && p.cap_stage[0] <= 16 && p.n <= 255;
         p.ovf_cap = 4 * n_vox;
         CK(wk.ovf_list.reserve((size_t)p.ovf_cap * sizeof(int)));

@@ -1393,6 +1393,51 @@ __global__ void __launch_bounds__(TPV_THREADS, 4) k_noddi_stage3_tpv(const FitPa
                 p.extra[2 * vox + 1] = odi * tf;
             }
             if (p.support_out) p.support_out[vox] = ns;
+            if (p.coeff_out || (p.flags & (FLAG_RMSE | FLAG_NRMSE))) {
+                // passive atoms in ascending atom order (<= CAPT of them)
+                int sat[CAPT];
+                double sxv[CAPT];
+                unsigned mm = inP;
+#pragma unroll
+                for (int q = 0; q < CAPT; ++q) {
+                    const bool on = mm != 0u;
+                    const int a = on ? __ffs(mm) - 1 : 0;
+                    mm &= mm - 1;
+                    sat[q] = on ? (int)sa[a][tid] : 0;
+                    sxv[q] = on ? xof(a) : 0.0;
+                }
+                if (p.coeff_out) {
+                    double *co = p.coeff_out + vox * p.n;
+                    for (int jj = 0; jj < p.n; ++jj) co[jj] = 0.0;
+#pragma unroll
+                    for (int q = 0; q < CAPT; ++q)
+                        if (q < np) co[sat[q]] = sxv[q];
+                }
+                if (p.flags & (FLAG_RMSE | FLAG_NRMSE)) {  // fit_errors (amico/models.pyx:45-71), same operation order
+                    const float *S = (const float *)p.slab + (size_t)dir * p.slab_stride;
+                    const float *yf = (const float *)p.y + vox * m;
+                    const double *yd = (const double *)p.y + vox * m;
+                    double den = 0.0;
+                    if (p.flags & FLAG_NRMSE)
+                        for (int i = 0; i < m; ++i) {
+                            const double yi = p.y_f64 ? yd[i] : (double)yf[i];
+                            den = madd(den, yi, yi);
+                        }
+                    double acc_r = 0.0, acc_n = 0.0;
+                    for (int i = 0; i < m; ++i) {
+                        const float *Si = S + (size_t)i * p.n_pad;
+                        double ye = 0.0;
+#pragma unroll
+                        for (int q = 0; q < CAPT; ++q)
+                            if (q < np && sxv[q] != 0.0) ye = madd(ye, (double)Si[sat[q]], sxv[q]);
+                        const double d = (p.y_f64 ? yd[i] : (double)yf[i]) - ye, dq = d * d;
+                        acc_r += dq / (double)m;
+                        if (den > 1e-16) acc_n += dq / den;
+                    }
+                    if (p.flags & FLAG_RMSE) p.rmse[vox] = sqrt(acc_r);
+                    if (p.flags & FLAG_NRMSE) p.nrmse[vox] = den > 1e-16 ? sqrt(acc_n) : 0.0;
+                }
+            }
         }
         if (redo_me) {
             const int slot = atomicAdd(redo_count, 1);

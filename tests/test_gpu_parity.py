@@ -463,6 +463,23 @@ def test_noddi_kernel_variants_agree(monkeypatch, env):
     assert pass_fraction(alt["estimates_mod"], base["estimates_mod"]) >= 0.999
 
 
+@pytest.mark.parametrize("env", [{"AMX_TPV3": "0"}, {"AMX_LEAN1": "0", "AMX_LEAN2": "0"}, {"AMX_TPV3_CAP": "3"}, {"AMX_TPV1": "1"},
+                                 {"AMX_TPV1": "1", "AMX_TPV1_CAP": "6"}, {"AMX_PAIR1": "1"}])
+def test_noddi_second_generation_kernels_are_bit_identical(monkeypatch, env):
+    """The second-generation stage kernels (amx_lean.cuh: inlined lean solvers for stages 1 / 2, one voxel per thread for stage 3 --
+    the defaults -- and the opt-in stage-1 variants) run the same floating-point operations in the same order as the warp-per-voxel
+    kernels they replace: maps, RMSE / NRMSE, coefficients and supports are EQUAL, also through the hand-back path of the
+    thread-per-voxel kernels (AMX_TPV3_CAP = 3: most voxels outgrow the per-thread capacity and are re-fitted by k_noddi_stage<3>)."""
+    P = synth.make_problem(2, n_vox=20000, seed=21)
+    base = gpu_fit(P, debug=True, rmse=True, nrmse=True, extra=True)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    alt = gpu_fit(P, debug=True, rmse=True, nrmse=True, extra=True)
+    for k in ("estimates", "estimates_mod", "rmse", "nrmse", "x", "support", "lut"):
+        assert np.array_equal(base[k], alt[k]), k
+    assert alt["_counters"]["overflow_voxels"] == 0
+
+
 def test_noddi_whole_brain_protocol_m288():
     """cfg3 protocol (18 b0 + 2x135 directions, m = 288): same kernels, bigger rows."""
     P = synth.make_problem(3, n_vox=6000)
