@@ -359,7 +359,8 @@ class Evaluation:
         self.KERNELS = KERNELS
         if htable is not None:
             self.htable = htable
-        self.model.invalidate_plan()  # new tables: the device copies follow
+        # the plan cache is keyed on the tables' content (models._fingerprint): new tables are noticed at the next fit, equal ones
+        # (the usual multi-subject loop re-loading the same kernels) keep their device copies
 
     # ------------------------------------------------------------------ fit (core.py:407-498)
     @property

@@ -559,7 +559,7 @@ def main():
     maps = parallel.gather_maps(est_dev, rank, world)
     checksum = float(maps.sum().item()) if maps is not None else None
 
-    fit_kernel_name = ("amx::k_noddi_stage<1|2|3> (NNLS / LARS / NNLS+maps stage kernels, timed as one span)"
+    fit_kernel_name = ("amx::k_noddi_stage1_lean | k_noddi_stage2_lean | k_noddi_stage3_tpv (NNLS / LARS / NNLS+maps stage kernels, timed as one span)"
                        if mid == "NODDI" else "amx::k_fit (fused per-voxel fit)")
     line = None
     plan_n_atoms = plan.n_atoms
@@ -597,8 +597,9 @@ def main():
             try:
                 nv = int(ks[0].get("n_vox", 1048576))
                 # scalar FP64 flop from the ncu thread-instruction counters + the DMMA flop of the three A^T Y micro-GEMMs
-                # (2 x rows x 32 NPL padded atoms per voxel: stages 1 and 3 over m rows, stage 2 over the DWI rows)
-                dmma = 2.0 * (2 * m + P.scheme.dwi_count) * 32 * ((plan_n_atoms + 31) // 32)
+                # (2 x rows x 32 NPL padded atoms per voxel: stage 1 over m rows, stage 2 over the DWI rows)
+                # (stage 3 reads the c1 stage 1 stored, so two GEMMs per voxel: m rows + the DWI rows)
+                dmma = 2.0 * (m + P.scheme.dwi_count) * 32 * ((plan_n_atoms + 31) // 32)
                 flops = sum(float(k["fp64_flop_scalar"]) for k in ks) / nv + dmma
                 winst = sum(float(k["smsp__inst_executed.sum"]) for k in ks) / nv
                 vps = n_vox / k_s

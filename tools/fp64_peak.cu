@@ -4,7 +4,7 @@
 //   kind 0: DFMA   -- 8 independent fma chains per thread (2 flop per lane and instruction)
 //   kind 1: DMMA   -- mma.sync.m8n8k4.f64 (the instruction the A^T Y micro-GEMMs use), 4 independent accumulators
 //                     per warp (8*8*4*2 = 512 flop per warp and instruction)
-//   kind 2: issue  -- independent integer IMAD chains: warp instructions per second (the issue-slot roofline)
+//   kind 2: issue  -- independent integer LOP3 / IADD3 chains: warp instructions per second (the issue-slot roofline)
 //
 // Built by __graft_entry__.build() into tools/libfp64peak.so; called by bench.py through ctypes.
 #include <cuda_runtime.h>
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) k_issue(double *out, int iters, int a, in
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = x[i] * a + b;
+            for (int i = 0; i < 8; ++i) x[i] = (x[i] ^ a) + b;  // LOP3 + IADD3: full-rate ALU instructions (IMAD issues at half rate)
         }
     }
     int s = 0;
@@ -106,6 +106,6 @@ extern "C" int fp64_peak(int device, int kind, double *result)
     const double threads = (double)grid * block, warps = threads / 32.0, n_inst = (double)iters * 8.0;
     if (kind == 0) *result = threads * n_inst * 8.0 * 2.0 / (best * 1e-3) / 1e12;
     else if (kind == 1) *result = warps * n_inst * 4.0 * 512.0 / (best * 1e-3) / 1e12;
-    else *result = warps * n_inst * 8.0 / (best * 1e-3) / 1e12;
+    else *result = warps * n_inst * 8.0 * 2.0 / (best * 1e-3) / 1e12;  // two instructions per element and step
     return 0;
 }
