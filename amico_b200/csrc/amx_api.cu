@@ -958,8 +958,13 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     const size_t n = (size_t)a->n_vox, m = (size_t)pl->m, nm = (size_t)pl->n_maps;
     const size_t ysz = a->y_dtype == AMX_F64 ? 8 : 4;
     const size_t extra_w = has_extra ? (pl->model == AMX_MODEL_NODDI ? 2 : m) : 0;
-    cudaStream_t st = pl->stream;  // the caller's stream: everything is ordered after / joined back into it
-    if (!host && a->stream) st = (cudaStream_t)a->stream;
+    // The caller's stream: everything is ordered after / joined back into it.  Device-resident inputs are produced by the caller's
+    // own stream-ordered work, so a NULL stream means the LEGACY DEFAULT stream (what a cudaStream_t of 0 denotes everywhere else,
+    // and what PyTorch hands out as its default stream), never the plan's private non-blocking stream: running there let a fit
+    // start while the default stream was still writing y / dirs (seen as garbage maps of the first fit after a long-running
+    // producer, and as NaNs in the sharded bench).  Host buffers: the plan's own stream.
+    cudaStream_t st = pl->stream;
+    if (!host) st = a->stream ? (cudaStream_t)a->stream : cudaStreamLegacy;
 
     // The volume is cut into voxel chunks that alternate between two compute streams (each with its own workspace):
     // the ragged end of one chunk's stage kernels is filled by the next chunk's kernels, and for host buffers the
@@ -1147,6 +1152,11 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     long long h_status[2][8] = {{0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}, {0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}};
     for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(h_status[b], pl->work[b].status.p, sizeof h_status[b], cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (env_int("AMX_DEBUG_TOTALS", 0) && pl->work[0].bins.p) {  // diagnostics: tile count, binned voxels and the three queue heads of work set 0
+        int h_tot[6] = {0, 0, 0, 0, 0, 0};
+        cudaMemcpy(h_tot, (int *)pl->work[0].bins.p + 4 * pl->ndirs, sizeof h_tot, cudaMemcpyDeviceToHost);
+        for (int k = 0; k < 6; ++k) pl->last_cnt[10 + k] = h_tot[k];
+    }
     {   // pageable outputs: pinned landing buffers -> the caller's arrays
         double *user[4] = {a->estimates, a->dirs, a->rmse, a->nrmse};
         const size_t bytes[4] = {n * nm * sizeof(double), n * 3 * sizeof(double), n * sizeof(double), n * sizeof(double)};

@@ -1,6 +1,9 @@
 // Device kernels of the per-voxel fit: LUT index + binning, table construction, fused fit.
 #pragma once
 #include "amx_solvers.cuh"
+#ifndef AMX_GEMM_INLINE
+#define AMX_GEMM_INLINE __noinline__
+#endif
 
 namespace amx {
 
@@ -384,7 +387,7 @@ __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b)
 // c1[v][k] = sum_r y_v[r] A[r][k] for the batch's voxels -> out[v * NA + k]   (NODDI stage 1 / stage 3 right-hand side)
 // normy (optional): ||y_v||^2 of the batch's voxels -> normy[v]
 template <int NT, int TP, typename TS>
-__device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *y, int y_f64, long long myvox, bool vvalid,
+__device__ AMX_GEMM_INLINE void gemm_c1(const TS *S, int n_pad, int m, const void *y, int y_f64, long long myvox, bool vvalid,
                                      double *out, int NA, int lane, double *normy = nullptr)
 {
     const int kk = lane & 3, g = lane >> 2;
@@ -424,7 +427,7 @@ __device__ __noinline__ void gemm_c1(const TS *S, int n_pad, int m, const void *
 // NODDI stage 2 right-hand side for the batch: y2 = max(y_R - x_iso iso_R [- x_dot], 0) (amico/models.pyx:918-925),
 // c2[v][k] = sum_j (A[R_j][k] norms[j][k]) y2_v[j]; also ||y2_v||^2 -> normx[v].
 template <int NT, int TP, typename TS, bool NC>
-__device__ __noinline__ void gemm_c2(const TS *S, int n_pad, int n, int n_wm, int dc, const int *__restrict__ rows, const void *y,
+__device__ AMX_GEMM_INLINE void gemm_c2(const TS *S, int n_pad, int n, int n_wm, int dc, const int *__restrict__ rows, const void *y,
                                      int y_f64, int m, long long myvox, bool vvalid, double xiso, double xdot, int exvivo,
                                      const double *__restrict__ norms, int ldn, double *out, int NA, double *normx, int lane)
 {

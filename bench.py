@@ -393,6 +393,10 @@ def sharded_cfg3(rank, world, dev, steps):
         allt = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(allt, t)
         fit_ms.append([float(a[0]) for a in allt]); gather_ms.append(max(float(a[1]) for a in allt)); tot_ms.append(max(float(a[2]) for a in allt))
+    # diagnostics: non-finite values in this rank's own maps (before the gather) next to those in the gathered volume
+    nf = torch.tensor([float((~torch.isfinite(est)).sum().item())], dtype=torch.float64, device=dev)
+    nf_all = [torch.empty_like(nf) for _ in range(world)]
+    dist.all_gather(nf_all, nf)
     plan.close()
     if rank != 0:
         return None
@@ -402,6 +406,7 @@ def sharded_cfg3(rank, world, dev, steps):
             "broadcast_ms": 1e3 * t_bcast_nccl, "fit_ms_per_rank": [float(x) for x in np.mean(np.array(fit_ms), axis=0)],
             "gather_ms": float(np.mean(gather_ms)), "gather_bytes": int(n_total * 3 * 4), "ms_per_volume": tot,
             "voxels_per_s": n_total / tot * 1e3, "checksum": float(torch.nan_to_num(maps).sum().item()), "nan_values": int(torch.isnan(maps).sum().item()),
+            "nonfinite_per_rank_before_gather": [int(x.item()) for x in nf_all],
             "what": "per step: barrier, fit of the rank's slab (device-resident), NCCL gather of the float32 maps on rank 0; max over ranks"}
 
 

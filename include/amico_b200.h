@@ -126,7 +126,7 @@ typedef struct amx_fit_args {
     int32_t *support_out; /* optional out [n_vox]: NODDI stage-2 support size incl. iso(/dot);
                              other models: number of non-zero coefficients */
     double *coeff_out;    /* optional out [n_vox][n_atoms]: the fitted coefficients x (diagnostics / tests) */
-    void *stream;    /* cudaStream_t to run on (AMX_SPACE_DEVICE); NULL = the plan's own stream */
+    void *stream;    /* cudaStream_t to run on (AMX_SPACE_DEVICE); NULL = the legacy default stream (stream 0) */
 } amx_fit_args;
 
 /* Fit every voxel.  Synchronous for AMX_SPACE_HOST; for AMX_SPACE_DEVICE the work is enqueued on

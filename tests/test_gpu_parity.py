@@ -480,6 +480,29 @@ def test_noddi_second_generation_kernels_are_bit_identical(monkeypatch, env):
     assert alt["_counters"]["overflow_voxels"] == 0
 
 
+def test_device_fit_is_ordered_after_the_callers_stream():
+    """Device-resident inputs are produced by stream-ordered work of the caller (here: torch's default stream, whose handle is 0).
+    The fit must be ordered after it -- a NULL stream is the legacy default stream, not a private non-blocking one -- or it reads
+    y / dirs while they are still being written and its maps are overwritten by the caller's pending fill of the output."""
+    import torch
+    from amico_b200.plan import Plan
+    P = synth.make_problem(2, n_vox=8)
+    l1, l2 = orc().DEFAULT_LAMBDAS["NODDI"]
+    dev = torch.device("cuda:0")
+    n = 1 << 20
+    with Plan("NODDI", P.KERNELS, P.htable, P.params, dwi_idx=P.scheme.dwi_idx, device=0) as plan:
+        torch.cuda.synchronize()
+        y, d = synth.make_voxels_torch("NODDI", P.KERNELS, P.htable, n, 77, dev)   # asynchronous producer, no synchronisation below
+        est = torch.full((n, 3), 777.0, dtype=torch.float64, device=dev)
+        plan.fit(y, d, l1, l2, out=est)
+        torch.cuda.synchronize()
+        assert bool((est != 777.0).all()) and bool(torch.isfinite(est).all())
+        again = torch.empty_like(est)
+        plan.fit(y, d, l1, l2, out=again)
+        torch.cuda.synchronize()
+        assert torch.equal(est, again)
+
+
 def test_noddi_whole_brain_protocol_m288():
     """cfg3 protocol (18 b0 + 2x135 directions, m = 288): same kernels, bigger rows."""
     P = synth.make_problem(3, n_vox=6000)
