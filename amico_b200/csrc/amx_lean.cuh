@@ -12,22 +12,9 @@
 
 namespace amx {
 
-// 64-bit shuffle as two 32-bit shuffles with plain moves around them (the header's version packs through volatile asm,
-// which made ptxas emit a three-XOR register swap after every use in the substitution loops)
-__device__ __forceinline__ double shfl2(double v, int src)
-{
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_sync(FULL, lo, src);
-    hi = __shfl_sync(FULL, hi, src);
-    return __hiloint2double(hi, lo);
-}
-__device__ __forceinline__ double shfl2_xor(double v, int m)
-{
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_xor_sync(FULL, lo, m);
-    hi = __shfl_xor_sync(FULL, hi, m);
-    return __hiloint2double(hi, lo);
-}
+// 64-bit shuffles: amx_warp.cuh (two 32-bit shuffles, no volatile asm pack)
+__device__ __forceinline__ double shfl2(double v, int src) { return shfl(v, src); }
+__device__ __forceinline__ double shfl2_xor(double v, int m) { return shfl_xor(v, m); }
 
 // per-warp workspace of the lean NNLS (doubles): packed factor, x by passive position, passive list, batch ||y||^2
 template <int CAP>
@@ -744,6 +731,9 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
 #pragma unroll
     for (int s = 0; s < NPL; ++s) sup[s] = 0u;
     if (L <= 0) return 0;
+    unsigned kin = 0u;  // bit s: atom lane + 32 s exists
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) kin |= (lane + 32 * s < K ? 1u : 0u) << s;
     int cur;
     {
         double bv = 0.0;
@@ -879,16 +869,14 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
         // picks the best of its own atoms by cross-multiplication (|a/b| < |c/d| <=> |a| d < |c| b for b, d > 0), so only one
         // reciprocal per lane and step is needed.
         double bnum = 0.0, bden = 0.0;  // best candidate of this lane: step = bnum / bden (bden > 0), none while bden == 0
-        int mk = -1;                    // its atom; lanes without a candidate still offer their lowest atom (step = inf)
+        int mk = lane < K ? lane : -1;  // its atom; lanes without a candidate still offer their lowest atom (step = inf)
+        const unsigned open_ = kin & ~act;  // bit s: atom lane + 32 s exists and is not active
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
-            const int k = lane + 32 * s;
-            if (k < K) {
-                if (mk < 0) mk = k;
-                if (!((act >> s) & 1u) && sl[s] < 1.0) {
-                    const double num = cc - DtR[k], den = 1.0 - sl[s];
-                    if (bden == 0.0 || fabs(num) * bden < fabs(bnum) * den) { bnum = num; bden = den; mk = k; }
-                }
+            if (((open_ >> s) & 1u) && sl[s] < 1.0) {
+                const int k = lane + 32 * s;
+                const double num = cc - DtR[k], den = 1.0 - sl[s];
+                if (bden == 0.0 || fabs(num) * bden < fabs(bnum) * den) { bnum = num; bden = den; mk = k; }
             }
         }
         const double mine = bden != 0.0 ? bnum * __drcp_rn(bden) : INFINITY;
@@ -912,10 +900,8 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
             if (coef_l < 0.0) coef_l = 0.0;
         }
 #pragma unroll
-        for (int s = 0; s < NPL; ++s) {
-            int k = lane + 32 * s;
-            if (k < K) DtR[k] = fma(-step, sl[s], DtR[k]);
-        }
+        for (int s = 0; s < NPL; ++s)
+            if ((kin >> s) & 1u) DtR[lane + 32 * s] = fma(-step, sl[s], DtR[lane + 32 * s]);
         normX += coeff1 * step * step - 2.0 * coeff2 * step;
         __syncwarp();
         if (step == step_max) {

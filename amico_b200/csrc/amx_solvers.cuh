@@ -186,8 +186,8 @@ __device__ AMX_SOLVER_INLINE int warp_nnls(const double *__restrict__ T, int ldT
             double vv = v * v, vz = v * zl;  // both 0 beyond np (v is); two interleaved butterfly sums
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                vv += __shfl_xor_sync(FULL, vv, o);
-                vz += __shfl_xor_sync(FULL, vz, o);
+                vv += shfl_xor(vv, o);
+                vz += shfl_xor(vz, o);
             }
             const double hjj = T[(size_t)AT(j) * (ldT + 1)];
             d2 = hjj - vv;
@@ -621,8 +621,8 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
                 double dot = lane < i ? ur * g : 0.0, usum = lane < i ? ur : 0.0;  // two interleaved butterfly sums
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
-                    dot += __shfl_xor_sync(FULL, dot, o);
-                    usum += __shfl_xor_sync(FULL, usum, o);
+                    dot += shfl_xor(dot, o);
+                    usum += shfl_xor(usum, o);
                 }
                 const double schur = 1.0 / (shfl(g, i) - dot);
                 // row sums of the inverse after the Schur update: old rows += schur u_r (sum(u) - 1), new row = schur (1 - sum(u))
@@ -720,8 +720,8 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         double coeff1 = lane <= i ? sg * ul : 0.0, coeff2 = lane <= i ? dl * ul : 0.0;  // two interleaved butterfly sums
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-            coeff1 += __shfl_xor_sync(FULL, coeff1, o);
-            coeff2 += __shfl_xor_sync(FULL, coeff2, o);
+            coeff1 += shfl_xor(coeff1, o);
+            coeff2 += shfl_xor(coeff2, o);
         }
         const double step_max2 = cc - lambda1;
         step = fmin(fmin(step, step_max2), step_max);
@@ -880,7 +880,7 @@ __device__ __noinline__ bool warp_nnqp_dense(const double *__restrict__ Hd, int 
         g = fma(h1, shfl(x, min(k + 1, n - 1)), g);
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, __shfl_xor_sync(FULL, scale, o));
+    for (int o = 16; o > 0; o >>= 1) scale = fmax(scale, shfl_xor(scale, o));
     const double tol = 1e-10 * scale;
     const bool bad = in && ((x > 0.0) ? (fabs(g) > tol) : (x < 0.0 || g < -tol));
     if (__any_sync(FULL, bad)) return false;

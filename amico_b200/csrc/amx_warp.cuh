@@ -14,12 +14,28 @@ __constant__ int c_lc_cap = LC;
 
 __device__ __forceinline__ int tri(int r, int c) { return ((r * (r + 1)) >> 1) + c; }  // r >= c
 
-__device__ __forceinline__ double shfl(double v, int src) { return __shfl_sync(FULL, v, src); }
+// 64-bit shuffles as two 32-bit shuffles with plain moves around them: the header's double overload packs its result through
+// volatile asm, after which ptxas emitted a three-XOR register swap per use in the substitution loops (5 % of the instructions of
+// the first-generation NODDI stage 1, tools/ncu_sass_annot.py).
+__device__ __forceinline__ double shfl(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(FULL, lo, src);
+    hi = __shfl_sync(FULL, hi, src);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor(double v, int m)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(FULL, lo, m);
+    hi = __shfl_xor_sync(FULL, hi, m);
+    return __hiloint2double(hi, lo);
+}
 
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor(v, o);
     return v;
 }
 

@@ -1,4 +1,7 @@
 set -x
-python tools/nan_probe3.py 23 2>&1 | grep '"cfg": 3' | sed 's/"timing".*"counters"/"counters"/' | cut -c1-200
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "ordered_after or second_generation or at_scale" 2>&1 | tail -3
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
 bash tools/bench_sweep.sh "AMX_LEAN2=1" 2>&1 | tail -1
+timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-pipeline --no-configs 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('checksum', repr(d['maps_checksum']))"
+python tools/bench_models.py 1048576 2>&1 | tail -3; python -c "
+import json; d=json.load(open('gpurun_out/bench_models.json'))
+for k,v in d.items(): print(k, round(v['voxels_per_s']/1e6,1))"
