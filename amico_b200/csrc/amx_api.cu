@@ -586,8 +586,10 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
             return AMX_OK;
         };
         // AMX_TPV3_CAP = 3: test hook, most voxels outgrow the per-thread capacity and take the hand-back path
-        if (int rc3 = env_int("AMX_TPV3_CAP", 6) <= 3 ? launch_t3(k_noddi_stage3_tpv<NPL, 3>, tpv3_smem_bytes<3>())
-                                                      : launch_t3(k_noddi_stage3_tpv<NPL, 6>, tpv3_smem_bytes<6>()))
+        const int cap3 = env_int("AMX_TPV3_CAP", 6);
+        if (int rc3 = cap3 <= 3   ? launch_t3(k_noddi_stage3_tpv<NPL, 3>, tpv3_smem_bytes<3>())
+                      : cap3 == 5 ? launch_t3(k_noddi_stage3_tpv<NPL, 5>, tpv3_smem_bytes<5>())
+                                  : launch_t3(k_noddi_stage3_tpv<NPL, 6>, tpv3_smem_bytes<6>()))
             return rc3;
         p3.tiles = p.redo_tiles;
         p3.n_tiles_ptr = p.redo_count + 2;

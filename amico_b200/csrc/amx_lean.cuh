@@ -40,7 +40,9 @@ __device__ __forceinline__ int nnls_lean(const double *__restrict__ T, const int
     int myP = 0;                           // atom at this lane's passive position (mirror of P[lane])
 #pragma unroll
     for (int s = 0; s < NPL; ++s) avail |= (lane + 32 * s < n ? 1u : 0u) << s;
+    asm volatile("" : "+r"(avail));  // opaque: otherwise re-derived from lane and n in every outer iteration (3 % of the instructions)
     const double *Tl = T + lane;
+    asm volatile("" : "+l"(Tl));     // likewise the table pointer (re-built from the kernel parameters before every row otherwise)
     double *myrow = Lp + tri(lane, 0);  // this lane's row of the factor (dereferenced only while lane < np <= CAP)
     for (;;) {
         if (np >= mcap) break;
@@ -85,7 +87,7 @@ __device__ __forceinline__ int nnls_lean(const double *__restrict__ T, const int
             warp_argmax_pos(bv, bj);
             j = bj;
             if (j < 0) break;
-            const double *Tj = T + (unsigned)(j * ldT);
+            const double *Tj = Tl + (j * ldT - lane);  // = T + j ldT, from the pointer that is held in registers
             double t = (lane < np) ? Tj[myP] : 0.0;  // = T[P[lane]][j] (the table is exactly symmetric)
             const double hjj = Tj[j], cj = cs[j];
 #pragma unroll 1
@@ -734,6 +736,9 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
     unsigned kin = 0u;  // bit s: atom lane + 32 s exists
 #pragma unroll
     for (int s = 0; s < NPL; ++s) kin |= (lane + 32 * s < K ? 1u : 0u) << s;
+    asm volatile("" : "+r"(kin));  // opaque: kept in a register instead of being re-derived in every step
+    const double *Tq = T;
+    asm volatile("" : "+l"(Tq));   // likewise the table pointer
     int cur;
     {
         double bv = 0.0;
@@ -766,7 +771,7 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
             __syncwarp();
             double g = 0.0;
             if (lane <= i) {
-                g = T[(unsigned)(cur * ldT + ind_l)];
+                g = Tq[(unsigned)(cur * ldT + ind_l)];
                 gs[lane] = g;
             }
             __syncwarp();
@@ -830,19 +835,23 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
         // largest step before an active coefficient crosses zero (last index wins ties)
         double step_max = INFINITY;
         int fz = -1;
-        if (lane <= i) {
-            double r = -coef_l / ul;
-            if (r > 0.0) { step_max = r; fz = lane; }
+        // r = -coef / u is positive only for a positive coefficient that decreases (u < 0): most steps have none, and the fp64
+        // division is a ~30-instruction subroutine the whole warp would walk through -- skip it (and the arg-min) then
+        if (__any_sync(FULL, lane <= i && coef_l > 0.0 && ul < 0.0)) {
+            if (lane <= i) {
+                double r = -coef_l / ul;
+                if (r > 0.0) { step_max = r; fz = lane; }
+            }
+            warp_argmin<false>(step_max, fz);
+            if (fz < 0) step_max = INFINITY;
         }
-        warp_argmin<false>(step_max, fz);
-        if (fz < 0) step_max = INFINITY;
         const double cc = fabs(shfl2(dl, 0));
         // correlation slopes T[:, S] u; rows are L2-resident: fetch GD rows at a time
         double sl[NPL];
 #pragma unroll
         for (int s = 0; s < NPL; ++s) sl[s] = 0.0;
         {   // two rows in flight, accumulated in path order
-            const double *Tl = T + lane;
+            const double *Tl = Tq + lane;
             int j = 0;
 #pragma unroll 1
             for (; j + 2 <= i + 1; j += 2) {
@@ -1103,25 +1112,43 @@ __device__ __forceinline__ void tpv_aspace_service(const TpvWS<CAPT> &ws, const 
         const float *S = (const float *)p.slab + (size_t)r_dir * p.slab_stride;
         const float *Sj = S + r_atomj;
         double a2 = 0.0, ay = 0.0;
+        // four row chunks (128 rows) per trip, every chunk's dictionary loads in flight together; each row's residual and the two
+        // per-lane sums are accumulated in the order warp_nnls uses (passive atoms in pairs, rows lane, lane + 32, ...)
+        constexpr int CH = 4;
 #pragma unroll 1
-        for (int i0 = 0; i0 < m; i0 += 32) {
-            const int i = i0 + lane;
-            const bool on = i < m;
-            const float *Si = S + (size_t)(on ? i : 0) * p.n_pad;
-            double r = (double)Sj[(size_t)(on ? i : 0) * p.n_pad];
+        for (int i0 = 0; i0 < m; i0 += 32 * CH) {
+            const float *Si[CH];
+            double r[CH], yv[CH];
+            bool on[CH];
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+                const int i = i0 + 32 * c + lane;
+                on[c] = i < m;
+                const size_t row = (size_t)(on[c] ? i : 0) * p.n_pad;
+                Si[c] = S + row;
+                r[c] = (double)Sj[row];
+                yv[c] = !on[c] ? 0.0 : p.y_f64 ? ((const double *)p.y)[r_vox * m + i] : (double)((const float *)p.y)[r_vox * m + i];
+            }
 #pragma unroll 1
             for (int a = 0; a < r_np; a += 2) {
                 const int a1 = min(a + 1, r_np - 1);
-                const float s0 = Si[atom_of_thread(a, st)], s1 = Si[atom_of_thread(a1, st)];
+                const int at0 = atom_of_thread(a, st), at1 = atom_of_thread(a1, st);
                 const double b0 = ws.bs[a][st], b1 = (a + 1 < r_np) ? ws.bs[a1][st] : 0.0;
-                r = fma(-(double)s0, b0, r);
-                r = fma(-(double)s1, b1, r);
+                float s0[CH], s1[CH];
+#pragma unroll
+                for (int c = 0; c < CH; ++c) { s0[c] = Si[c][at0]; s1[c] = Si[c][at1]; }
+#pragma unroll
+                for (int c = 0; c < CH; ++c) {
+                    r[c] = fma(-(double)s0[c], b0, r[c]);
+                    r[c] = fma(-(double)s1[c], b1, r[c]);
+                }
             }
-            if (on) {
-                const double yi = p.y_f64 ? ((const double *)p.y)[r_vox * m + i] : (double)((const float *)p.y)[r_vox * m + i];
-                a2 = fma(r, r, a2);
-                ay = fma(r, yi, ay);
-            }
+#pragma unroll
+            for (int c = 0; c < CH; ++c)
+                if (on[c]) {
+                    a2 = fma(r[c], r[c], a2);
+                    ay = fma(r[c], yv[c], ay);
+                }
         }
         a2 = warp_sum(a2);
         ay = warp_sum(ay);
@@ -1301,17 +1328,29 @@ __global__ void __launch_bounds__(TPV_THREADS, 4) k_noddi_stage3_tpv(const FitPa
                         prow[k] = on ? atom_of(k) * ldT : 0;
                         xk[k] = on ? ws.xs[k][tid] : 0.0;
                     }
-                    for (unsigned mm = valid; mm; mm &= mm - 1) {
-                        const int a = __ffs(mm) - 1, atom = sa[a][tid];
-                        const double *Ta = T + atom;
-                        double w = cg[atom];
-                        double gk[CAPT];
+                    for (unsigned mm = valid; mm;) {  // two atoms per trip: both atoms' Gram entries in flight together
+                        const int a0 = __ffs(mm) - 1;
+                        mm &= mm - 1;
+                        const bool two = mm != 0u;
+                        const int a1 = two ? __ffs(mm) - 1 : a0;
+                        mm &= mm - 1;
+                        const int atom0 = sa[a0][tid], atom1 = sa[a1][tid];
+                        const double *T0 = T + atom0, *T1p = T + atom1;
+                        double w0 = cg[atom0], w1 = cg[atom1];
+                        double g0[CAPT], g1[CAPT];
 #pragma unroll
-                        for (int k = 0; k < CAPT; ++k) gk[k] = (k < np) ? Ta[prow[k]] : 0.0;
+                        for (int k = 0; k < CAPT; ++k) {
+                            g0[k] = (k < np) ? T0[prow[k]] : 0.0;
+                            g1[k] = (k < np) ? T1p[prow[k]] : 0.0;
+                        }
 #pragma unroll
                         for (int k = 0; k < CAPT; ++k)
-                            if (k < np) w = fma(-gk[k], xk[k], w);
-                        if (w > bv) { bv = w; j = a; }
+                            if (k < np) {
+                                w0 = fma(-g0[k], xk[k], w0);
+                                w1 = fma(-g1[k], xk[k], w1);
+                            }
+                        if (w0 > bv) { bv = w0; j = a0; }
+                        if (two && w1 > bv) { bv = w1; j = a1; }
                     }
                     if (j < 0) { pend = false; run = false; }
                 }

@@ -665,12 +665,16 @@ __device__ __noinline__ int warp_lars_fast(const double *__restrict__ T, int ldT
         // largest step before an active coefficient crosses zero (last index wins ties)
         double step_max = INFINITY;
         int fz = -1;
-        if (lane <= i) {
-            double r = -coef_l / ul;
-            if (r > 0.0) { step_max = r; fz = lane; }
+        // r = -coef / u is positive only for a positive coefficient that decreases (u < 0): most steps have none, and the fp64
+        // division is a ~30-instruction subroutine the whole warp would walk through -- skip it (and the arg-min) then
+        if (__any_sync(FULL, lane <= i && coef_l > 0.0 && ul < 0.0)) {
+            if (lane <= i) {
+                double r = -coef_l / ul;
+                if (r > 0.0) { step_max = r; fz = lane; }
+            }
+            warp_argmin<false>(step_max, fz);
+            if (fz < 0) step_max = INFINITY;
         }
-        warp_argmin<false>(step_max, fz);
-        if (fz < 0) step_max = INFINITY;
         const double cc = fabs(shfl(dl, 0));
         // correlation slopes T[:, S] u; rows are L2-resident: fetch GD rows at a time
         double sl[NPL];

@@ -1,7 +1,9 @@
 set -x
-timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
-bash tools/bench_sweep.sh "AMX_LEAN2=1" 2>&1 | tail -1
-timeout 300 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --no-pipeline --no-configs 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('checksum', repr(d['maps_checksum']))"
-python tools/bench_models.py 1048576 2>&1 | tail -3; python -c "
-import json; d=json.load(open('gpurun_out/bench_models.json'))
-for k,v in d.items(): print(k, round(v['voxels_per_s']/1e6,1))"
+bash tools/bench_sweep.sh "AMX_LEAN2=1" 2>&1 | grep -v "^=="
+timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --no-e2e --no-pipeline --no-configs 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('checksum', repr(d['maps_checksum']), d['roofline']['kernel_ms_per_launch'], d['roofline']['frac'])"
+timeout 300 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:k_noddi_stage -c 3 --csv --log-file gpurun_out/h22.csv python bench.py --steps 1 --warmup 1 --no-cpu --no-e2e --no-pipeline --no-configs > /dev/null 2>&1
+python - <<'P'
+import csv
+for r in csv.reader(open('gpurun_out/h22.csv')):
+    if len(r)>10 and r[0].isdigit(): print(r[4][:50], r[-3], r[-1])
+P
