@@ -557,7 +557,7 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
     }
     // Stages 2 and 3: more resident warps hide more of the L2 latency of the Gram rows as long as registers (64K / threads)
     // and shared memory (workspace x warps <= 227 KB) allow; the 1024-thread builds spill ~150 bytes.
-    const int w2 = env_int("AMX_STAGE2_WARPS", 28), w3 = env_int("AMX_STAGE3_WARPS", 24);
+    const int w2 = env_int("AMX_STAGE2_WARPS", 32), w3 = env_int("AMX_STAGE3_WARPS", 24);
     auto launch_wide = [&](auto kern, int warps, unsigned ws_doubles) -> int {
         const size_t sw = fixed + (size_t)ws_doubles * 8 * warps;
         CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sw));
@@ -586,7 +586,7 @@ int launch_noddi_split_t(const FitParams &p, int grid, int block, size_t smem, c
             return AMX_OK;
         };
         // AMX_TPV3_CAP = 3: test hook, most voxels outgrow the per-thread capacity and take the hand-back path
-        const int cap3 = env_int("AMX_TPV3_CAP", 6);
+        const int cap3 = env_int("AMX_TPV3_CAP", 5);
         if (int rc3 = cap3 <= 3   ? launch_t3(k_noddi_stage3_tpv<NPL, 3>, tpv3_smem_bytes<3>())
                       : cap3 == 5 ? launch_t3(k_noddi_stage3_tpv<NPL, 5>, tpv3_smem_bytes<5>())
                                   : launch_t3(k_noddi_stage3_tpv<NPL, 6>, tpv3_smem_bytes<6>()))

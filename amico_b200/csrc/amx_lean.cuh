@@ -96,12 +96,8 @@ __device__ __forceinline__ int nnls_lean(const double *__restrict__ T, const int
                 if (lane > k && lane < np) t = fma(-myrow[k], vk, t);
             }
             v = (lane < np) ? t * rdl : 0.0;
-            double vv = v * v, vz = v * zl;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                vv += shfl2_xor(vv, o);
-                vz += shfl2_xor(vz, o);
-            }
+            double vv = v * v, vz = v * zl;  // both 0 beyond np
+            if (np > 0) warp_sum2_upto(vv, vz, np);
             d2 = hjj - vv;
             znum = cj - vz;
             if (use_as && np > 0 && d2 < 1e-10 * hjj) {
@@ -785,11 +781,7 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
                     u[lane] = ur;
                 }
                 double dot = lane < i ? ur * g : 0.0, usum = lane < i ? ur : 0.0;  // two interleaved butterfly sums
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    dot += shfl2_xor(dot, o);
-                    usum += shfl2_xor(usum, o);
-                }
+                warp_sum2_upto(dot, usum, i);
                 const double schur = 1.0 / (shfl2(g, i) - dot);
                 // row sums of the inverse after the Schur update: old rows += schur u_r (sum(u) - 1), new row = schur (1 - sum(u))
                 if (lane < i) rs_l = fma(schur * ur, usum - 1.0, rs_l);
@@ -896,11 +888,7 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
         double step = step0;
         cur = bk;
         double coeff1 = lane <= i ? sg * ul : 0.0, coeff2 = lane <= i ? dl * ul : 0.0;  // two interleaved butterfly sums
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            coeff1 += shfl2_xor(coeff1, o);
-            coeff2 += shfl2_xor(coeff2, o);
-        }
+        warp_sum2_upto(coeff1, coeff2, i + 1);
         const double step_max2 = cc - lambda1;
         step = fmin(fmin(step, step_max2), step_max);
         if (step == INFINITY) break;

@@ -32,6 +32,28 @@ __device__ __forceinline__ double shfl_xor(double v, int m)
     return __hiloint2double(hi, lo);
 }
 
+// Two interleaved butterfly sums of values that are zero on the lanes >= cnt (warp-uniform cnt): the 32-lane tree
+// (offsets 16, 8, 4, 2, 1) adds zeros in its upper levels, so for cnt <= 8 the three lower levels on lanes 0..7 plus one
+// broadcast give the bit-identical result for fewer shuffles.  All lanes receive the sums.
+__device__ __forceinline__ void warp_sum2_upto(double &a, double &b, int cnt)
+{
+    if (cnt <= 8) {
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += shfl_xor(a, o);
+            b += shfl_xor(b, o);
+        }
+        a = shfl(a, 0);
+        b = shfl(b, 0);
+    } else {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += shfl_xor(a, o);
+            b += shfl_xor(b, o);
+        }
+    }
+}
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll

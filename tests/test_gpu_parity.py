@@ -463,7 +463,7 @@ def test_noddi_kernel_variants_agree(monkeypatch, env):
     assert pass_fraction(alt["estimates_mod"], base["estimates_mod"]) >= 0.999
 
 
-@pytest.mark.parametrize("env", [{"AMX_TPV3": "0"}, {"AMX_LEAN1": "0", "AMX_LEAN2": "0"}, {"AMX_TPV3_CAP": "3"}, {"AMX_TPV1": "1"},
+@pytest.mark.parametrize("env", [{"AMX_TPV3": "0"}, {"AMX_LEAN1": "0", "AMX_LEAN2": "0"}, {"AMX_TPV3_CAP": "3"}, {"AMX_TPV3_CAP": "6", "AMX_STAGE2_WARPS": "28"}, {"AMX_TPV1": "1"},
                                  {"AMX_TPV1": "1", "AMX_TPV1_CAP": "6"}, {"AMX_PAIR1": "1"}])
 def test_noddi_second_generation_kernels_are_bit_identical(monkeypatch, env):
     """The second-generation stage kernels (amx_lean.cuh: inlined lean solvers for stages 1 / 2, one voxel per thread for stage 3 --

@@ -63,7 +63,7 @@ for k, c in kern.items():
     d.update({w: c[w] for w in WATCH if c[w]})
     d.update(usage.get(k, {}))
     out.append(d)
-want = ("k_noddi_stage1_lean<5, 1024, 16>", "k_noddi_stage2_lean<5, 896>", "k_noddi_stage3_tpv<5, 6>", "k_noddi_stage<3, 5, float, 768>", "k_lasso_batched<2, 1, float, 1024>",
+want = ("k_noddi_stage1_lean<5, 1024, 16>", "k_noddi_stage2_lean<5, 1024>", "k_noddi_stage3_tpv<5, 5>", "k_noddi_stage<3, 5, float, 768>", "k_lasso_batched<2, 1, float, 1024>",
         "k_lasso_batched<1, 1, float, 1024>", "k_lasso_batched<3, 1, double, 1024>", "k_fit<2, 1, float>", "k_noddi_exact<5, float>", "k_preprocess",
         "k_dti", "k_gram<float>", "k_lut")
 head = [d for d in out if any(w.replace(" ", "") in d["kernel"].replace("(int)", "").replace(" ", "") for w in want)]
