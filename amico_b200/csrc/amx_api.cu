@@ -1154,11 +1154,6 @@ int amx_fit(amx_plan *pl, const amx_fit_args *a, int64_t *err_voxel)
     long long h_status[2][8] = {{0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}, {0, (long long)1 << 62, 0, 0, 0, 0, 0, 0}};
     for (int b = 0; b < ncs; ++b) CK(cudaMemcpyAsync(h_status[b], pl->work[b].status.p, sizeof h_status[b], cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (env_int("AMX_DEBUG_TOTALS", 0) && pl->work[0].bins.p) {  // diagnostics: tile count, binned voxels and the three queue heads of work set 0
-        int h_tot[6] = {0, 0, 0, 0, 0, 0};
-        cudaMemcpy(h_tot, (int *)pl->work[0].bins.p + 4 * pl->ndirs, sizeof h_tot, cudaMemcpyDeviceToHost);
-        for (int k = 0; k < 6; ++k) pl->last_cnt[10 + k] = h_tot[k];
-    }
     {   // pageable outputs: pinned landing buffers -> the caller's arrays
         double *user[4] = {a->estimates, a->dirs, a->rmse, a->nrmse};
         const size_t bytes[4] = {n * nm * sizeof(double), n * 3 * sizeof(double), n * sizeof(double), n * sizeof(double)};

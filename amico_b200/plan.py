@@ -220,5 +220,4 @@ class Plan:
         out = (C.c_int64 * 16)()
         L.check(L.load().amx_plan_last_counters(self._h, out, 16))
         return {"launches": out[0], "tiles": out[1], "overflow_voxels": out[2], "smem_bytes": out[3], "warps_per_cta": out[4],
-                "tma_staged": bool(out[5]), "slow_path_voxels": out[6], "grid": out[7], "exact_path_voxels": out[8],
-                **({"debug_totals": [int(out[k]) for k in range(10, 16)]} if os.environ.get("AMX_DEBUG_TOTALS") else {})}
+                "tma_staged": bool(out[5]), "slow_path_voxels": out[6], "grid": out[7], "exact_path_voxels": out[8]}

@@ -1,3 +1,3 @@
-# scratch command list for gpurun calls; the round-2 measurement pass is tools/profile_r02.sh
-bash tools/profile_r02.sh
-python -c "import __graft_entry__ as g; g.smoke()"
+set -x
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/bench_r02_2gpu.json 2> gpurun_out/bench_r02_2gpu.err; tail -2 gpurun_out/bench_r02_2gpu.err
