@@ -90,10 +90,20 @@ __device__ __forceinline__ int nnls_lean(const double *__restrict__ T, const int
             const double *Tj = Tl + (j * ldT - lane);  // = T + j ldT, from the pointer that is held in registers
             double t = (lane < np) ? Tj[myP] : 0.0;  // = T[P[lane]][j] (the table is exactly symmetric)
             const double hjj = Tj[j], cj = cs[j];
+            {   // v = L^-1 t (forward substitution, lane a owns row a); two steps per trip: half the loop / convergence-check overhead
+                const bool mine = lane < np;
+                int k = 0;
 #pragma unroll 1
-            for (int k = 0; k < np; ++k) {  // v = L^-1 t (forward substitution, lane a owns row a)
-                const double vk = shfl2(t * rdl, k);
-                if (lane > k && lane < np) t = fma(-myrow[k], vk, t);
+                for (; k + 2 <= np; k += 2) {
+                    const double v0 = shfl2(t * rdl, k);
+                    if (mine && lane > k) t = fma(-myrow[k], v0, t);
+                    const double v1 = shfl2(t * rdl, k + 1);
+                    if (mine && lane > k + 1) t = fma(-myrow[k + 1], v1, t);
+                }
+                if (k < np) {
+                    const double v0 = shfl2(t * rdl, k);
+                    if (mine && lane > k) t = fma(-myrow[k], v0, t);
+                }
             }
             v = (lane < np) ? t * rdl : 0.0;
             double vv = v * v, vz = v * zl;  // both 0 beyond np
@@ -167,11 +177,15 @@ __device__ __forceinline__ int nnls_lean(const double *__restrict__ T, const int
             {   // s = L^-T z (back substitution, lane a owns column a)
                 s = (lane < np) ? zl : 0.0;
                 const double *col = Lp + tri(np - 1, 0) + lane;  // element (k, lane) of row k, walking up
+                int k = np - 1;
 #pragma unroll 1
-                for (int k = np - 1; k >= 0; --k) {
-                    const double sk = shfl2(s * rdl, k);
-                    if (lane < k) s = fma(-*col, sk, s);
+                for (; k >= 1; k -= 2) {  // two steps per trip (step 0 updates no lane)
+                    const double s0 = shfl2(s * rdl, k);
+                    if (lane < k) s = fma(-*col, s0, s);
                     col -= k;
+                    const double s1 = shfl2(s * rdl, k - 1);
+                    if (lane < k - 1) s = fma(-*col, s1, s);
+                    col -= k - 1;
                 }
                 s = (lane < np) ? s * rdl : 0.0;
             }
