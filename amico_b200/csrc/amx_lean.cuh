@@ -714,13 +714,16 @@ __device__ __forceinline__ double sym_row_dot_lean(const double *Mi, const int r
     double acc = 0.0;
     const double *prow = Mi + tri(r, 0);  // (r, c), c < r
     const double *pcol = Mi + r;          // (c, r), c >= r: at tri(c, 0) + r
-    int step = 1;
+    int c = 0;
 #pragma unroll 1
-    for (int c = 0; c < n; ++c) {
+    for (; c + 2 <= n; c += 2) {  // two terms per trip; (c, r) sits c + 1 packed entries after (c - 1, r)
         acc = fma(*(c < r ? prow : pcol), v[c], acc);
-        ++prow;
-        pcol += step++;
+        pcol += c + 1;
+        acc = fma(*(c + 1 < r ? prow + 1 : pcol), v[c + 1], acc);
+        pcol += c + 2;
+        prow += 2;
     }
+    if (c < n) acc = fma(*(c < r ? prow : pcol), v[c], acc);
     return acc;
 }
 
@@ -804,8 +807,14 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
                 if (lane < i) {
                     const double su = schur * ur;
                     double *mp = Mi + tri(lane, lane);  // element (k, lane), k = lane..: the packed index grows by k + 1 per row
+                    int k = lane;
 #pragma unroll 1
-                    for (int k = lane; k < i; ++k) {
+                    for (; k + 2 <= i; k += 2) {  // two rows per trip
+                        mp[0] = fma(su, u[k], mp[0]);
+                        mp[k + 1] = fma(su, u[k + 1], mp[k + 1]);
+                        mp += 2 * k + 3;
+                    }
+                    if (k < i) {
                         *mp = fma(su, u[k], *mp);
                         mp += k + 1;
                     }
