@@ -112,6 +112,27 @@ def fp64_peaks(device):
     return out
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Multi-rank runs: pin this process (and the pinned host buffers it first-touches afterwards) to the CPUs NVML reports as
+    local to its GPU, so that eight ranks do not stream their H2D traffic out of one NUMA node.  Best effort: returns the CPU
+    list, or None when NVML / the affinity call is unavailable or the GPU reports every CPU (one node: nothing to gain)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < ncpu]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus or len(cpus) >= len(allowed):
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
 
@@ -444,6 +465,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: amico_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 and os.environ.get("AMX_BENCH_BIND", "1") != "0" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -581,6 +603,7 @@ def main():
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload(args.cfg, n_vox, world),
             "clocks": clocks, "gpu_launches": int(launches),
+            "host_cpu_binding": ("GPU-local CPUs %d-%d (%d)" % (numa[0], numa[-1], len(numa))) if numa else "none (single rank, one NUMA node, or NVML unavailable)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(n_vox), "kernel": fit_kernel_name, "kernel_ms_per_launch": 1e3 * k_s,
                          "bytes_per_voxel": B, "compulsory_bytes_per_voxel": B0,

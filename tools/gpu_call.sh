@@ -1,3 +1,2 @@
 # scratch command list for gpurun calls; the round-2 measurement pass is tools/profile_r02.sh
 bash tools/profile_r02.sh
-python -c "import __graft_entry__ as g; g.smoke()"
