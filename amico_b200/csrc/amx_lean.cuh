@@ -892,21 +892,21 @@ __device__ __forceinline__ int lars_lean(const double *__restrict__ T, const int
         // first inactive atom reaching the common correlation: entry of smallest magnitude, lowest index.  Each lane first
         // picks the best of its own atoms by cross-multiplication (|a/b| < |c/d| <=> |a| d < |c| b for b, d > 0), so only one
         // reciprocal per lane and step is needed.
-        double bnum = 0.0, bden = 0.0;  // best candidate of this lane: step = bnum / bden (bden > 0), none while bden == 0
-        int mk = lane < K ? lane : -1;  // its atom; lanes without a candidate still offer their lowest atom (step = inf)
+        double bnum = INFINITY, bden = 1.0;  // best candidate of this lane: step = bnum / bden (bden > 0); inf / 1 while there is none
+        int mk = lane < K ? lane : -1;       // its atom; lanes without a candidate still offer their lowest atom (step = inf)
         const unsigned open_ = kin & ~act;  // bit s: atom lane + 32 s exists and is not active
 #pragma unroll
         for (int s = 0; s < NPL; ++s) {
             if (((open_ >> s) & 1u) && sl[s] < 1.0) {
                 const int k = lane + 32 * s;
                 const double num = cc - DtR[k], den = 1.0 - sl[s];
-                if (bden == 0.0 || fabs(num) * bden < fabs(bnum) * den) { bnum = num; bden = den; mk = k; }
+                if (fabs(num) * bden < fabs(bnum) * den) { bnum = num; bden = den; mk = k; }  // (the first candidate beats inf / 1)
             }
         }
-        const double mine = bden != 0.0 ? bnum * __drcp_rn(bden) : INFINITY;
+        const double mine = bnum * __drcp_rn(bden);
         double bt = fabs(mine);
         int bk = mk;
-        warp_argmin<true>(bt, bk);
+        warp_argmin_nonneg(bt, bk);
         const double step0 = shfl2(mine, bk & 31);  // lane (bk & 31) owns atom bk and offered exactly it
         double step = step0;
         cur = bk;

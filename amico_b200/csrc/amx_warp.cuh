@@ -96,6 +96,19 @@ __device__ __forceinline__ void warp_argmax(double &v, int &idx) { warp_argext<t
 template <bool LOWEST>
 __device__ __forceinline__ void warp_argmin(double &v, int &idx) { warp_argext<false, LOWEST>(v, idx); }
 
+// arg-min over NON-NEGATIVE values (+inf included): their bit patterns order like unsigned integers, so the order-preserving key
+// of warp_argext is not needed.  Lanes with idx < 0 do not take part; ties -> lowest index; idx < 0 when no lane took part.
+__device__ __forceinline__ void warp_argmin_nonneg(double &v, int &idx)
+{
+    const unsigned hi = idx >= 0 ? (unsigned)__double2hiint(v) : 0xffffffffu, lo = idx >= 0 ? (unsigned)__double2loint(v) : 0xffffffffu;
+    const unsigned hm = __reduce_min_sync(FULL, hi);
+    const unsigned lm = __reduce_min_sync(FULL, hi == hm ? lo : 0xffffffffu);
+    const bool win = idx >= 0 && hi == hm && lo == lm;
+    const int widx = __reduce_min_sync(FULL, win ? idx : 0x7fffffff);
+    v = __hiloint2double((int)hm, (int)lm);
+    idx = widx == 0x7fffffff ? -1 : widx;
+}
+
 // streaming loads that do not allocate in L1 (the dictionary slab and the signal pass through once per batch;
 // L1 is kept for the Gram rows the solvers re-read)
 __device__ __forceinline__ float ld_stream(const float *p)
